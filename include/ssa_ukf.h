@@ -1,0 +1,157 @@
+/* ssa_ukf.h — C ABI of libssa_ukf.so: the B200 (sm_100a) implementation of ssa-gym's per-step
+ * estimation hot path (UKF predict/update over every resident space object of every environment).
+ *
+ * This is the drop-in boundary.  Everything above it (gym.Env reset/step, RNG, failure messages,
+ * histories) stays Python; everything below is CUDA.  No torch types, only plain pointers/sizes.
+ * Every entry point returns 0 on success or a negative SSA_E* code; nothing throws.  All calls on
+ * one handle must come from one host thread; work is enqueued on the given CUDA stream and is
+ * asynchronous unless the function name says download/sync.
+ *
+ * Reference interfaces replaced (file:line in the read-only upstream AshHarvey/ssa-gym):
+ *   ssa_ukf_create        envs/ssa_tasker_simple_2.py:72-184  (__init__: dt, Q, R, observer, sigma-point
+ *                         parameters; filterpy MerweScaledSigmaPoints weights) and :211-218 (UKF objects)
+ *   ssa_ukf_reset         envs/ssa_tasker_simple_2.py:193-241 (reset: x_true[0], x_filter[0], P_0)
+ *   ssa_ukf_predict       envs/ssa_tasker_simple_2.py:265-287 (truth fx loop + filters[j].predict())
+ *                         -> filterpy UKF.predict -> envs/farnocchia.py:1053 fx, envs/dynamics.py:402 msqrt
+ *   ssa_ukf_update        envs/ssa_tasker_simple_2.py:292-315 (hx, visibility gate, filters[a].update(z))
+ *                         -> filterpy UKF.update -> envs/dynamics.py:219 hx, :342 mean_z, :260 residual_z
+ *   ssa_ukf_step          the whole of step(): SS2:243-367, fused (truth + predict + update + obs/error)
+ *   ssa_ukf_env_reduce    SS2:324-354 (reward / done), agents.py:7-9,35-42,66-81 (greedy taskers),
+ *                         SS2:410-425 (visible_objects)
+ *   ssa_ukf_scores        envs/reward.py:6-50
+ *   ssa_ukf_download      the numpy arrays the reference env exposes: x_true, x_filter, P_filter, obs,
+ *                         delta_pos, delta_vel, sigma_pos, sigma_vel, y, S, sigmas_h  (SS2:132-161)
+ */
+#ifndef SSA_UKF_H
+#define SSA_UKF_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSA_UKF_ABI_VERSION 1
+
+/* error codes */
+#define SSA_OK 0
+#define SSA_EINVAL (-1)  /* bad argument */
+#define SSA_ECUDA (-2)   /* CUDA runtime error; ssa_ukf_last_error() has the text */
+#define SSA_ENOMEM (-3)
+#define SSA_ENODEV (-4)  /* no CUDA device: there is no CPU fallback */
+
+/* obs_type (SS2:100-107) */
+#define SSA_OBS_AER 0
+#define SSA_OBS_XYZ 1
+/* reward_type (SS2:324-351) */
+#define SSA_REWARD_JONES 0
+#define SSA_REWARD_TRINARY 1
+#define SSA_REWARD_SHAPED 2
+
+/* Per-object status word (int32), also in ssa_gym_b200/csrc/ssa_ukf_core.h */
+#define SSA_STATUS_FAILED 0x1
+#define SSA_STATUS_LINALG 0x2
+#define SSA_STATUS_NAN 0x4
+#define SSA_STATUS_FXEXC 0x8
+#define SSA_STATUS_TRUTHEXC 0x10
+#define SSA_STATUS_IN_UPDATE 0x20
+
+typedef struct ssa_ukf_cfg {
+  int32_t abi_version;             /* SSA_UKF_ABI_VERSION */
+  int32_t n_objects;               /* N = n_envs * m */
+  int32_t n_envs;                  /* E; 1 for the drop-in env, N objects form E groups of m */
+  int32_t m;                       /* rso_count: objects per environment */
+  int32_t obs_type;                /* SSA_OBS_* */
+  int32_t resample_after_predict;  /* 1: filterpy >= 1.4.5 predict() re-draws sigmas_f from the prior */
+  int32_t reward_type;             /* SSA_REWARD_* (used by ssa_ukf_env_reduce) */
+  int32_t n_steps;                 /* n: episode length (done when i+1 >= n) */
+  double dt;                       /* time_step [s] */
+  double lam_plus_n;               /* (lambda + n) of MerweScaledSigmaPoints */
+  double Wm[13];                   /* mean weights, computed on the host with filterpy's expressions */
+  double Wc[13];                   /* covariance weights */
+  double Q[36];                    /* process noise, row-major 6x6 (Q_discrete_white_noise, SS2:110) */
+  double R[9];                     /* measurement noise, row-major 3x3, added element-wise to S */
+  double obs_itrs[3];              /* observer ECEF [m] (lla2ecef(obs_lla), SS2:94) */
+  double T[9];                     /* trans_uvw_ecef(lat,lon), row-major (transformations.py:341-343) */
+  double obs_limit;                /* elevation mask [rad] (SS2:85) */
+} ssa_ukf_cfg;
+
+typedef struct ssa_ukf ssa_ukf; /* opaque handle, owns all device buffers */
+
+/* fields for ssa_ukf_download / ssa_ukf_upload / ssa_ukf_device_ptr.
+ * Host layouts are the reference's numpy layouts (row-major):
+ *   X_TRUE, X_FILTER  double[N][6]       P_FILTER double[N][6][6] (symmetric, mirrored from the packed upper)
+ *   OBS               double[N][12] = [x(6), diag P(6)]  (results.py:60-72)
+ *   DELTA_POS/VEL, SIGMA_POS/VEL, TRACE   double[N]      (results.py:36-47; np.trace)
+ *   Z_TRUE, Y, Z_NOISE double[N][3]      S double[N][3][3]   SIGMAS_H double[N][13][3]
+ *   VISIBLE uint8[N] (SS2:418-425)       STATUS int32[N]     INFLATIONS int32[N]
+ *   ACTIONS int32[E]  REWARD double[E]  DONE uint8[E]  GREEDY int32[E][SSA_N_TASKERS]
+ * Device layouts are struct-of-arrays with leading dimension ssa_ukf_ld(h).        */
+enum ssa_field {
+  SSA_F_X_TRUE = 0, SSA_F_X_FILTER = 1, SSA_F_P_FILTER = 2, SSA_F_OBS = 3,
+  SSA_F_DELTA_POS = 4, SSA_F_DELTA_VEL = 5, SSA_F_SIGMA_POS = 6, SSA_F_SIGMA_VEL = 7, SSA_F_TRACE = 8,
+  SSA_F_Z_TRUE = 9, SSA_F_Y = 10, SSA_F_S = 11, SSA_F_SIGMAS_H = 12, SSA_F_Z_NOISE = 13,
+  SSA_F_VISIBLE = 14, SSA_F_STATUS = 15, SSA_F_INFLATIONS = 16,
+  SSA_F_ACTIONS = 17, SSA_F_REWARD = 18, SSA_F_DONE = 19, SSA_F_GREEDY = 20, SSA_F_SCORES = 21,
+  SSA_F_UPDATED = 22, SSA_F_COUNT_
+};
+
+/* heuristic taskers evaluated on the device by ssa_ukf_env_reduce (agents.py) */
+#define SSA_TASKER_NAIVE_GREEDY 0     /* argmax trace P over all objects           agents.py:7-9   */
+#define SSA_TASKER_VISIBLE_GREEDY 1   /* argmax trace P over visible objects       agents.py:35-42 */
+#define SSA_TASKER_POS_ERROR_GREEDY 2 /* argmax delta_pos over visible objects     agents.py:66-72 */
+#define SSA_TASKER_VEL_ERROR_GREEDY 3 /* argmax delta_vel over visible objects     agents.py:75-81 */
+#define SSA_N_TASKERS 4
+/* a visible-* tasker returns -1 when the reference would fall back to action_space.sample()
+ * (`not np.any(visible)` — also true when the only visible index is 0, agents.py:37).            */
+
+/* flags for ssa_ukf_step */
+#define SSA_STEP_TRUTH 0x1        /* propagate the true states (SS2:265-266) */
+#define SSA_STEP_PREDICT 0x2      /* UKF predict on every non-failed object (SS2:271-287) */
+#define SSA_STEP_UPDATE_ALL 0x4   /* catalog mode: update every object with its z_noise */
+#define SSA_STEP_UPDATE_ACT 0x8   /* RL mode: update object actions[e] of each env e (SS2:292-315) */
+#define SSA_STEP_EPILOGUE 0x10    /* obs / error / trace / visibility (SS2:320-322, 410-425) */
+
+int ssa_ukf_abi_version(void);
+const char* ssa_ukf_last_error(void);
+int ssa_ukf_device_count(void);
+
+int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out);
+int ssa_ukf_destroy(ssa_ukf* h);
+long ssa_ukf_ld(const ssa_ukf* h); /* leading dimension (padded N) of the device SoA arrays */
+
+/* reset(): host arrays in reference layout. P0 is one 6x6 (p0_per_object = 0) or N of them.     */
+int ssa_ukf_reset(ssa_ukf* h, const double* x_true, const double* x_filter, const double* P0,
+                  int p0_per_object, void* stream);
+
+/* per-step host inputs: actions int32[E] and/or z_noise double[N][3] (SS2:219-221 draws them at reset) */
+int ssa_ukf_upload(ssa_ukf* h, int field, const void* host, size_t bytes, void* stream);
+int ssa_ukf_download(ssa_ukf* h, int field, void* host, size_t bytes, void* stream); /* blocks until copied */
+/* raw device pointer of a field (device SoA layout) for zero-copy consumers (torch, NCCL) */
+int ssa_ukf_device_ptr(ssa_ukf* h, int field, void** dptr, size_t* bytes);
+
+/* The hot path.  M = trans_matrix[i] (row-major GCRS->ITRS).  `flags` selects the fused stages.  */
+int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream);
+/* Convenience wrappers with the reference's call structure */
+int ssa_ukf_predict(ssa_ukf* h, void* stream);                      /* truth + predict              */
+int ssa_ukf_update(ssa_ukf* h, const double M[9], int all, void* stream); /* update (all | actions[e]) + epilogue */
+
+/* per-environment reductions: reward / done (SS2:324-354) and the greedy taskers (agents.py).
+ * step_index = i after the increment of SS2:259; prev_sigma_argmax is kept on the device for 'shaped'. */
+int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stream);
+/* reward.py score terms from the current covariances: out double[N][6] =
+ * [score_scaled_trace_P, score_trace_P, score_scaled_det_P(dt), score_det_P, score_det_pos_P, |dpos|] */
+int ssa_ukf_scores(ssa_ukf* h, void* stream);
+
+int ssa_ukf_sync(ssa_ukf* h, void* stream);
+/* number of kernel launches issued through this handle so far (bench.py `gpu_launches`) */
+long ssa_ukf_launch_count(const ssa_ukf* h);
+
+/* FP64 pipe microbenchmark (dependent DFMA chains on every SM) used as the roofline denominator:
+ * returns achieved TFLOP/s (2 flop per DFMA), timed with CUDA events on `stream`.                  */
+int ssa_ukf_fp64_peak(int device, void* stream, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSA_UKF_H */

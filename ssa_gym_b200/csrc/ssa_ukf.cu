@@ -1,0 +1,948 @@
+// ssa_ukf.cu — sm_100a kernels and the C ABI (include/ssa_ukf.h) of the UKF hot path.
+//
+// Mapping: one object per 16-lane TEAM, two teams per warp, eight teams per
+// 128-thread CTA.  Lanes 0..12 of a team own the 13 sigma points, lane 13 owns the TRUE state,
+// lanes 14/15 shadow lane 13 (no divergence, no stores).  The propagation `fx` and the measurement
+// `hx` — >85 % of the fp64 work — therefore run with 14 of 16 lanes doing distinct useful work.  The
+// small linear algebra between them is spread over the lanes element by element through a 1.7 KB
+// shared-memory workspace per team (sigma set, deviations, cross terms); Cholesky and the 3x3
+// inverse are evaluated redundantly by every lane in registers (a redundant lane costs no issue
+// slots).  Reductions over the 13 sigma points are sequential k = 0..12 FMAs read from shared memory,
+// i.e. in a FIXED order, so the result is bit-identical to the host twin (tests/twin/twin.cpp).
+//
+// HBM layout: struct-of-arrays fp64, leading dimension ld = N rounded up to 32:
+//   xt[6][ld]  x[6][ld]  P[21][ld] (packed upper triangle)  + per-object scalars [ld]
+// AoS only where the reference's own array layout is the interface (obs[N][12], z_noise[N][3], ...).
+//
+// No tensor cores: nothing here is a dense contraction (13-term sums of 6x6 outer products).
+// No libdevice transcendental, no implicit FMA contraction (compiled with -fmad=false, every FMA is
+// explicit in the shared headers).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/ssa_ukf.h"
+#include "ssa_math.h"
+#include "ssa_meas.h"
+#include "ssa_orbit.h"
+#include "ssa_ukf_core.h"
+
+namespace {
+
+constexpr int kTeam = 16;
+constexpr int kTeamsPerCta = 8;
+constexpr int kCtaThreads = kTeam * kTeamsPerCta;  // 128
+// Per-team shared workspace, in doubles.  The stride is 16 (mod 32) 4-byte banks so that the two
+// teams of a warp touch disjoint bank halves when they read the same logical element.
+constexpr int WS_SG = 0;     // [13][6] propagated sigmas -> deviations -> dx
+constexpr int WS_ZZ = 78;    // [13][3] uvw -> measurement residuals
+constexpr int WS_XB = 117;   // [6] current filter mean
+constexpr int WS_PN = 123;   // [21] current packed covariance
+constexpr int WS_XT = 144;   // [6] current true state
+constexpr int WS_ZM = 150;   // [3] uvw mean
+constexpr int WS_SS = 153;   // [9] innovation covariance
+constexpr int WS_PX = 162;   // [18] cross covariance
+constexpr int WS_KK = 180;   // [18] gain
+constexpr int WS_TT = 198;   // [18] S K^T
+constexpr int kWsStride = 216;  // 432 words == 16 (mod 32)
+static_assert(WS_TT + 18 <= kWsStride, "workspace overflow");
+static_assert((kWsStride * 2) % 32 == 16, "team stride must be 16 banks (mod 32)");
+
+__constant__ unsigned char c_pi[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
+__constant__ unsigned char c_pj[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+__constant__ unsigned char c_sa[6] = {0, 0, 0, 1, 1, 2};
+__constant__ unsigned char c_sb[6] = {0, 1, 2, 1, 2, 2};
+
+struct KParams {
+  // state (SoA, leading dimension ld)
+  double* xt; double* x; double* P;
+  int32_t* status; int32_t* infl;
+  // inputs
+  const int32_t* actions;  // [E]
+  const double* z_noise;   // [N][3] AoS
+  // outputs
+  double* obs;             // [N][12] AoS
+  double* dpos; double* dvel; double* spos; double* svel; double* trace;  // [ld]
+  double* z_true;          // [N][3]
+  double* y;               // [N][3]
+  double* S;               // [N][9]
+  double* sigmas_h;        // [N][39]
+  uint8_t* visible; uint8_t* updated;
+  long ld;
+  int N, m, flags, obs_type, resample;
+  double dt, lam, obs_limit;
+  double Wm[13], Wc[13];
+  const double* qr;  // device constants: packed Q (21, upper triangle) then R (9, row-major)
+  ssa_obs ob;
+};
+
+__device__ __forceinline__ void team_sync(unsigned mask) { __syncwarp(mask); }
+
+// The fused step.  Stage selection by p.flags (uniform across the grid).
+__global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) {
+  __shared__ double ws_all[kTeamsPerCta * kWsStride];
+  const int lane32 = threadIdx.x & 31;
+  const int lane = threadIdx.x & 15;
+  const unsigned tmask = 0xFFFFu << (lane32 & 16);
+  const int team = threadIdx.x >> 4;
+  const long obj = (long)blockIdx.x * kTeamsPerCta + team;
+  if (obj >= p.N) return;  // a team leaves together
+  double* ws = ws_all + team * kWsStride;
+  const int flags = p.flags;
+  const long ld = p.ld;
+  const int truth_lane = (lane32 & 16) + 13;
+
+  // ---- stage the object's state into the team workspace ---------------------------------------
+  if (lane < 6) {
+    ws[WS_XB + lane] = p.x[lane * ld + obj];
+    ws[WS_XT + lane] = p.xt[lane * ld + obj];
+  }
+  ws[WS_PN + lane] = p.P[lane * ld + obj];
+  if (lane < 5) ws[WS_PN + 16 + lane] = p.P[(16 + lane) * ld + obj];
+  int status = p.status[obj];
+  int infl_count = 0;
+  int code = 0;
+  team_sync(tmask);
+
+  double x[6], xt[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { x[i] = ws[WS_XB + i]; xt[i] = ws[WS_XT + i]; }
+
+  double sg[6];   // this lane's sigma point for the update (sigmas_f[lane])
+  double U[SSA_NP];
+  bool have_sig = false;
+
+  // ---- truth propagation + predict ----------------------------------------------------------------
+  if (flags & (SSA_STEP_TRUTH | SSA_STEP_PREDICT)) {
+    bool live = (flags & SSA_STEP_PREDICT) && !(status & SSA_ST_FAILED);
+    if (live) {
+      const int infl = ssa_robust_chol6(ws + WS_PN, 1, p.lam, U);
+      if (infl < 0) { live = false; code |= SSA_ST_LINALG; }
+      else if (infl > 0) infl_count += 1;
+    }
+    double s[6], f[6];
+    if (live && lane < 13) {
+      ssa_sigma_point(x, U, lane, s);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) s[i] = xt[i];
+    }
+    const int exc = ssa_fx(s, p.dt, f);
+    if (flags & SSA_STEP_TRUTH) {
+      if (lane == 13) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ws[WS_XT + i] = f[i];
+        if (exc) status |= SSA_ST_TRUTHEXC;
+      }
+      status = __shfl_sync(tmask, status, truth_lane);
+    }
+    if (live) {
+      if (lane < 13) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ws[WS_SG + lane * 6 + i] = f[i];
+      }
+      if (__any_sync(tmask, (lane < 13) && exc)) { live = false; code |= SSA_ST_FXEXC; }
+    }
+    team_sync(tmask);
+    if (live) {
+      // unscented transform: mean (lanes 0..5), deviations (lanes 0..12), covariance (21 elements)
+      if (lane < 6) ws[WS_XB + lane] = ssa_wmean13(ws + WS_SG, 6, lane, p.Wm);
+      team_sync(tmask);
+      int nan = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { x[i] = ws[WS_XB + i]; nan |= ssa_isnan(x[i]); }
+      if (lane < 13) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ws[WS_SG + lane * 6 + i] = f[i] - x[i];
+      }
+      team_sync(tmask);
+      {
+        const int i = c_pi[lane], j = c_pj[lane];
+        ws[WS_PN + lane] = ssa_wcov13(ws + WS_SG, 6, i, ws + WS_SG, 6, j, p.Wc) + __ldg(p.qr + lane);
+        if (lane < 5) {
+          const int i2 = c_pi[16 + lane], j2 = c_pj[16 + lane];
+          ws[WS_PN + 16 + lane] = ssa_wcov13(ws + WS_SG, 6, i2, ws + WS_SG, 6, j2, p.Wc) + __ldg(p.qr + 16 + lane);
+        }
+      }
+      team_sync(tmask);
+      if (nan) code |= SSA_ST_NAN;
+      if (p.resample) {
+        const int infl2 = ssa_robust_chol6(ws + WS_PN, 1, p.lam, U);
+        if (infl2 < 0) code |= SSA_ST_LINALG;
+        else if (infl2 > 0) infl_count += 1;
+      }
+      if (!code) {
+        if (p.resample) {
+          ssa_sigma_point(x, U, lane < 13 ? lane : 0, sg);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) sg[i] = f[i];
+        }
+        have_sig = true;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xt[i] = ws[WS_XT + i];
+  }
+
+  if (code) {  // filter_error(): sentinels (SS2:369-382)
+    status |= SSA_ST_FAILED | code;
+    if (lane < 6) ws[WS_XB + lane] = lane < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL;
+    {
+      const int i = c_pi[lane], j = c_pj[lane];
+      ws[WS_PN + lane] = (i == j) ? (i < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL) : 0.0;
+      if (lane < 5) {
+        const int i2 = c_pi[16 + lane], j2 = c_pj[16 + lane];
+        ws[WS_PN + 16 + lane] = (i2 == j2) ? (i2 < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL) : 0.0;
+      }
+    }
+    team_sync(tmask);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = ws[WS_XB + i];
+    code = 0;
+  }
+
+  // ---- measurement: truth elevation (visibility) on lane 13, sigma measurements on lanes 0..12 ----
+  bool want_upd = (flags & SSA_STEP_UPDATE_ALL) != 0;
+  if (flags & SSA_STEP_UPDATE_ACT) want_upd = want_upd || (p.actions[obj / p.m] == (int)(obj % p.m));
+  const bool want_meas = want_upd || (flags & SSA_STEP_EPILOGUE);
+  int updated = 0;
+  if (want_meas) {
+    bool do_upd = want_upd && !(status & SSA_ST_FAILED);
+    if (do_upd && !have_sig) {
+      // stand-alone update: sigmas_f of filterpy after predict() are exactly sigma_points(x, P)
+      const int infl = ssa_robust_chol6(ws + WS_PN, 1, p.lam, U);
+      if (infl < 0) { do_upd = false; code |= SSA_ST_LINALG | SSA_ST_IN_UPDATE; }
+      else ssa_sigma_point(x, U, lane < 13 ? lane : 0, sg);
+    }
+    double hin[6], zk[3];
+    const bool sigma_lane = do_upd && lane < 13;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) hin[i] = sigma_lane ? sg[i] : xt[i];
+    ssa_hx_aer(hin, &p.ob, zk);
+    // broadcast the truth measurement of lane 13
+    double zt[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) zt[a] = __shfl_sync(tmask, zk[a], truth_lane);
+    const int visible = zt[1] >= p.obs_limit;  // SS2:424
+    if (lane == 13) p.visible[obj] = (uint8_t)visible;
+    if (p.obs_type == SSA_OBS_XYZ) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { zt[a] = xt[a]; zk[a] = hin[a]; }
+    }
+    if (do_upd) {
+      if (p.z_true && lane < 3) p.z_true[obj * 3 + lane] = zt[lane];  // SS2:298
+      if (visible) {
+        double z[3], zp[3], rz[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) z[a] = zt[a] + (p.z_noise ? p.z_noise[obj * 3 + a] : 0.0);
+        if (p.obs_type == SSA_OBS_AER) {
+          if (lane < 13) {
+            double uvw[3];
+            ssa_aer2uvw(zk, uvw);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) ws[WS_ZZ + lane * 3 + a] = uvw[a];
+          }
+          team_sync(tmask);
+          if (lane < 3) ws[WS_ZM + lane] = ssa_wmean13(ws + WS_ZZ, 3, lane, p.Wm);
+          team_sync(tmask);
+          double zm[3];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) zm[a] = ws[WS_ZM + a];
+          ssa_uvw2aer(zm, zp);
+          ssa_residual_aer(zk, zp, rz);
+        } else {
+          if (lane < 13) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) ws[WS_ZZ + lane * 3 + a] = zk[a];
+          }
+          team_sync(tmask);
+          if (lane < 3) ws[WS_ZM + lane] = ssa_wmean13(ws + WS_ZZ, 3, lane, p.Wm);
+          team_sync(tmask);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) { zp[a] = ws[WS_ZM + a]; rz[a] = zk[a] - zp[a]; }
+        }
+        if (lane < 13) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) ws[WS_ZZ + lane * 3 + a] = rz[a];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) ws[WS_SG + lane * 6 + i] = sg[i] - x[i];
+        }
+        team_sync(tmask);
+        // 6 unique elements of S and 18 of Pxz over 16 lanes (two rounds)
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+          const int e = lane + 16 * round;
+          if (e < 6) {
+            const int a = c_sa[e], b = c_sb[e];
+            double s;
+            if (p.obs_type == SSA_OBS_AER) s = ssa_wouter13(ws + WS_ZZ, 3, a, ws + WS_ZZ, 3, b, p.Wc);
+            else s = ssa_wcov13(ws + WS_ZZ, 3, a, ws + WS_ZZ, 3, b, p.Wc);
+            ws[WS_SS + 3 * a + b] = s + __ldg(p.qr + 21 + 3 * a + b);
+            if (a != b) {
+              double s2 = s;
+              if (p.obs_type != SSA_OBS_AER) s2 = ssa_wcov13(ws + WS_ZZ, 3, b, ws + WS_ZZ, 3, a, p.Wc);
+              ws[WS_SS + 3 * b + a] = s2 + __ldg(p.qr + 21 + 3 * b + a);
+            }
+          } else if (e < 24) {
+            const int i = (e - 6) / 3, a = (e - 6) % 3;
+            ws[WS_PX + (e - 6)] = ssa_wouter13(ws + WS_SG, 6, i, ws + WS_ZZ, 3, a, p.Wc);
+          }
+        }
+        team_sync(tmask);
+        double Sm[9], SI[9], yr[3];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Sm[e] = ws[WS_SS + e];
+        const int ok = ssa_inv3(Sm, SI);
+        if (p.obs_type == SSA_OBS_AER) ssa_residual_aer(z, zp, yr);
+        else {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) yr[a] = z[a] - zp[a];
+        }
+        if (lane < 6) {
+          double K[3];
+          const double px0 = ws[WS_PX + lane * 3], px1 = ws[WS_PX + lane * 3 + 1], px2 = ws[WS_PX + lane * 3 + 2];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            K[a] = ssa_fma(px2, SI[6 + a], ssa_fma(px1, SI[3 + a], ssa_mul(px0, SI[a])));
+            ws[WS_KK + lane * 3 + a] = K[a];
+          }
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+            ws[WS_TT + a * 6 + lane] =
+                ssa_fma(Sm[3 * a + 2], K[2], ssa_fma(Sm[3 * a + 1], K[1], ssa_mul(Sm[3 * a], K[0])));
+          ws[WS_XB + lane] = x[lane < 6 ? lane : 0] + ssa_fma(K[2], yr[2], ssa_fma(K[1], yr[1], ssa_mul(K[0], yr[0])));
+        }
+        team_sync(tmask);
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+          const int e = lane + 16 * round;
+          if (e < 21) {
+            const int i = c_pi[e], j = c_pj[e];
+            const double kt = ssa_fma(ws[WS_KK + i * 3 + 2], ws[WS_TT + 12 + j],
+                                      ssa_fma(ws[WS_KK + i * 3 + 1], ws[WS_TT + 6 + j],
+                                              ssa_mul(ws[WS_KK + i * 3], ws[WS_TT + j])));
+            ws[WS_PN + e] = ws[WS_PN + e] - kt;
+          }
+        }
+        int nan = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { x[i] = ws[WS_XB + i]; nan |= ssa_isnan(x[i]); }
+        if (p.y && lane < 3) p.y[obj * 3 + lane] = yr[lane];
+        if (p.S && lane < 9) p.S[obj * 9 + lane] = Sm[lane];
+        if (p.sigmas_h && lane < 13) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) p.sigmas_h[obj * 39 + lane * 3 + a] = zk[a];
+        }
+        updated = 1;
+        if (!ok) code |= SSA_ST_LINALG | SSA_ST_IN_UPDATE;
+        else if (nan) code |= SSA_ST_NAN | SSA_ST_IN_UPDATE;
+        team_sync(tmask);
+      }
+    }
+    if (code) {
+      status |= SSA_ST_FAILED | code;
+      if (lane < 6) ws[WS_XB + lane] = lane < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL;
+      {
+        const int i = c_pi[lane], j = c_pj[lane];
+        ws[WS_PN + lane] = (i == j) ? (i < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL) : 0.0;
+        if (lane < 5) {
+          const int i2 = c_pi[16 + lane], j2 = c_pj[16 + lane];
+          ws[WS_PN + 16 + lane] = (i2 == j2) ? (i2 < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL) : 0.0;
+        }
+      }
+      team_sync(tmask);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) x[i] = ws[WS_XB + i];
+    }
+  }
+  if (lane == 13 && p.updated) p.updated[obj] = (uint8_t)updated;
+
+  // ---- write back state ----------------------------------------------------------------------------
+  team_sync(tmask);
+  if (lane < 6) {
+    p.x[lane * ld + obj] = ws[WS_XB + lane];
+    if (flags & SSA_STEP_TRUTH) p.xt[lane * ld + obj] = ws[WS_XT + lane];
+  }
+  p.P[lane * ld + obj] = ws[WS_PN + lane];
+  if (lane < 5) p.P[(16 + lane) * ld + obj] = ws[WS_PN + 16 + lane];
+  if (lane == 0) {
+    p.status[obj] = status;
+    if (infl_count) p.infl[obj] += infl_count;
+  }
+
+  // ---- epilogue: observation row, errors, trace (results.py:36-72) -------------------------------
+  if (flags & SSA_STEP_EPILOGUE) {
+    if (lane < 12) {
+      const int d = lane < 6 ? 0 : lane - 6;
+      p.obs[obj * 12 + lane] = lane < 6 ? ws[WS_XB + lane] : ws[WS_PN + ssa_pidx(d, d)];
+    }
+    if (lane == 12 || lane == 13) {
+      const int o = (lane == 12) ? 0 : 3;
+      const double d0 = x[o] - xt[o], d1 = x[o + 1] - xt[o + 1], d2 = x[o + 2] - xt[o + 2];
+      const double dd = ssa_sqrt(ssa_fma(d2, d2, ssa_fma(d1, d1, ssa_mul(d0, d0))));
+      const double sp = (lane == 12) ? ssa_sqrt((ws[WS_PN + 0] + ws[WS_PN + 6]) + ws[WS_PN + 11])
+                                     : ssa_sqrt((ws[WS_PN + 15] + ws[WS_PN + 18]) + ws[WS_PN + 20]);
+      if (lane == 12) { p.dpos[obj] = dd; p.spos[obj] = sp; }
+      else { p.dvel[obj] = dd; p.svel[obj] = sp; }
+    }
+    if (lane == 14) p.trace[obj] = ssa_trace6(ws + WS_PN, 1);
+  }
+}
+
+// ---- per-environment reductions: reward/done and greedy taskers ------------------------------------
+struct EnvParams {
+  const double* dpos; const double* dvel; const double* spos; const double* trace;
+  const uint8_t* visible;
+  double* reward; uint8_t* done; int32_t* greedy; double* env_stats;  // env_stats[E][4]: max dpos, trinary, argmax spos, n_visible
+  int E, m, reward_type, n_steps, step_index;
+};
+
+struct ArgMax { double v; int i; };
+__device__ __forceinline__ ArgMax am_better(ArgMax a, ArgMax b) {
+  // np.argmax semantics: first maximum wins (lowest index among equal values)
+  if (b.i < 0) return a;
+  if (a.i < 0) return b;
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__device__ __forceinline__ ArgMax am_warp(ArgMax a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax b;
+    b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+    b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    a = am_better(a, b);
+  }
+  return a;
+}
+
+// One CTA per environment; threads stride over the m objects of the env.
+__global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) {
+  const int e = blockIdx.x;
+  const long base = (long)e * p.m;
+  ArgMax a_trace{0.0, -1}, a_vtrace{0.0, -1}, a_vdpos{0.0, -1}, a_vdvel{0.0, -1}, a_spos{0.0, -1}, a_dpos{0.0, -1};
+  int tri = 0, nvis = 0, vis_nonzero = 0;
+  for (int j = threadIdx.x; j < p.m; j += blockDim.x) {
+    const double dp = p.dpos[base + j], dv = p.dvel[base + j], sp = p.spos[base + j], tr = p.trace[base + j];
+    const int vis = p.visible[base + j];
+    a_trace = am_better(a_trace, ArgMax{tr, j});
+    a_spos = am_better(a_spos, ArgMax{sp, j});
+    a_dpos = am_better(a_dpos, ArgMax{dp, j});
+    if (vis) {
+      a_vtrace = am_better(a_vtrace, ArgMax{tr, j});
+      a_vdpos = am_better(a_vdpos, ArgMax{dp, j});
+      a_vdvel = am_better(a_vdvel, ArgMax{dv, j});
+      nvis += 1;
+      vis_nonzero |= (j != 0);
+    }
+    tri += (dp < 1e4) + (dp < 1e7);  // results.py:431-433
+  }
+  __shared__ ArgMax sm[6][4];
+  __shared__ int si[3][4];
+  ArgMax r[6] = {am_warp(a_trace), am_warp(a_vtrace), am_warp(a_vdpos), am_warp(a_vdvel), am_warp(a_spos), am_warp(a_dpos)};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tri += __shfl_xor_sync(0xffffffffu, tri, o);
+    nvis += __shfl_xor_sync(0xffffffffu, nvis, o);
+    vis_nonzero |= __shfl_xor_sync(0xffffffffu, vis_nonzero, o);
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    for (int q = 0; q < 6; ++q) sm[q][w] = r[q];
+    si[0][w] = tri; si[1][w] = nvis; si[2][w] = vis_nonzero;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int q = 0; q < 6; ++q) for (int k = 1; k < nw; ++k) sm[q][0] = am_better(sm[q][0], sm[q][k]);
+    for (int k = 1; k < nw; ++k) { si[0][0] += si[0][k]; si[1][0] += si[1][k]; si[2][0] |= si[2][k]; }
+    const double max_dpos = sm[5][0].v;
+    // `if not np.any(visible)` tests the INDEX array: it is also false-y when the only visible
+    // object is index 0 (agents.py:37) -> the reference samples a random action; we return -1.
+    const int any_vis = si[2][0];
+    p.greedy[e * SSA_N_TASKERS + SSA_TASKER_NAIVE_GREEDY] = sm[0][0].i;
+    p.greedy[e * SSA_N_TASKERS + SSA_TASKER_VISIBLE_GREEDY] = any_vis ? sm[1][0].i : -1;
+    p.greedy[e * SSA_N_TASKERS + SSA_TASKER_POS_ERROR_GREEDY] = any_vis ? sm[2][0].i : -1;
+    p.greedy[e * SSA_N_TASKERS + SSA_TASKER_VEL_ERROR_GREEDY] = any_vis ? sm[3][0].i : -1;
+    const double trinary = ((double)si[0][0] / (double)p.m) / 2.0;
+    p.env_stats[e * 4 + 0] = max_dpos;
+    p.env_stats[e * 4 + 1] = trinary;
+    p.env_stats[e * 4 + 2] = (double)sm[4][0].i;
+    p.env_stats[e * 4 + 3] = (double)si[1][0];
+    double reward = 0.0;
+    int done = 0;
+    if (p.reward_type == SSA_REWARD_JONES) {  // SS2:324-336
+      if (max_dpos > 5e6) { done = 1; reward = 0.0; }
+      else if (max_dpos < 3e4) { done = 1; reward = 1.0; }
+      else if (p.step_index + 1 >= p.n_steps) { done = 1; reward = 0.0; }
+    } else if (p.reward_type == SSA_REWARD_TRINARY) {  // SS2:337-338
+      reward = trinary;
+    } else {  // 'shaped' needs the reward history: finished on the host from env_stats (SS2:339-351)
+      if (max_dpos > 5e6) { done = 1; reward = 0.0; }
+      else if (max_dpos < 3e4) { done = 1; reward = 1.0; }
+    }
+    if (p.step_index + 1 >= p.n_steps) done = 1;  // SS2:353-354
+    p.reward[e] = reward;
+    p.done[e] = (uint8_t)done;
+  }
+}
+
+// reward.py:6-50 score terms, one thread per object
+__global__ void ssa_scores_kernel(const double* __restrict__ P, const double* __restrict__ dpos, double* out, long ld,
+                                  int N, double dt) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double a[6][6];
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) { a[i][j] = P[ssa_pidx(i, j) * ld + n]; a[j][i] = a[i][j]; }
+  const double pe = ssa_sqrt((a[0][0] + a[1][1]) + a[2][2]);
+  const double ve = ssa_sqrt((a[3][3] + a[4][4]) + a[5][5]);
+  out[n * 6 + 0] = ssa_fma(ve, 30.0, pe);  // score_scaled_trace_P
+  out[n * 6 + 1] = ((((a[0][0] + a[1][1]) + a[2][2]) + a[3][3]) + a[4][4]) + a[5][5];  // score_trace_P
+  // determinants by Gaussian elimination with partial pivoting (np.linalg.det = LU)
+  double det3;
+  {
+    const double m00 = a[0][0], m01 = a[0][1], m02 = a[0][2], m11 = a[1][1], m12 = a[1][2], m22 = a[2][2];
+    det3 = m00 * (m11 * m22 - m12 * m12) - m01 * (m01 * m22 - m12 * m02) + m02 * (m01 * m12 - m11 * m02);
+  }
+  double det = 1.0;
+  for (int c = 0; c < 6; ++c) {
+    int pv = c;
+    for (int i = c + 1; i < 6; ++i) if (fabs(a[i][c]) > fabs(a[pv][c])) pv = i;
+    if (pv != c) { for (int j = 0; j < 6; ++j) { const double t = a[c][j]; a[c][j] = a[pv][j]; a[pv][j] = t; } det = -det; }
+    det *= a[c][c];
+    if (a[c][c] == 0.0) break;
+    const double rp = 1.0 / a[c][c];
+    for (int i = c + 1; i < 6; ++i) {
+      const double l = a[i][c] * rp;
+      for (int j = c + 1; j < 6; ++j) a[i][j] -= l * a[c][j];
+    }
+  }
+  const double dt2 = dt * dt, dt6 = dt2 * dt2 * dt2;
+  out[n * 6 + 2] = pow(det * dt6, 1.0 / 12.0);  // score_scaled_det_P (host-side numpy uses np.power too)
+  out[n * 6 + 3] = det;                          // score_det_P
+  out[n * 6 + 4] = det3;                         // score_det_pos_P
+  out[n * 6 + 5] = dpos[n];                      // |delta pos| (score_neg_max_pos_error = -max over objects)
+}
+
+// ---- layout conversion kernels (reference AoS <-> device SoA) ---------------------------------------
+__global__ void ssa_aos_to_soa(const double* __restrict__ src, double* __restrict__ dst, int N, int C, long ld) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)N * C) return;
+  const long n = t / C;
+  const int c = (int)(t % C);
+  dst[c * ld + n] = src[t];
+}
+__global__ void ssa_soa_to_aos(const double* __restrict__ src, double* __restrict__ dst, int N, int C, long ld) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)N * C) return;
+  const long n = t / C;
+  const int c = (int)(t % C);
+  dst[t] = src[c * ld + n];
+}
+// full 6x6 AoS [N][36] (or one shared 6x6 when per_object == 0) -> packed SoA (upper triangle)
+__global__ void ssa_pfull_to_packed(const double* __restrict__ src, double* __restrict__ dst, int N, long ld,
+                                    int per_object) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)N * SSA_NP) return;
+  const long n = t / SSA_NP;
+  const int e = (int)(t % SSA_NP);
+  const int i = c_pi[e], j = c_pj[e];
+  dst[e * ld + n] = src[(per_object ? n * 36 : 0) + i * 6 + j];
+}
+__global__ void ssa_packed_to_pfull(const double* __restrict__ src, double* __restrict__ dst, int N, long ld) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)N * 36) return;
+  const long n = t / 36;
+  const int r = (int)(t % 36) / 6, c = (int)(t % 36) % 6;
+  const int i = r < c ? r : c, j = r < c ? c : r;
+  dst[t] = src[ssa_pidx(i, j) * ld + n];
+}
+__global__ void ssa_fill_i32(int32_t* p, long n, int v) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) p[t] = v;
+}
+
+// FP64 pipe microbenchmark: 8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) ssa_dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    v0 = __fma_rn(v0, a, b); v1 = __fma_rn(v1, a, b); v2 = __fma_rn(v2, a, b); v3 = __fma_rn(v3, a, b);
+    v4 = __fma_rn(v4, a, b); v5 = __fma_rn(v5, a, b); v6 = __fma_rn(v6, a, b); v7 = __fma_rn(v7, a, b);
+  }
+  const double s = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+thread_local char g_err[512] = "";
+int set_err(const char* what, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return SSA_ECUDA;
+}
+#define CK(call)                                         \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return set_err(#call, e_);    \
+  } while (0)
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+struct ssa_ukf {
+  ssa_ukf_cfg cfg;
+  int device;
+  long ld;
+  long launches;
+  // one slab for all fp64 SoA state
+  double* slab;
+  double *xt, *x, *P, *dpos, *dvel, *spos, *svel, *trace;
+  double *obs, *z_noise, *z_true, *y, *S, *sigmas_h, *scores, *reward, *env_stats;
+  double* stage;  // staging for AoS<->SoA conversion ([N][39] doubles)
+  double* qr;     // packed Q (21) + R (9)
+  int32_t *status, *infl, *actions, *greedy;
+  uint8_t *visible, *updated, *done;
+  size_t stage_bytes;
+};
+
+extern "C" {
+
+int ssa_ukf_abi_version(void) { return SSA_UKF_ABI_VERSION; }
+const char* ssa_ukf_last_error(void) { return g_err; }
+int ssa_ukf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+long ssa_ukf_ld(const ssa_ukf* h) { return h ? h->ld : 0; }
+long ssa_ukf_launch_count(const ssa_ukf* h) { return h ? h->launches : 0; }
+
+int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
+  if (!cfg || !out) { snprintf(g_err, sizeof(g_err), "null argument"); return SSA_EINVAL; }
+  if (cfg->abi_version != SSA_UKF_ABI_VERSION) { snprintf(g_err, sizeof(g_err), "ABI version mismatch"); return SSA_EINVAL; }
+  if (cfg->n_objects <= 0 || cfg->m <= 0 || cfg->n_envs <= 0 || (long)cfg->n_envs * cfg->m != cfg->n_objects) {
+    snprintf(g_err, sizeof(g_err), "need n_objects == n_envs * m > 0");
+    return SSA_EINVAL;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    snprintf(g_err, sizeof(g_err), "no CUDA device: libssa_ukf has no CPU fallback");
+    return SSA_ENODEV;
+  }
+  if (device < 0 || device >= ndev) { snprintf(g_err, sizeof(g_err), "bad device index"); return SSA_EINVAL; }
+  CK(cudaSetDevice(device));
+  ssa_ukf* h = new (std::nothrow) ssa_ukf();
+  if (!h) return SSA_ENOMEM;
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->device = device;
+  const long N = cfg->n_objects, E = cfg->n_envs;
+  h->ld = (N + 31) / 32 * 32;
+  const long ld = h->ld;
+  // fp64 slab: xt 6, x 6, P 21, dpos dvel spos svel trace 5 (SoA rows of ld) + AoS outputs
+  const size_t n_soa = (size_t)(6 + 6 + 21 + 5) * ld;
+  const size_t n_aos = (size_t)N * (12 + 3 + 3 + 3 + 9 + 39 + 6) + (size_t)E * (1 + 4) + 32;
+  cudaError_t e = cudaMalloc(&h->slab, (n_soa + n_aos) * sizeof(double));
+  if (e != cudaSuccess) { delete h; return set_err("cudaMalloc(slab)", e); }
+  cudaMemset(h->slab, 0, (n_soa + n_aos) * sizeof(double));
+  double* q = h->slab;
+  h->xt = q; q += 6 * ld;
+  h->x = q; q += 6 * ld;
+  h->P = q; q += 21 * ld;
+  h->dpos = q; q += ld; h->dvel = q; q += ld; h->spos = q; q += ld; h->svel = q; q += ld; h->trace = q; q += ld;
+  h->obs = q; q += N * 12;
+  h->z_noise = q; q += N * 3;
+  h->z_true = q; q += N * 3;
+  h->y = q; q += N * 3;
+  h->S = q; q += N * 9;
+  h->sigmas_h = q; q += N * 39;
+  h->scores = q; q += N * 6;
+  h->reward = q; q += E;
+  h->env_stats = q; q += E * 4;
+  h->qr = q; q += 32;
+  {
+    double qr[30];
+    int e2 = 0;
+    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) qr[e2++] = cfg->Q[6 * i + j];
+    for (int k = 0; k < 9; ++k) qr[21 + k] = cfg->R[k];
+    e = cudaMemcpy(h->qr, qr, sizeof(qr), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(h->slab); delete h; return set_err("cudaMemcpy(qr)", e); }
+  }
+  h->stage_bytes = (size_t)N * 39 * sizeof(double);
+  if ((e = cudaMalloc(&h->stage, h->stage_bytes)) != cudaSuccess) { ssa_ukf_destroy(h); return set_err("cudaMalloc(stage)", e); }
+  if ((e = cudaMalloc(&h->status, sizeof(int32_t) * (2 * ld + E + E * SSA_N_TASKERS))) != cudaSuccess) {
+    ssa_ukf_destroy(h);
+    return set_err("cudaMalloc(int)", e);
+  }
+  cudaMemset(h->status, 0, sizeof(int32_t) * (2 * ld + E + E * SSA_N_TASKERS));
+  h->infl = h->status + ld;
+  h->actions = h->infl + ld;
+  h->greedy = h->actions + E;
+  if ((e = cudaMalloc(&h->visible, 2 * ld + E)) != cudaSuccess) { ssa_ukf_destroy(h); return set_err("cudaMalloc(u8)", e); }
+  cudaMemset(h->visible, 0, 2 * ld + E);
+  h->updated = h->visible + ld;
+  h->done = h->updated + ld;
+  *out = h;
+  return SSA_OK;
+}
+
+int ssa_ukf_destroy(ssa_ukf* h) {
+  if (!h) return SSA_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->slab);
+  cudaFree(h->stage);
+  cudaFree(h->status);
+  cudaFree(h->visible);
+  delete h;
+  return SSA_OK;
+}
+
+static int upload_soa(ssa_ukf* h, const double* host, double* dst, int C, cudaStream_t st) {
+  const long N = h->cfg.n_objects;
+  CK(cudaMemcpyAsync(h->stage, host, sizeof(double) * N * C, cudaMemcpyHostToDevice, st));
+  const long tot = N * C;
+  ssa_aos_to_soa<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->stage, dst, (int)N, C, h->ld);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SSA_OK;
+}
+
+int ssa_ukf_reset(ssa_ukf* h, const double* x_true, const double* x_filter, const double* P0, int p0_per_object,
+                  void* stream) {
+  if (!h || !x_true || !x_filter || !P0) { snprintf(g_err, sizeof(g_err), "null argument"); return SSA_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  const long N = h->cfg.n_objects;
+  int rc;
+  if ((rc = upload_soa(h, x_true, h->xt, 6, st))) return rc;
+  CK(cudaStreamSynchronize(st));  // the staging buffer is reused
+  if ((rc = upload_soa(h, x_filter, h->x, 6, st))) return rc;
+  CK(cudaStreamSynchronize(st));
+  if (p0_per_object) {
+    // chunk through the staging buffer ([N][39] doubles >= [N][36])
+    CK(cudaMemcpyAsync(h->stage, P0, sizeof(double) * N * 36, cudaMemcpyHostToDevice, st));
+  } else {
+    CK(cudaMemcpyAsync(h->stage, P0, sizeof(double) * 36, cudaMemcpyHostToDevice, st));
+  }
+  ssa_pfull_to_packed<<<(unsigned)((N * SSA_NP + 255) / 256), 256, 0, st>>>(h->stage, h->P, (int)N, h->ld, p0_per_object);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(h->status, 0, sizeof(int32_t) * 2 * h->ld, st));
+  CK(cudaMemsetAsync(h->visible, 0, 2 * h->ld, st));
+  CK(cudaStreamSynchronize(st));
+  return SSA_OK;
+}
+
+static int field_info(ssa_ukf* h, int field, void** p, size_t* bytes, int* soa_cols) {
+  const size_t N = h->cfg.n_objects, E = h->cfg.n_envs, ld = h->ld;
+  *soa_cols = 0;
+  switch (field) {
+    case SSA_F_X_TRUE: *p = h->xt; *bytes = 6 * ld * 8; *soa_cols = 6; break;
+    case SSA_F_X_FILTER: *p = h->x; *bytes = 6 * ld * 8; *soa_cols = 6; break;
+    case SSA_F_P_FILTER: *p = h->P; *bytes = 21 * ld * 8; *soa_cols = 21; break;
+    case SSA_F_OBS: *p = h->obs; *bytes = N * 12 * 8; break;
+    case SSA_F_DELTA_POS: *p = h->dpos; *bytes = N * 8; break;
+    case SSA_F_DELTA_VEL: *p = h->dvel; *bytes = N * 8; break;
+    case SSA_F_SIGMA_POS: *p = h->spos; *bytes = N * 8; break;
+    case SSA_F_SIGMA_VEL: *p = h->svel; *bytes = N * 8; break;
+    case SSA_F_TRACE: *p = h->trace; *bytes = N * 8; break;
+    case SSA_F_Z_TRUE: *p = h->z_true; *bytes = N * 3 * 8; break;
+    case SSA_F_Y: *p = h->y; *bytes = N * 3 * 8; break;
+    case SSA_F_S: *p = h->S; *bytes = N * 9 * 8; break;
+    case SSA_F_SIGMAS_H: *p = h->sigmas_h; *bytes = N * 39 * 8; break;
+    case SSA_F_Z_NOISE: *p = h->z_noise; *bytes = N * 3 * 8; break;
+    case SSA_F_VISIBLE: *p = h->visible; *bytes = N; break;
+    case SSA_F_UPDATED: *p = h->updated; *bytes = N; break;
+    case SSA_F_STATUS: *p = h->status; *bytes = N * 4; break;
+    case SSA_F_INFLATIONS: *p = h->infl; *bytes = N * 4; break;
+    case SSA_F_ACTIONS: *p = h->actions; *bytes = E * 4; break;
+    case SSA_F_REWARD: *p = h->reward; *bytes = E * 8; break;
+    case SSA_F_DONE: *p = h->done; *bytes = E; break;
+    case SSA_F_GREEDY: *p = h->greedy; *bytes = E * SSA_N_TASKERS * 4; break;
+    case SSA_F_SCORES: *p = h->scores; *bytes = N * 6 * 8; break;
+    default: snprintf(g_err, sizeof(g_err), "unknown field %d", field); return SSA_EINVAL;
+  }
+  return SSA_OK;
+}
+
+int ssa_ukf_device_ptr(ssa_ukf* h, int field, void** dptr, size_t* bytes) {
+  if (!h || !dptr) return SSA_EINVAL;
+  int cols;
+  size_t b;
+  int rc = field_info(h, field, dptr, &b, &cols);
+  if (bytes) *bytes = b;
+  return rc;
+}
+
+int ssa_ukf_upload(ssa_ukf* h, int field, const void* host, size_t bytes, void* stream) {
+  if (!h || !host) return SSA_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  void* p; size_t b; int cols;
+  int rc = field_info(h, field, &p, &b, &cols);
+  if (rc) return rc;
+  const size_t N = h->cfg.n_objects;
+  if (field == SSA_F_X_TRUE || field == SSA_F_X_FILTER) {
+    if (bytes != N * 6 * 8) { snprintf(g_err, sizeof(g_err), "size mismatch"); return SSA_EINVAL; }
+    rc = upload_soa(h, (const double*)host, (double*)p, 6, st);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    return SSA_OK;
+  }
+  if (field == SSA_F_P_FILTER) {
+    if (bytes != N * 36 * 8) { snprintf(g_err, sizeof(g_err), "size mismatch"); return SSA_EINVAL; }
+    CK(cudaMemcpyAsync(h->stage, host, bytes, cudaMemcpyHostToDevice, st));
+    ssa_pfull_to_packed<<<(unsigned)((N * SSA_NP + 255) / 256), 256, 0, st>>>(h->stage, h->P, (int)N, h->ld, 1);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return SSA_OK;
+  }
+  if (bytes != b) { snprintf(g_err, sizeof(g_err), "size mismatch for field %d: got %zu want %zu", field, bytes, b); return SSA_EINVAL; }
+  CK(cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, st));
+  return SSA_OK;
+}
+
+int ssa_ukf_download(ssa_ukf* h, int field, void* host, size_t bytes, void* stream) {
+  if (!h || !host) return SSA_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  void* p; size_t b; int cols;
+  int rc = field_info(h, field, &p, &b, &cols);
+  if (rc) return rc;
+  const size_t N = h->cfg.n_objects;
+  if (field == SSA_F_X_TRUE || field == SSA_F_X_FILTER) {
+    if (bytes != N * 6 * 8) { snprintf(g_err, sizeof(g_err), "size mismatch"); return SSA_EINVAL; }
+    ssa_soa_to_aos<<<(unsigned)((N * 6 + 255) / 256), 256, 0, st>>>((const double*)p, h->stage, (int)N, 6, h->ld);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, h->stage, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SSA_OK;
+  }
+  if (field == SSA_F_P_FILTER) {
+    if (bytes != N * 36 * 8) { snprintf(g_err, sizeof(g_err), "size mismatch"); return SSA_EINVAL; }
+    ssa_packed_to_pfull<<<(unsigned)((N * 36 + 255) / 256), 256, 0, st>>>(h->P, h->stage, (int)N, h->ld);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, h->stage, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SSA_OK;
+  }
+  if (bytes != b) { snprintf(g_err, sizeof(g_err), "size mismatch for field %d: got %zu want %zu", field, bytes, b); return SSA_EINVAL; }
+  CK(cudaMemcpyAsync(host, p, bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SSA_OK;
+}
+
+int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
+  if (!h) return SSA_EINVAL;
+  if ((flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE)) && !M) {
+    snprintf(g_err, sizeof(g_err), "trans_matrix required for update/epilogue");
+    return SSA_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  const ssa_ukf_cfg& c = h->cfg;
+  p.xt = h->xt; p.x = h->x; p.P = h->P; p.status = h->status; p.infl = h->infl;
+  p.actions = h->actions; p.z_noise = h->z_noise;
+  p.obs = h->obs; p.dpos = h->dpos; p.dvel = h->dvel; p.spos = h->spos; p.svel = h->svel; p.trace = h->trace;
+  p.z_true = h->z_true; p.y = h->y; p.S = h->S; p.sigmas_h = h->sigmas_h;
+  p.visible = h->visible; p.updated = h->updated;
+  p.ld = h->ld; p.N = c.n_objects; p.m = c.m; p.flags = flags; p.obs_type = c.obs_type; p.resample = c.resample_after_predict;
+  p.dt = c.dt; p.lam = c.lam_plus_n; p.obs_limit = c.obs_limit;
+  memcpy(p.Wm, c.Wm, sizeof(p.Wm)); memcpy(p.Wc, c.Wc, sizeof(p.Wc));
+  p.qr = h->qr;
+  if (M) memcpy(p.ob.M, M, sizeof(p.ob.M));
+  memcpy(p.ob.obs_itrs, c.obs_itrs, sizeof(p.ob.obs_itrs));
+  memcpy(p.ob.T, c.T, sizeof(p.ob.T));
+  const unsigned grid = (unsigned)((c.n_objects + kTeamsPerCta - 1) / kTeamsPerCta);
+  ssa_step_kernel<<<grid, kCtaThreads, 0, st>>>(p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SSA_OK;
+}
+
+int ssa_ukf_predict(ssa_ukf* h, void* stream) {
+  return ssa_ukf_step(h, nullptr, SSA_STEP_TRUTH | SSA_STEP_PREDICT, stream);
+}
+int ssa_ukf_update(ssa_ukf* h, const double M[9], int all, void* stream) {
+  return ssa_ukf_step(h, M, (all ? SSA_STEP_UPDATE_ALL : SSA_STEP_UPDATE_ACT) | SSA_STEP_EPILOGUE, stream);
+}
+
+int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stream) {
+  (void)M;
+  if (!h) return SSA_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  EnvParams p;
+  p.dpos = h->dpos; p.dvel = h->dvel; p.spos = h->spos; p.trace = h->trace; p.visible = h->visible;
+  p.reward = h->reward; p.done = h->done; p.greedy = h->greedy; p.env_stats = h->env_stats;
+  p.E = h->cfg.n_envs; p.m = h->cfg.m; p.reward_type = h->cfg.reward_type; p.n_steps = h->cfg.n_steps;
+  p.step_index = step_index;
+  ssa_env_reduce_kernel<<<(unsigned)p.E, 128, 0, st>>>(p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SSA_OK;
+}
+
+int ssa_ukf_scores(ssa_ukf* h, void* stream) {
+  if (!h) return SSA_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.n_objects;
+  ssa_scores_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(h->P, h->dpos, h->scores, h->ld, N, h->cfg.dt);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SSA_OK;
+}
+
+int ssa_ukf_sync(ssa_ukf* h, void* stream) {
+  if (!h) return SSA_EINVAL;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return SSA_OK;
+}
+
+int ssa_ukf_fp64_peak(int device, void* stream, double* tflops) {
+  if (!tflops) return SSA_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { snprintf(g_err, sizeof(g_err), "no CUDA device"); return SSA_ENODEV; }
+  CK(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double* out;
+  CK(cudaMalloc(&out, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  ssa_dfma_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 0.999999, 1e-9);  // warm-up
+  float best = 1e30f;
+  for (int r = 0; r < 5; ++r) {
+    CK(cudaEventRecord(e0, st));
+    ssa_dfma_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 0.999999, 1e-9);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  const double flop = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+  *tflops = flop / (best * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return SSA_OK;
+}
+
+}  // extern "C"
