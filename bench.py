@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — the headline metric of BASELINE.json on B200: RSO UKF predict+update per second.
+
+A "step" = one pass of the hot path (truth fx + UKF predict + UKF update + obs/error epilogue) over
+one batch of synthetic input: the C2 workload of SURVEY.md 8(d) — a 20 000-orbit catalog, every object
+predicted and updated once per step (ssa_tasker_simple_2.py:243-367 for every RSO).  One process per
+GPU; every rank owns an independent 20 000-object catalog (weak scaling, no data-path collective —
+objects never couple); rank 0 prints ONE JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c4] [--impl reference]
+
+`--impl reference` times the CPU oracle port of the reference's algorithm (oracle/ukf_oracle.c, OpenMP
+over all host cores) on the same workload — the reference itself is pure Python around filterpy and
+cannot be built or installed offline (DESIGN.md "Reference arm").
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Algorithmic cost per unit (one object: truth fx + predict + update + epilogue), DESIGN.md §5.
+FLOP_PER_UNIT = 39.0e3        # SURVEY 8(d) counting convention (fma=2, div=sqrt=10, sin=cos=40, ...)
+BYTES_PER_UNIT = 48 + 168 + 48 + 24 + 4 + 48 + 168 + 48 + 96 + 40 + 4 + 2   # packed-P SoA layout: 698 B
+CEL2TER06AXY = [+0.973104317697536, +0.230363826239128, -0.000703163481769,
+                -0.230363800456036, +0.973104570632801, +0.000118545368117,
+                +0.000711560162594, +0.000046626402444, +0.999999745754024]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--objects", type=int, default=0, help="override objects per rank")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    return ap.parse_args()
+
+
+def workload_inputs(n_objects, rank, steps):
+    from ssa_gym_b200.catalog import synthetic_catalog, tiled_catalog
+    from ssa_gym_b200.transformations import arcsec2rad
+    if n_objects <= 20000:
+        cat = synthetic_catalog(n_objects, seed=rank)
+    else:
+        cat = tiled_catalog(n_objects, synthetic_catalog(20000, 0), seed=2 + rank)
+    x = cat + np.random.RandomState(1000 + rank).normal(size=(n_objects, 6)) * np.array([1e5] * 3 + [1e2] * 3)
+    P0 = np.diag([1e10] * 3 + [1e4] * 3)
+    zn = np.random.RandomState(2000 + rank).normal(size=(steps, n_objects, 3)) * np.array([arcsec2rad, arcsec2rad, 1e3])
+    return cat, x, P0, zn
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_lib():
+    import subprocess as sp
+    lib = os.path.join(ROOT, "oracle", "liboracle.so")
+    src = os.path.join(ROOT, "oracle", "ukf_oracle.c")
+    if not os.path.isfile(lib) or os.path.getmtime(src) > os.path.getmtime(lib):
+        sp.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s"], check=True)
+    return ctypes.CDLL(lib)
+
+
+def run_oracle_steps(cfg, cat, x, P0, zn, n_steps, budget_s=None):
+    """Time the CPU oracle (all host threads) on the workload.  Returns (units/s, steps run, threads)."""
+    L = oracle_lib()
+    L.oracle_num_threads.restype = ctypes.c_int
+    N = len(cat)
+    vp = ctypes.c_void_p
+    ptr = lambda a: a.ctypes.data_as(vp)
+    xt, xf = cat.copy(), x.copy()
+    P = np.ascontiguousarray(np.broadcast_to(P0, (N, 6, 6))).copy()
+    status, infl = np.zeros(N, np.int32), np.zeros(N, np.int32)
+    obs = np.zeros((N, 12))
+    sc = [np.zeros(N) for _ in range(5)]
+    vis, upd = np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+    M = np.array(CEL2TER06AXY)
+    flags = 0x1 | 0x2 | 0x4 | 0x10
+
+    def one(s):
+        L.oracle_step(ctypes.byref(cfg), ptr(M), ctypes.c_int(flags), ptr(xt), ptr(xf), ptr(P), ptr(status), ptr(infl), None,
+                      ptr(zn[s % len(zn)]), ptr(obs), ptr(sc[0]), ptr(sc[1]), ptr(sc[2]), ptr(sc[3]), ptr(sc[4]),
+                      None, None, None, None, ptr(vis), ptr(upd))
+    one(0)  # warm-up (page-in, thread pool)
+    t0 = time.perf_counter()
+    done = 0
+    for s in range(n_steps):
+        one(s + 1)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return N * done / dt, done, L.oracle_num_threads(), dt
+
+
+def make_cfg(N):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from ssa_gym_b200 import _lib
+    from ssa_gym_b200.transformations import arcsec2rad, lla2ecef, trans_uvw_ecef
+    from ssa_gym_b200.ukf import Q_discrete_white_noise_block, merwe_weights
+    Wm, Wc, lam = merwe_weights()
+    c = _lib.SsaUkfCfg()
+    c.abi_version, c.n_objects, c.n_envs, c.m = 1, N, 1, N
+    c.obs_type, c.resample_after_predict, c.reward_type, c.n_steps = 0, 1, 0, 480
+    c.dt, c.lam_plus_n = 20.0, lam
+    for i in range(13):
+        c.Wm[i], c.Wc[i] = Wm[i], Wc[i]
+    for i, v in enumerate(Q_discrete_white_noise_block(20.0, 0.000025 ** 2).ravel()):
+        c.Q[i] = v
+    for i, v in enumerate(np.diag([arcsec2rad ** 2] * 2 + [1e3 ** 2]).ravel()):
+        c.R[i] = v
+    lla = np.array([np.radians(38.828198), np.radians(-77.305352), 20.0])
+    for i, v in enumerate(lla2ecef(lla)):
+        c.obs_itrs[i] = v
+    for i, v in enumerate(np.asarray(trans_uvw_ecef(lla[0], lla[1]), dtype=float).ravel()):
+        c.T[i] = v
+    c.obs_limit = np.radians(-90.0)
+    return c
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_obj = a.objects or (20000 if a.workload == "c2" else 1_000_000 // max(world, 1))
+    wl_name = ("C2: 20000-orbit catalog per GPU, UKF predict+update of every object per step" if a.workload == "c2"
+               else f"C4: 1M-object catalog sharded over {world} GPU(s), {n_obj} objects per rank")
+    config = {"workload": wl_name, "objects_per_gpu": n_obj, "dt_s": 20.0, "obs_type": "aer",
+              "sigma_points": "merwe alpha=1e-4 beta=2 kappa=-3", "trans_matrix": "SOFA Cel2Ter06aXY (tests.py:107-109)",
+              "l2": "flushed between timed steps (256 MiB write)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cat, x, P0, zn = workload_inputs(n_obj, 0, max(a.steps, 1) + 1)
+        cfg = make_cfg(n_obj)
+        for w in range(max(a.warmup, 0)):
+            pass
+        val, done, threads, dt = run_oracle_steps(cfg, cat, x, P0, zn, a.steps)
+        line = {"impl": "reference", "metric": "RSO UKF predict+update per second", "value": val, "unit": "object-updates/s",
+                "n_gpus": a.gpus, "steps": done, "warmup": a.warmup, "ms_per_step": dt / done * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "object-updates/s", "cores": threads, "kind": "port",
+                                 "sample": f"{done} steps x {n_obj} objects (the full per-GPU batch), oracle/ukf_oracle.c, OpenMP"},
+                "e2e": {"value": val, "unit": "object-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from ssa_gym_b200 import _lib
+    from ssa_gym_b200.ukf import BatchedUKF, fp64_peak_tflops
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the UKF hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    F = _lib
+    cat, x, P0, zn = workload_inputs(n_obj, rank, 8)
+    cfg = make_cfg(n_obj)
+    ukf = BatchedUKF(n_envs=1, m=n_obj, dt=20.0, Q=np.array(cfg.Q).reshape(6, 6), R=np.array(cfg.R).reshape(3, 3),
+                     obs_lla=[np.radians(38.828198), np.radians(-77.305352), 20.0], obs_limit_rad=np.radians(-90.0),
+                     device=local_rank)
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    ukf.reset(cat, x, P0, stream=sp)
+    M = np.array(CEL2TER06AXY)
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE
+    # device-resident measurement noise for `value` (inputs already in HBM): 8 pre-drawn slices, rotated
+    zn_dev = torch.from_numpy(zn).cuda()
+    zview = ukf.torch_view(F.F_Z_NOISE)  # zero-copy torch view of the handle's z_noise buffer [N,3]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def load_noise(s):
+        # device-to-device copy of slice s into the handle's z_noise buffer (outside the timed events)
+        zview.copy_(zn_dev[s % 8], non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -----------------------------------------------------------------------------------
+    for w in range(max(a.warmup, 3)):
+        load_noise(w)
+        ukf.step(M, flags, stream=sp)
+    torch.cuda.synchronize()
+    peak_tf = fp64_peak_tflops(local_rank, sp)
+
+    # ---- timed: exactly K steps, per-step CUDA events on the launching stream, L2 flushed between steps ---
+    sampler = ClockSampler(local_rank)
+    launches0 = ukf.launch_count
+    barrier()
+    sampler.start()
+    evs = []
+    t_wall0 = time.perf_counter()
+    for s in range(a.steps):
+        load_noise(s)
+        flush.fill_(s & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ukf.step(M, flags, stream=sp)
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_ms = float(np.sum(step_ms))
+    launches = ukf.launch_count - launches0
+    status = ukf.download(F.F_STATUS)
+    n_failed = int((status & 1).sum())
+
+    # back-to-back (no flush) for reference
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in range(a.steps):
+        ukf.step(M, flags, stream=sp)
+    e1.record(stream)
+    barrier()
+    b2b_ms = e0.elapsed_time(e1) / a.steps
+
+    # ---- e2e: the user-facing call with HOST buffers: H2D z_noise + M each step, D2H obs + errors ----
+    zn_pin = torch.from_numpy(zn).pin_memory()
+    obs_pin = torch.empty((n_obj, 12), dtype=torch.float64).pin_memory()
+    dpos_pin = torch.empty(n_obj, dtype=torch.float64).pin_memory()
+    st_pin = torch.empty(n_obj, dtype=torch.int32).pin_memory()
+    zn_np, obs_np, dpos_np, st_np = zn_pin.numpy(), obs_pin.numpy(), dpos_pin.numpy(), st_pin.numpy()
+    for w in range(3):
+        ukf.upload(F.F_Z_NOISE, zn_np[w % 8], stream=sp)
+        ukf.step(M, flags, stream=sp)
+        ukf.download(F.F_OBS, out=obs_np, stream=sp)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in range(a.steps):
+        ukf.upload(F.F_Z_NOISE, zn_np[s % 8], stream=sp)
+        ukf.step(M, flags, stream=sp)
+        ukf.download(F.F_OBS, out=obs_np, stream=sp)
+        ukf.download(F.F_DELTA_POS, out=dpos_np, stream=sp)
+        ukf.download(F.F_STATUS, out=st_np, stream=sp)
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / a.steps
+    h2d = zn_np[0].nbytes + 72
+    d2h = obs_np.nbytes + dpos_np.nbytes + st_np.nbytes
+
+    # ---- reduce over ranks (max time) --------------------------------------------------------------
+    t = torch.tensor([total_ms, b2b_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, b2b_ms, e2e_ms = [float(v) for v in t.tolist()]
+    ms_per_step = total_ms / a.steps
+    units = n_obj * world
+    value = units / (ms_per_step * 1e-3)
+    e2e_val = units / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        kern_ms = float(np.mean(step_ms))
+        ach_tf = FLOP_PER_UNIT * n_obj / (kern_ms * 1e-3) / 1e12
+        ach_gb = BYTES_PER_UNIT * n_obj / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "RSO UKF predict+update per second", "value": value, "unit": "object-updates/s",
+            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config,
+            "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                         "traffic": None,
+                         "note": "kernel ssa_step_kernel; achieved = 39 kflop/object (SURVEY 8d convention) x objects / mean "
+                                 "CUDA-event launch time; peak = DFMA microbenchmark measured live in this run "
+                                 "(ssa_ukf_fp64_peak; FP64 is not in MEASURED_PEAKS.json)",
+                         "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"}},
+            "e2e": {"value": e2e_val, "unit": "object-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "extra": {"ms_per_step_back_to_back_no_flush": b2b_ms, "wall_s_timed_region": t_wall, "failed_filters": n_failed,
+                      "step_ms_min": float(np.min(step_ms)), "step_ms_max": float(np.max(step_ms))},
+        }
+        if not a.no_cpu_baseline:
+            catc, xc, P0c, znc = workload_inputs(n_obj, 0, 4)
+            val, done, threads, dtc = run_oracle_steps(cfg, catc, xc, P0c, znc, 10 ** 6, budget_s=a.cpu_seconds)
+            line["cpu_baseline"] = {"value": val, "unit": "object-updates/s", "cores": threads, "kind": "port",
+                                    "sample": f"{done} steps x {n_obj} objects in {dtc:.1f} s, oracle/ukf_oracle.c (reference "
+                                              f"operation order, libm), OpenMP over host threads"}
+        print(json.dumps(line))
+    ukf.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

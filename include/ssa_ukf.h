@@ -111,6 +111,7 @@ enum ssa_field {
 #define SSA_STEP_UPDATE_ALL 0x4   /* catalog mode: update every object with its z_noise */
 #define SSA_STEP_UPDATE_ACT 0x8   /* RL mode: update object actions[e] of each env e (SS2:292-315) */
 #define SSA_STEP_EPILOGUE 0x10    /* obs / error / trace / visibility (SS2:320-322, 410-425) */
+#define SSA_STEP_RECORD 0x20      /* also store z_true, y, S, sigmas_h of updated objects (SS2:298-304) */
 
 int ssa_ukf_abi_version(void);
 const char* ssa_ukf_last_error(void);
@@ -150,6 +151,27 @@ long ssa_ukf_launch_count(const ssa_ukf* h);
 /* FP64 pipe microbenchmark (dependent DFMA chains on every SM) used as the roofline denominator:
  * returns achieved TFLOP/s (2 flop per DFMA), timed with CUDA events on `stream`.                  */
 int ssa_ukf_fp64_peak(int device, void* stream, double* tflops);
+
+/* ---- operator-level entry points -----------------------------------------------------------------
+ * The reference's plug points are Python callables handed to filterpy through env_config
+ * (envs/__init__.py:27-28: fx, hx, mean_z, residual_z, msqrt).  These evaluate the DEVICE build of
+ * the same operators on host arrays (synchronous; n independent evaluations, one GPU thread each), so
+ * that calling an operator directly runs the code the fused kernel runs.  Also used by the parity
+ * tests to compare sm_100a with the host twin function by function.                                  */
+/* op: 0 sin 1 cos 2 tan 3 atan 4 asin 5 acos 6 exp 7 log 8 sinh 9 cosh 10 tanh 11 atanh 12 asinh
+ *     13 acosh 14 x^(2/3) 15 atan2(a,b) 16 python a%b 17 a/b 18 sqrt                                  */
+int ssa_unit_math(int op, const double* a, const double* b, double* out, int n, int device);
+/* fx_xyz_farnocchia (envs/farnocchia.py:1053): x[n][6] -> out[n][6]; exc[n] != 0 where numba would raise */
+int ssa_unit_fx(const double* x, double dt, double* out, int32_t* exc, int n, int device);
+/* hx_aer_erfa (envs/dynamics.py:219): x[n][stride] (first 3 used) -> out[n][3] = az, el, range      */
+int ssa_unit_hx_aer(const double* x, int stride, const double M[9], const double obs_itrs[3], const double T[9],
+                    double* out, int n, int device);
+/* op 0: aer2uvw  1: uvw2aer  2: residual_z_aer(a, b)   (transformations.py:283-316, dynamics.py:260) */
+int ssa_unit_aer(int op, const double* a, const double* b, double* out, int n, int device);
+/* robust_cholesky(lam * P) (envs/dynamics.py:402): packed upper [n][21] in/out; ret = attempt or -1  */
+int ssa_unit_robust_chol(const double* P_packed, double lam, double* U_packed, int32_t* ret, int n, int device);
+/* numpy.linalg.inv of 3x3 (filterpy UKF.update SI = inv(S))                                          */
+int ssa_unit_inv3(const double* S, double* SI, int32_t* ok, int n, int device);
 
 #ifdef __cplusplus
 }

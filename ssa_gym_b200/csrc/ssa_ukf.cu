@@ -578,6 +578,69 @@ __global__ void __launch_bounds__(256) ssa_dfma_peak_kernel(double* out, int ite
   if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// ---- unit kernels: the device build of single functions, one thread per element.  They exist so that
+// the tests can demand bit-equality between sm_100a and the host twin function by function, and so
+// that the Python operator callables (fx, hx, ...) evaluate on the device when called directly. ----
+__global__ void ssa_unit_math_kernel(int op, const double* a, const double* b, double* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = a[i], y = b ? b[i] : 0.0;
+  double r;
+  switch (op) {
+    case 0: r = ssa_sin(x); break;      case 1: r = ssa_cos(x); break;     case 2: r = ssa_tan(x); break;
+    case 3: r = ssa_atan(x); break;     case 4: r = ssa_asin(x); break;    case 5: r = ssa_acos(x); break;
+    case 6: r = ssa_exp(x); break;      case 7: r = ssa_log(x); break;     case 8: r = ssa_sinh(x); break;
+    case 9: r = ssa_cosh(x); break;     case 10: r = ssa_tanh(x); break;   case 11: r = ssa_atanh(x); break;
+    case 12: r = ssa_asinh(x); break;   case 13: r = ssa_acosh(x); break;  case 14: r = ssa_pow23(x); break;
+    case 15: r = ssa_atan2(x, y); break; case 16: r = ssa_pymod(x, y); break;
+    case 17: r = ssa_div(x, y); break;  case 18: r = ssa_sqrt(x); break;
+    default: r = ssa_nan();
+  }
+  out[i] = r;
+}
+__global__ void ssa_unit_fx_kernel(const double* x, double dt, double* out, int32_t* exc, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s[6], f[6];
+  for (int k = 0; k < 6; ++k) s[k] = x[6 * (long)i + k];
+  exc[i] = ssa_fx(s, dt, f);
+  for (int k = 0; k < 6; ++k) out[6 * (long)i + k] = f[k];
+}
+__global__ void ssa_unit_hx_kernel(const double* x, ssa_obs ob, double* out, int n, int stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s[3], z[3];
+  for (int k = 0; k < 3; ++k) s[k] = x[stride * (long)i + k];
+  ssa_hx_aer(s, &ob, z);
+  for (int k = 0; k < 3; ++k) out[3 * (long)i + k] = z[k];
+}
+__global__ void ssa_unit_aer_kernel(int op, const double* a, const double* b, double* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double u[3], v[3] = {0, 0, 0}, r[3];
+  for (int k = 0; k < 3; ++k) { u[k] = a[3 * (long)i + k]; if (b) v[k] = b[3 * (long)i + k]; }
+  if (op == 0) ssa_aer2uvw(u, r);
+  else if (op == 1) ssa_uvw2aer(u, r);
+  else ssa_residual_aer(u, v, r);
+  for (int k = 0; k < 3; ++k) out[3 * (long)i + k] = r[k];
+}
+__global__ void ssa_unit_chol_kernel(const double* P, double lam, double* U, int32_t* ret, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double u[SSA_NP];
+  ret[i] = ssa_robust_chol6(P + (long)i * SSA_NP, 1, lam, u);
+  for (int e = 0; e < SSA_NP; ++e) U[(long)i * SSA_NP + e] = u[e];
+}
+__global__ void ssa_unit_inv3_kernel(const double* S, double* SI, int32_t* ok, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s[9], si[9];
+  for (int e = 0; e < 9; ++e) s[e] = S[(long)i * 9 + e];
+  ok[i] = ssa_inv3(s, si);
+  for (int e = 0; e < 9; ++e) SI[(long)i * 9 + e] = si[e];
+}
+
 thread_local char g_err[512] = "";
 int set_err(const char* what, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -854,7 +917,7 @@ int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
   p.xt = h->xt; p.x = h->x; p.P = h->P; p.status = h->status; p.infl = h->infl;
   p.actions = h->actions; p.z_noise = h->z_noise;
   p.obs = h->obs; p.dpos = h->dpos; p.dvel = h->dvel; p.spos = h->spos; p.svel = h->svel; p.trace = h->trace;
-  p.z_true = h->z_true; p.y = h->y; p.S = h->S; p.sigmas_h = h->sigmas_h;
+  if (flags & SSA_STEP_RECORD) { p.z_true = h->z_true; p.y = h->y; p.S = h->S; p.sigmas_h = h->sigmas_h; }
   p.visible = h->visible; p.updated = h->updated;
   p.ld = h->ld; p.N = c.n_objects; p.m = c.m; p.flags = flags; p.obs_type = c.obs_type; p.resample = c.resample_after_predict;
   p.dt = c.dt; p.lam = c.lam_plus_n; p.obs_limit = c.obs_limit;
@@ -942,6 +1005,104 @@ int ssa_ukf_fp64_peak(int device, void* stream, double* tflops) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(out);
+  return SSA_OK;
+}
+
+// ---- unit entry points (host buffers in, host buffers out; synchronous) ------------------------------
+static int unit_alloc(const void* host, size_t bytes, void** d) {
+  CK(cudaMalloc(d, bytes ? bytes : 8));
+  if (host) CK(cudaMemcpy(*d, host, bytes, cudaMemcpyHostToDevice));
+  return SSA_OK;
+}
+#define UNIT_BEGIN(device)                                                                                  \
+  int ndev_ = 0;                                                                                            \
+  if (cudaGetDeviceCount(&ndev_) != cudaSuccess || ndev_ == 0) {                                            \
+    snprintf(g_err, sizeof(g_err), "no CUDA device: libssa_ukf has no CPU fallback");                       \
+    return SSA_ENODEV;                                                                                      \
+  }                                                                                                         \
+  CK(cudaSetDevice(device));
+
+int ssa_unit_math(int op, const double* a, const double* b, double* out, int n, int device) {
+  UNIT_BEGIN(device)
+  double *da = nullptr, *db = nullptr, *dout = nullptr;
+  int rc;
+  if ((rc = unit_alloc(a, sizeof(double) * n, (void**)&da))) return rc;
+  if (b && (rc = unit_alloc(b, sizeof(double) * n, (void**)&db))) return rc;
+  if ((rc = unit_alloc(nullptr, sizeof(double) * n, (void**)&dout))) return rc;
+  ssa_unit_math_kernel<<<(n + 127) / 128, 128>>>(op, da, db, dout, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return SSA_OK;
+}
+int ssa_unit_fx(const double* x, double dt, double* out, int32_t* exc, int n, int device) {
+  UNIT_BEGIN(device)
+  double *dx = nullptr, *dout = nullptr; int32_t* dexc = nullptr;
+  int rc;
+  if ((rc = unit_alloc(x, sizeof(double) * 6 * n, (void**)&dx))) return rc;
+  if ((rc = unit_alloc(nullptr, sizeof(double) * 6 * n, (void**)&dout))) return rc;
+  if ((rc = unit_alloc(nullptr, sizeof(int32_t) * n, (void**)&dexc))) return rc;
+  ssa_unit_fx_kernel<<<(n + 127) / 128, 128>>>(dx, dt, dout, dexc, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dout, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(exc, dexc, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dout); cudaFree(dexc);
+  return SSA_OK;
+}
+int ssa_unit_hx_aer(const double* x, int stride, const double M[9], const double obs_itrs[3], const double T[9],
+                    double* out, int n, int device) {
+  UNIT_BEGIN(device)
+  ssa_obs ob;
+  memcpy(ob.M, M, sizeof(ob.M)); memcpy(ob.obs_itrs, obs_itrs, sizeof(ob.obs_itrs)); memcpy(ob.T, T, sizeof(ob.T));
+  double *dx = nullptr, *dout = nullptr;
+  int rc;
+  if ((rc = unit_alloc(x, sizeof(double) * stride * n, (void**)&dx))) return rc;
+  if ((rc = unit_alloc(nullptr, sizeof(double) * 3 * n, (void**)&dout))) return rc;
+  ssa_unit_hx_kernel<<<(n + 127) / 128, 128>>>(dx, ob, dout, n, stride);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dout, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dout);
+  return SSA_OK;
+}
+int ssa_unit_aer(int op, const double* a, const double* b, double* out, int n, int device) {
+  UNIT_BEGIN(device)
+  double *da = nullptr, *db = nullptr, *dout = nullptr;
+  int rc;
+  if ((rc = unit_alloc(a, sizeof(double) * 3 * n, (void**)&da))) return rc;
+  if (b && (rc = unit_alloc(b, sizeof(double) * 3 * n, (void**)&db))) return rc;
+  if ((rc = unit_alloc(nullptr, sizeof(double) * 3 * n, (void**)&dout))) return rc;
+  ssa_unit_aer_kernel<<<(n + 127) / 128, 128>>>(op, da, db, dout, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dout, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return SSA_OK;
+}
+int ssa_unit_robust_chol(const double* P_packed, double lam, double* U_packed, int32_t* ret, int n, int device) {
+  UNIT_BEGIN(device)
+  double *dp = nullptr, *du = nullptr; int32_t* dr = nullptr;
+  int rc;
+  if ((rc = unit_alloc(P_packed, sizeof(double) * 21 * n, (void**)&dp))) return rc;
+  if ((rc = unit_alloc(nullptr, sizeof(double) * 21 * n, (void**)&du))) return rc;
+  if ((rc = unit_alloc(nullptr, sizeof(int32_t) * n, (void**)&dr))) return rc;
+  ssa_unit_chol_kernel<<<(n + 127) / 128, 128>>>(dp, lam, du, dr, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(U_packed, du, sizeof(double) * 21 * n, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ret, dr, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dp); cudaFree(du); cudaFree(dr);
+  return SSA_OK;
+}
+int ssa_unit_inv3(const double* S, double* SI, int32_t* ok, int n, int device) {
+  UNIT_BEGIN(device)
+  double *ds = nullptr, *di = nullptr; int32_t* dk = nullptr;
+  int rc;
+  if ((rc = unit_alloc(S, sizeof(double) * 9 * n, (void**)&ds))) return rc;
+  if ((rc = unit_alloc(nullptr, sizeof(double) * 9 * n, (void**)&di))) return rc;
+  if ((rc = unit_alloc(nullptr, sizeof(int32_t) * n, (void**)&dk))) return rc;
+  ssa_unit_inv3_kernel<<<(n + 127) / 128, 128>>>(ds, di, dk, n);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(SI, di, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ok, dk, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+  cudaFree(ds); cudaFree(di); cudaFree(dk);
   return SSA_OK;
 }
 

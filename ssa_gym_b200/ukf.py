@@ -1,0 +1,196 @@
+"""Host-side mirror of the filter objects of the reference, backed by the CUDA library.
+
+The reference keeps one filterpy `UnscentedKalmanFilter` per RSO (ssa_tasker_simple_2.py:211-218) and
+loops over them in Python.  `BatchedUKF` owns ALL filters of all environments as one device-resident
+struct-of-arrays and advances them with one fused kernel launch per step through the C ABI
+(include/ssa_ukf.h).  Weights, Q and the observer constants are computed here on the host with the
+same Python/numpy expressions filterpy and the reference use, so the device receives bit-identical
+constants (sum(Wm) != 1 must be reproduced, not "fixed").
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .transformations import lla2ecef, trans_uvw_ecef
+
+
+def merwe_weights(n=6, alpha=1e-4, beta=2.0, kappa=-3.0):
+    """filterpy MerweScaledSigmaPoints._compute_weights, same expression order."""
+    lambda_ = alpha ** 2 * (n + kappa) - n
+    c = .5 / (n + lambda_)
+    Wc = np.full(2 * n + 1, c)
+    Wm = np.full(2 * n + 1, c)
+    Wc[0] = lambda_ / (n + lambda_) + (1 - alpha ** 2 + beta)
+    Wm[0] = lambda_ / (n + lambda_)
+    return Wm, Wc, lambda_ + n
+
+
+def Q_discrete_white_noise_block(dt, var, block_size=3):
+    """filterpy.common.Q_discrete_white_noise(dim=2, dt, var, block_size=3, order_by_dim=False) (SS2:110)."""
+    Q2 = np.array([[.25 * dt ** 4, .5 * dt ** 3], [.5 * dt ** 3, dt ** 2]], dtype=float)
+    out = np.zeros((2 * block_size, 2 * block_size))
+    for i in range(2):
+        for j in range(2):
+            out[i * block_size:(i + 1) * block_size, j * block_size:(j + 1) * block_size] = np.eye(block_size) * Q2[i, j]
+    return out * var
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class BatchedUKF:
+    """N = n_envs * m unscented Kalman filters resident on one GPU.
+
+    Parameters mirror the reference's env_config (envs/__init__.py:23-28)."""
+
+    def __init__(self, n_envs, m, dt, Q, R, obs_lla, obs_limit_rad, alpha=1e-4, beta=2.0, kappa=-3.0,
+                 obs_type="aer", reward_type="jones", n_steps=480, resample_after_predict=True, device=0):
+        self.lib = _lib.require_gpu()
+        self.n_envs, self.m, self.N = int(n_envs), int(m), int(n_envs) * int(m)
+        self.device = int(device)
+        Wm, Wc, lam_plus_n = merwe_weights(6, alpha, beta, kappa)
+        self.Wm, self.Wc, self.lam_plus_n = Wm, Wc, lam_plus_n
+        cfg = _lib.SsaUkfCfg()
+        cfg.abi_version = _lib.SSA_UKF_ABI_VERSION
+        cfg.n_objects, cfg.n_envs, cfg.m = self.N, self.n_envs, self.m
+        cfg.obs_type = {"aer": _lib.OBS_AER, "xyz": _lib.OBS_XYZ}[obs_type]
+        cfg.resample_after_predict = 1 if resample_after_predict else 0
+        cfg.reward_type = {"jones": _lib.REWARD_JONES, "trinary": _lib.REWARD_TRINARY, "shaped": _lib.REWARD_SHAPED}[reward_type]
+        cfg.n_steps = int(n_steps)
+        cfg.dt = float(dt)
+        cfg.lam_plus_n = float(lam_plus_n)
+        Q = np.asarray(Q, dtype=np.float64).reshape(6, 6)
+        R = np.asarray(R, dtype=np.float64)
+        if R.ndim == 1:  # tests.py:162 passes a 1-D R: `P += noise_cov` broadcasts it over the rows
+            R = np.tile(R, (3, 1))
+        R = R.reshape(3, 3)
+        obs_lla = np.asarray(obs_lla, dtype=np.float64)
+        self.obs_lla = obs_lla
+        self.obs_itrs = lla2ecef(obs_lla)
+        T = trans_uvw_ecef(obs_lla[0], obs_lla[1])
+        for i in range(13):
+            cfg.Wm[i], cfg.Wc[i] = Wm[i], Wc[i]
+        for i, v in enumerate(Q.ravel()):
+            cfg.Q[i] = v
+        for i, v in enumerate(R.ravel()):
+            cfg.R[i] = v
+        for i in range(3):
+            cfg.obs_itrs[i] = self.obs_itrs[i]
+        for i, v in enumerate(np.asarray(T, dtype=np.float64).ravel()):
+            cfg.T[i] = v
+        cfg.obs_limit = float(obs_limit_rad)
+        self.cfg = cfg
+        self.Q, self.R, self.T = Q, R, T
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.ssa_ukf_create(ctypes.byref(cfg), self.device, ctypes.byref(h)), "ssa_ukf_create")
+        self.h = h
+        self.ld = self.lib.ssa_ukf_ld(h)
+        self._shapes = {
+            _lib.F_X_TRUE: ((self.N, 6), np.float64), _lib.F_X_FILTER: ((self.N, 6), np.float64),
+            _lib.F_P_FILTER: ((self.N, 6, 6), np.float64), _lib.F_OBS: ((self.N, 12), np.float64),
+            _lib.F_DELTA_POS: ((self.N,), np.float64), _lib.F_DELTA_VEL: ((self.N,), np.float64),
+            _lib.F_SIGMA_POS: ((self.N,), np.float64), _lib.F_SIGMA_VEL: ((self.N,), np.float64),
+            _lib.F_TRACE: ((self.N,), np.float64), _lib.F_Z_TRUE: ((self.N, 3), np.float64),
+            _lib.F_Y: ((self.N, 3), np.float64), _lib.F_S: ((self.N, 3, 3), np.float64),
+            _lib.F_SIGMAS_H: ((self.N, 13, 3), np.float64), _lib.F_Z_NOISE: ((self.N, 3), np.float64),
+            _lib.F_VISIBLE: ((self.N,), np.uint8), _lib.F_UPDATED: ((self.N,), np.uint8),
+            _lib.F_STATUS: ((self.N,), np.int32), _lib.F_INFLATIONS: ((self.N,), np.int32),
+            _lib.F_ACTIONS: ((self.n_envs,), np.int32), _lib.F_REWARD: ((self.n_envs,), np.float64),
+            _lib.F_DONE: ((self.n_envs,), np.uint8), _lib.F_GREEDY: ((self.n_envs, _lib.N_TASKERS), np.int32),
+            _lib.F_SCORES: ((self.N, 6), np.float64),
+        }
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ssa_ukf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- state ------------------------------------------------------------------------------------
+    def reset(self, x_true, x_filter, P0, stream=None):
+        x_true = np.ascontiguousarray(x_true, dtype=np.float64).reshape(self.N, 6)
+        x_filter = np.ascontiguousarray(x_filter, dtype=np.float64).reshape(self.N, 6)
+        P0 = np.ascontiguousarray(P0, dtype=np.float64)
+        per_obj = 1 if (P0.size == self.N * 36 and P0.size != 36) else 0
+        if per_obj:
+            P0 = P0.reshape(self.N, 36)
+        else:
+            P0 = P0.reshape(36)
+        _lib.check(self.lib.ssa_ukf_reset(self.h, _ptr(x_true), _ptr(x_filter), _ptr(P0), per_obj, stream), "ssa_ukf_reset")
+
+    def upload(self, field, arr, stream=None):
+        shape, dtype = self._shapes[field]
+        arr = np.ascontiguousarray(arr, dtype=dtype).reshape(shape)
+        _lib.check(self.lib.ssa_ukf_upload(self.h, field, _ptr(arr), arr.nbytes, stream), "ssa_ukf_upload")
+        return arr  # keep alive until the stream has consumed it (async H2D)
+
+    def download(self, field, out=None, stream=None):
+        shape, dtype = self._shapes[field]
+        if out is None:
+            out = np.empty(shape, dtype=dtype)
+        _lib.check(self.lib.ssa_ukf_download(self.h, field, _ptr(out), out.nbytes, stream), "ssa_ukf_download")
+        return out
+
+    def device_ptr(self, field):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _lib.check(self.lib.ssa_ukf_device_ptr(self.h, field, ctypes.byref(p), ctypes.byref(n)), "ssa_ukf_device_ptr")
+        return p.value, n.value
+
+    def torch_view(self, field):
+        """Zero-copy torch tensor over a handle-owned device buffer (AoS fields keep their host shape;
+        SoA fields X_TRUE / X_FILTER / P_FILTER come back as [rows, ld])."""
+        import torch
+        ptr, nbytes = self.device_ptr(field)
+        shape, dtype = self._shapes[field]
+        if field in (_lib.F_X_TRUE, _lib.F_X_FILTER):
+            shape = (6, self.ld)
+        elif field == _lib.F_P_FILTER:
+            shape = (21, self.ld)
+        typestr = {np.dtype(np.float64): "<f8", np.dtype(np.int32): "<i4", np.dtype(np.uint8): "|u1"}[np.dtype(dtype)]
+
+        class _CAI:
+            pass
+        o = _CAI()
+        o.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+        return torch.as_tensor(o, device=torch.device("cuda", self.device))
+
+    # -- the hot path -----------------------------------------------------------------------------
+    def step(self, M, flags, stream=None):
+        M = np.ascontiguousarray(M, dtype=np.float64).reshape(9) if M is not None else None
+        _lib.check(self.lib.ssa_ukf_step(self.h, _ptr(M) if M is not None else None, int(flags), stream), "ssa_ukf_step")
+
+    def predict(self, stream=None):
+        _lib.check(self.lib.ssa_ukf_predict(self.h, stream), "ssa_ukf_predict")
+
+    def update(self, M, all_objects=False, stream=None):
+        M = np.ascontiguousarray(M, dtype=np.float64).reshape(9)
+        _lib.check(self.lib.ssa_ukf_update(self.h, _ptr(M), 1 if all_objects else 0, stream), "ssa_ukf_update")
+
+    def env_reduce(self, step_index, stream=None):
+        _lib.check(self.lib.ssa_ukf_env_reduce(self.h, None, int(step_index), stream), "ssa_ukf_env_reduce")
+
+    def scores(self, stream=None):
+        _lib.check(self.lib.ssa_ukf_scores(self.h, stream), "ssa_ukf_scores")
+        return self.download(_lib.F_SCORES, stream=stream)
+
+    def sync(self, stream=None):
+        _lib.check(self.lib.ssa_ukf_sync(self.h, stream), "ssa_ukf_sync")
+
+    @property
+    def launch_count(self):
+        return int(self.lib.ssa_ukf_launch_count(self.h))
+
+
+def fp64_peak_tflops(device=0, stream=None):
+    lib = _lib.require_gpu()
+    v = ctypes.c_double()
+    _lib.check(lib.ssa_ukf_fp64_peak(int(device), stream, ctypes.byref(v)), "ssa_ukf_fp64_peak")
+    return v.value

@@ -1,0 +1,169 @@
+"""-m gpu: the sm_100a kernels against the host twin — BIT-EXACT, through the C ABI.
+
+The twin (tests/twin/twin.cpp) is the host build of the product's own __host__ __device__ headers; the
+independent oracle checks live in test_gpu_vs_oracle.py / test_twin_vs_oracle.py.  Bit-exactness is the
+bar for every output (float and integer) at BASELINE.json's full C2 size (20 000 objects).
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+from ssa_gym_b200 import _lib
+from ssa_gym_b200.ukf import BatchedUKF
+
+pytestmark = pytest.mark.gpu
+
+F = _lib
+FULL = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE | F.STEP_RECORD
+
+
+def _rng_args(rng, n):
+    return np.concatenate([rng.uniform(-7, 7, n), rng.uniform(-1e3, 1e3, n), rng.standard_normal(n) * 1e-3,
+                           np.pi * np.arange(-8, 9) / 2, [0.0, -0.0, 1.0, -1.0, 0.5, -0.5]])
+
+
+@pytest.mark.parametrize("op", ["sin", "cos", "tan", "atan", "exp", "sinh", "cosh", "tanh", "asinh"])
+def test_math_unary_bitexact(op):
+    x = _rng_args(np.random.default_rng(1), 20000)
+    assert H.bits_equal(H.lib_math("gpu", op, x), H.lib_math("twin", op, x))
+
+
+@pytest.mark.parametrize("op,lo,hi", [("asin", -1, 1), ("acos", -1, 1), ("atanh", -0.999, 0.999), ("log", 1e-300, 1e10),
+                                      ("acosh", 1, 1e6), ("pow23", 1e-9, 1e9)])
+def test_math_domain_bitexact(op, lo, hi):
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.uniform(lo, hi, 20000), [lo, hi], 1 - 10.0 ** rng.uniform(-16, 0, 500) if op in ("asin", "acos") else []])
+    assert H.bits_equal(H.lib_math("gpu", op, x), H.lib_math("twin", op, x))
+
+
+def test_math_binary_bitexact():
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal(50000) * 10.0 ** rng.uniform(-3, 8, 50000)
+    b = rng.standard_normal(50000) * 10.0 ** rng.uniform(-3, 8, 50000)
+    assert H.bits_equal(H.lib_math("gpu", "atan2", a, b), H.lib_math("twin", "atan2", a, b))
+    m = np.full(a.size, 2 * np.pi)
+    assert H.bits_equal(H.lib_math("gpu", "pymod", a, m), H.lib_math("twin", "pymod", a, m))
+    assert np.array_equal(H.lib_math("gpu", "pymod", a, m), a % (2 * np.pi))  # == numpy's python-mod
+
+
+def test_fx_bitexact_catalog():
+    cat, x, _, _ = H.c2_inputs(20000)
+    for dt in (20.0, 600.0, 86400.0):
+        for states in (cat, x):
+            g, ge = H.lib_fx("gpu", states, dt)
+            t, te = H.lib_fx("twin", states, dt)
+            assert H.bits_equal(g, t) and np.array_equal(ge, te)
+
+
+def test_hx_bitexact():
+    cat, x, _, _ = H.c2_inputs(20000)
+    cfg = H.make_cfg(20000)
+    oi, T = np.array(cfg.obs_itrs), np.array(cfg.T)
+    assert H.bits_equal(H.lib_hx("gpu", x, H.CEL2TER06AXY, oi, T), H.lib_hx("twin", x, H.CEL2TER06AXY, oi, T))
+
+
+def _gpu_run(cfg_kwargs, cat, x, P0, zn, flags_seq, actions=None, N=None, E=None, m=None):
+    N = len(cat)
+    ukf = BatchedUKF(n_envs=E or 1, m=m or N, dt=cfg_kwargs.get("dt", 20.0),
+                     Q=np.array(H.make_cfg(N, **cfg_kwargs).Q).reshape(6, 6),
+                     R=np.array(H.make_cfg(N, **cfg_kwargs).R).reshape(3, 3),
+                     obs_lla=[np.radians(H.OBSERVER_DEG[0]), np.radians(H.OBSERVER_DEG[1]), H.OBSERVER_DEG[2]],
+                     obs_limit_rad=np.radians(cfg_kwargs.get("obs_limit_deg", -90.0)),
+                     obs_type=cfg_kwargs.get("obs_type", "aer"), resample_after_predict=cfg_kwargs.get("resample", True))
+    ukf.reset(cat, x, P0)
+    for s, flags in enumerate(flags_seq):
+        if actions is not None:
+            ukf.upload(F.F_ACTIONS, actions[s])
+        ukf.upload(F.F_Z_NOISE, zn[s])
+        ukf.step(H.CEL2TER06AXY, flags)
+    ukf.sync()
+    return ukf
+
+
+def _compare_all(ukf, st, check_update_outputs=True):
+    D = ukf.download
+    assert H.bits_equal(D(F.F_X_TRUE), st.x_true)
+    assert H.bits_equal(D(F.F_X_FILTER), st.x)
+    assert H.bits_equal(H.pack_P(D(F.F_P_FILTER)), H.pack_P(st.P))
+    assert np.array_equal(D(F.F_STATUS), st.status)
+    assert np.array_equal(D(F.F_INFLATIONS), st.infl)
+    assert H.bits_equal(D(F.F_OBS), st.obs)
+    for f, a in ((F.F_DELTA_POS, st.dpos), (F.F_DELTA_VEL, st.dvel), (F.F_SIGMA_POS, st.spos), (F.F_SIGMA_VEL, st.svel),
+                 (F.F_TRACE, st.trace)):
+        assert H.bits_equal(D(f), a)
+    assert np.array_equal(D(F.F_VISIBLE), st.visible)
+    assert np.array_equal(D(F.F_UPDATED), st.updated)
+    if check_update_outputs:
+        upd = st.updated.astype(bool)
+        assert H.bits_equal(D(F.F_Y)[upd], st.y[upd])
+        assert H.bits_equal(D(F.F_S)[upd], st.S[upd])
+        assert H.bits_equal(D(F.F_SIGMAS_H)[upd], st.sigmas_h[upd])
+
+
+@pytest.mark.parametrize("obs_limit_deg", [-90.0, 15.0])
+def test_fused_step_bitexact_c2(obs_limit_deg):
+    """C2: 20 000 objects, fused truth+predict+update+epilogue, 4 steps, all outputs bit-equal to the twin."""
+    N, steps = 20000, 4
+    cat, x, P0, zn = H.c2_inputs(N, steps)
+    kw = dict(obs_limit_deg=obs_limit_deg)
+    cfg = H.make_cfg(N, **kw)
+    st = H.HostState(cat, x, P0)
+    for s in range(steps):
+        H.cpu_step("twin", cfg, st, H.CEL2TER06AXY, FULL, z_noise=zn[s])
+    ukf = _gpu_run(kw, cat, x, P0, zn, [FULL] * steps)
+    _compare_all(ukf, st)
+    ukf.close()
+
+
+def test_split_predict_update_equals_fused():
+    """predict() then update() as two launches (the reference's call structure) == the fused launch."""
+    N, steps = 4096, 3
+    cat, x, P0, zn = H.c2_inputs(N, steps)
+    cfg = H.make_cfg(N)
+    st = H.HostState(cat, x, P0)
+    for s in range(steps):
+        H.cpu_step("twin", cfg, st, H.CEL2TER06AXY, FULL, z_noise=zn[s])
+    seq = []
+    for s in range(steps):
+        seq += [F.STEP_TRUTH | F.STEP_PREDICT, F.STEP_UPDATE_ALL | F.STEP_EPILOGUE | F.STEP_RECORD]
+    zn2 = np.repeat(zn, 2, axis=0)
+    ukf = _gpu_run({}, cat, x, P0, zn2, seq)
+    _compare_all(ukf, st)
+    ukf.close()
+
+
+def test_rl_mode_actions_bitexact():
+    """E envs x m objects, one tasked object per env (SS2:292-315), ragged N (not a multiple of 8/32)."""
+    E, m, steps = 1037, 10, 5
+    N = E * m
+    cat, x, P0, zn = H.c2_inputs(N, steps)
+    rng = np.random.RandomState(5)
+    actions = rng.randint(0, m, size=(steps, E)).astype(np.int32)
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ACT | F.STEP_EPILOGUE | F.STEP_RECORD
+    cfg = H.make_cfg(N, E=E, m=m, obs_limit_deg=10.0)
+    st = H.HostState(cat, x, P0)
+    for s in range(steps):
+        H.cpu_step("twin", cfg, st, H.CEL2TER06AXY, flags, actions=actions[s], z_noise=zn[s])
+    ukf = _gpu_run(dict(obs_limit_deg=10.0), cat, x, P0, zn, [flags] * steps, actions=actions, E=E, m=m)
+    _compare_all(ukf, st, check_update_outputs=False)
+    upd = st.updated.astype(bool)
+    assert 0 < upd.sum() < E  # some tasked objects are below the elevation mask
+    assert H.bits_equal(ukf.download(F.F_Y)[upd], st.y[upd])
+    ukf.close()
+
+
+@pytest.mark.parametrize("obs_type,resample", [("xyz", True), ("aer", False), ("xyz", False)])
+def test_variants_bitexact(obs_type, resample):
+    N, steps = 2048, 3
+    cat, x, P0, zn = H.c2_inputs(N, steps)
+    R = np.diag([125.0] * 3) if obs_type == "xyz" else None
+    kw = dict(obs_type=obs_type, resample=resample, R=R)
+    cfg = H.make_cfg(N, **kw)
+    if obs_type == "xyz":
+        zn = np.random.RandomState(7).normal(size=(steps, N, 3)) * 10.0
+    st = H.HostState(cat, x, P0)
+    for s in range(steps):
+        H.cpu_step("twin", cfg, st, H.CEL2TER06AXY, FULL, z_noise=zn[s])
+    ukf = _gpu_run(kw, cat, x, P0, zn, [FULL] * steps)
+    _compare_all(ukf, st)
+    ukf.close()
