@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -71,8 +72,16 @@ struct KParams {
   double* S;               // [N][9]
   double* sigmas_h;        // [N][39]
   uint8_t* visible; uint8_t* updated;
+  // scratch of the split pipeline (SoA, leading dimension ld)
+  double* U;      // [21][ld] packed Cholesky factor of (lambda+n) P
+  double* F;      // [13][6][ld] propagated sigma points
+  double* ZS;     // [13][3][ld] measurement sigma points
+  double* UVW;    // [13][3][ld] their Cartesian images
+  double* ZT;     // [3][ld] az/el/range of the TRUE state
+  int32_t* code;  // [ld] failure code raised in this step
+  int32_t* exc;   // [ld] OR of the fx exception flags of the 13 sigma points
   long ld;
-  int N, m, flags, obs_type, resample;
+  int N, E, m, flags, obs_type, resample;
   double dt, lam, obs_limit;
   double Wm[13], Wc[13];
   const double* qr;  // device constants: packed Q (21, upper triangle) then R (9, row-major)
@@ -393,6 +402,381 @@ __global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) 
   }
 }
 
+
+// =====================================================================================================
+// Split pipeline (default): five launches per step, each with the thread mapping that suits its stage.
+//   k_factor   one thread per object      robust Cholesky of (lambda+n) P                  -> U
+//   k_fx       one thread per (k, object) fx of sigma point k (k = 13: the TRUE state)     -> F, xt
+//   k_ut       one thread per object      unscented transform, +Q, re-factorisation        -> x, P, U
+//   k_hx       one thread per (k, object) hx of re-drawn sigma point k (k = 13: truth)     -> ZS, UVW, ZT
+//   k_update   one thread per object      S, Pxz, K, state/covariance update, epilogue     -> x, P, obs...
+// Objects are the fastest-varying thread index everywhere, so every load/store of the SoA arrays is a
+// fully coalesced 256-byte warp access; a block of k_fx / k_hx works on ONE sigma index k, so the
+// row-of-U selection is uniform.  All lanes do distinct useful work (no redundant factorisation, no idle
+// lanes), intermediates stay in L2 for C2-sized batches.  The arithmetic of every output element is the
+// same sequence of rounded operations as in the team kernel and the host twin.
+// =====================================================================================================
+constexpr int kSplitThreads = 128;
+
+__global__ void __launch_bounds__(kSplitThreads) k_factor(const KParams p) {
+  const long obj = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (obj >= p.N) return;
+  const long ld = p.ld;
+  const int st = p.status[obj];
+  int code = 0;
+  p.exc[obj] = 0;
+  const bool predict = (p.flags & SSA_STEP_PREDICT) != 0;
+  const bool update = (p.flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT)) != 0;
+  if ((predict || update) && !(st & SSA_ST_FAILED)) {
+    double U[SSA_NP];
+    const int r = ssa_robust_chol6(p.P + obj, ld, p.lam, U);
+    if (r < 0) {
+      code = SSA_ST_LINALG | (predict ? 0 : SSA_ST_IN_UPDATE);
+    } else {
+      if (r > 0 && predict) p.infl[obj] += 1;
+#pragma unroll
+      for (int e = 0; e < SSA_NP; ++e) p.U[e * ld + obj] = U[e];
+    }
+  }
+  p.code[obj] = code;
+}
+
+// sigma point k of object obj from x and the stored factor: s = x +- U[r, :]
+__device__ __forceinline__ void load_sigma(const KParams& p, long obj, int k, const double* x, double* s) {
+  const long ld = p.ld;
+  const int r = (k == 0) ? -1 : (k - 1) % 6;
+  const bool minus = k > 6;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double u = 0.0;
+    if (r >= 0 && r <= j) u = p.U[ssa_pidx(r, j) * ld + obj];
+    s[j] = minus ? (x[j] - u) : (x[j] + u);
+  }
+}
+
+__global__ void __launch_bounds__(kSplitThreads) k_fx(const KParams p) {
+  const long obj = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (obj >= p.N) return;
+  const int k = blockIdx.y;  // uniform per block
+  const long ld = p.ld;
+  double s[6], f[6];
+  if (k == 13) {
+    if (!(p.flags & SSA_STEP_TRUTH)) return;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s[i] = p.xt[i * ld + obj];
+    const int exc = ssa_fx(s, p.dt, f);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) p.xt[i * ld + obj] = f[i];
+    if (exc) atomicOr(p.status + obj, SSA_ST_TRUTHEXC);
+    return;
+  }
+  if (!(p.flags & SSA_STEP_PREDICT)) return;
+  if ((p.status[obj] & SSA_ST_FAILED) || p.code[obj]) return;
+  double x[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = p.x[i * ld + obj];
+  load_sigma(p, obj, k, x, s);
+  const int exc = ssa_fx(s, p.dt, f);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) p.F[(k * 6 + i) * ld + obj] = f[i];
+  if (exc) atomicOr(p.exc + obj, 1);
+}
+
+__device__ __forceinline__ void store_sentinel(const KParams& p, long obj) {
+  const long ld = p.ld;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) p.x[i * ld + obj] = i < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 6; ++j)
+      p.P[ssa_pidx(i, j) * ld + obj] = (i == j) ? (i < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL) : 0.0;
+}
+
+__global__ void __launch_bounds__(kSplitThreads) k_ut(const KParams p) {
+  const long obj = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (obj >= p.N) return;
+  if (!(p.flags & SSA_STEP_PREDICT)) return;
+  const long ld = p.ld;
+  int st = p.status[obj];
+  if (st & SSA_ST_FAILED) return;
+  int code = p.code[obj];
+  if (!code && p.exc[obj]) code = SSA_ST_FXEXC;
+  if (!code) {
+    const double* F = p.F + obj;
+    double xb[6];
+    int nan = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      double acc = ssa_mul(p.Wm[0], F[i * ld]);
+#pragma unroll
+      for (int k = 1; k < SSA_NSIG; ++k) acc = ssa_fma(p.Wm[k], F[(k * 6 + i) * ld], acc);
+      xb[i] = acc;
+      nan |= ssa_isnan(acc);
+    }
+    double Pn[SSA_NP];
+#pragma unroll
+    for (int e = 0; e < SSA_NP; ++e) Pn[e] = 0.0;
+#pragma unroll
+    for (int k = 0; k < SSA_NSIG; ++k) {
+      double y[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) y[i] = F[(k * 6 + i) * ld] - xb[i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j) Pn[ssa_pidx(i, j)] = ssa_fma(y[i], ssa_mul(p.Wc[k], y[j]), Pn[ssa_pidx(i, j)]);
+    }
+#pragma unroll
+    for (int e = 0; e < SSA_NP; ++e) Pn[e] = Pn[e] + __ldg(p.qr + e);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) p.x[i * ld + obj] = xb[i];
+#pragma unroll
+    for (int e = 0; e < SSA_NP; ++e) p.P[e * ld + obj] = Pn[e];
+    if (nan) code |= SSA_ST_NAN;
+    if (p.resample) {
+      double U[SSA_NP];
+      const int r2 = ssa_robust_chol6(Pn, 1, p.lam, U);
+      if (r2 < 0) code |= SSA_ST_LINALG;
+      else {
+        if (r2 > 0) p.infl[obj] += 1;
+#pragma unroll
+        for (int e = 0; e < SSA_NP; ++e) p.U[e * ld + obj] = U[e];
+      }
+    }
+  }
+  if (code) {
+    store_sentinel(p, obj);
+    p.status[obj] = st | SSA_ST_FAILED | code;
+  }
+  p.code[obj] = code;
+}
+
+// object index of update slot `idx` (ALL: identity; ACT: the tasked object of env idx), -1 if none
+__device__ __forceinline__ long upd_object(const KParams& p, long idx) {
+  if (p.flags & SSA_STEP_UPDATE_ALL) return idx < p.N ? idx : -1;
+  if (p.flags & SSA_STEP_UPDATE_ACT) {
+    if (idx >= p.E) return -1;
+    const int a = p.actions[idx];
+    if (a < 0 || a >= p.m) return -1;
+    return idx * (long)p.m + a;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(kSplitThreads) k_hx(const KParams p) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  const long ld = p.ld;
+  if (k == 13) {  // truth measurement of every object: visibility (SS2:418-425) and z_true
+    if (idx >= p.N) return;
+    double xt[3], zt[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) xt[i] = p.xt[i * ld + idx];
+    ssa_hx_aer(xt, &p.ob, zt);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p.ZT[a * ld + idx] = zt[a];
+    p.visible[idx] = (uint8_t)(zt[1] >= p.obs_limit);
+    return;
+  }
+  const long obj = upd_object(p, idx);
+  if (obj < 0) return;
+  if ((p.status[obj] & SSA_ST_FAILED) || p.code[obj]) return;
+  double s[6];
+  if (p.resample || !(p.flags & SSA_STEP_PREDICT) && false) {
+    double x[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = p.x[i * ld + obj];
+    load_sigma(p, obj, k, x, s);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s[i] = p.F[(k * 6 + i) * ld + obj];
+  }
+  double z[3];
+  if (p.obs_type == SSA_OBS_AER) {
+    double uvw[3];
+    ssa_hx_aer(s, &p.ob, z);
+    ssa_aer2uvw(z, uvw);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p.UVW[(k * 3 + a) * ld + obj] = uvw[a];
+  } else {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) z[a] = s[a];
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) p.ZS[(k * 3 + a) * ld + obj] = z[a];
+}
+
+__global__ void __launch_bounds__(kSplitThreads) k_update(const KParams p) {
+  const long obj = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (obj >= p.N) return;
+  const long ld = p.ld;
+  const int flags = p.flags;
+  int st = p.status[obj];
+  bool want_upd = (flags & SSA_STEP_UPDATE_ALL) != 0;
+  if (flags & SSA_STEP_UPDATE_ACT) want_upd = want_upd || (p.actions[obj / p.m] == (int)(obj % p.m));
+  const bool want_meas = want_upd || (flags & SSA_STEP_EPILOGUE);
+  int updated = 0;
+  int code = 0;
+  if (want_upd && !(st & SSA_ST_FAILED)) {
+    double zt[3];
+    const int visible = p.visible[obj];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) zt[a] = (p.obs_type == SSA_OBS_AER) ? p.ZT[a * ld + obj] : p.xt[a * ld + obj];
+    if (p.z_true) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) p.z_true[obj * 3 + a] = zt[a];
+    }
+    if (p.code[obj]) {
+      code = p.code[obj];  // stand-alone update whose factorisation failed
+    } else if (visible) {
+      double x[6], z[3], zp[3];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) x[i] = p.x[i * ld + obj];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) z[a] = zt[a] + (p.z_noise ? p.z_noise[obj * 3 + a] : 0.0);
+      const double* ZS = p.ZS + obj;
+      if (p.obs_type == SSA_OBS_AER) {
+        const double* UV = p.UVW + obj;
+        double zm[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          double acc = ssa_mul(p.Wm[0], UV[a * ld]);
+#pragma unroll
+          for (int k = 1; k < SSA_NSIG; ++k) acc = ssa_fma(p.Wm[k], UV[(k * 3 + a) * ld], acc);
+          zm[a] = acc;
+        }
+        ssa_uvw2aer(zm, zp);
+      } else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          double acc = ssa_mul(p.Wm[0], ZS[a * ld]);
+#pragma unroll
+          for (int k = 1; k < SSA_NSIG; ++k) acc = ssa_fma(p.Wm[k], ZS[(k * 3 + a) * ld], acc);
+          zp[a] = acc;
+        }
+      }
+      double Ss[9], Pxz[18];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Ss[e] = 0.0;
+#pragma unroll
+      for (int e = 0; e < 18; ++e) Pxz[e] = 0.0;
+      const bool from_f = !p.resample;
+#pragma unroll 1
+      for (int k = 0; k < SSA_NSIG; ++k) {
+        double zk[3], rz[3], sk[6];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) zk[a] = ZS[(k * 3 + a) * ld];
+        if (p.obs_type == SSA_OBS_AER) ssa_residual_aer(zk, zp, rz);
+        else {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) rz[a] = zk[a] - zp[a];
+        }
+        if (from_f) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) sk[i] = p.F[(k * 6 + i) * ld + obj];
+        } else {
+          load_sigma(p, obj, k, x, sk);
+        }
+        if (p.obs_type == SSA_OBS_AER) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = a; b < 3; ++b) Ss[3 * a + b] = ssa_fma(p.Wc[k], ssa_mul(rz[a], rz[b]), Ss[3 * a + b]);
+        } else {
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) Ss[3 * a + b] = ssa_fma(rz[a], ssa_mul(p.Wc[k], rz[b]), Ss[3 * a + b]);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const double dx = sk[i] - x[i];
+#pragma unroll
+          for (int a = 0; a < 3; ++a) Pxz[3 * i + a] = ssa_fma(p.Wc[k], ssa_mul(dx, rz[a]), Pxz[3 * i + a]);
+        }
+      }
+      double Sm[9], SI[9], yr[3];
+      if (p.obs_type == SSA_OBS_AER) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = a; b < 3; ++b) {
+            Sm[3 * a + b] = Ss[3 * a + b] + __ldg(p.qr + 21 + 3 * a + b);
+            Sm[3 * b + a] = Ss[3 * a + b] + __ldg(p.qr + 21 + 3 * b + a);
+          }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Sm[e] = Ss[e] + __ldg(p.qr + 21 + e);
+      }
+      const int ok = ssa_inv3(Sm, SI);
+      if (p.obs_type == SSA_OBS_AER) ssa_residual_aer(z, zp, yr);
+      else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) yr[a] = z[a] - zp[a];
+      }
+      double K[18], T[18];
+      int nan = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+          K[3 * i + a] = ssa_fma(Pxz[3 * i + 2], SI[6 + a], ssa_fma(Pxz[3 * i + 1], SI[3 + a], ssa_mul(Pxz[3 * i], SI[a])));
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+          T[a * 6 + i] = ssa_fma(Sm[3 * a + 2], K[3 * i + 2], ssa_fma(Sm[3 * a + 1], K[3 * i + 1], ssa_mul(Sm[3 * a], K[3 * i])));
+        const double xn = x[i] + ssa_fma(K[3 * i + 2], yr[2], ssa_fma(K[3 * i + 1], yr[1], ssa_mul(K[3 * i], yr[0])));
+        nan |= ssa_isnan(xn);
+        p.x[i * ld + obj] = xn;
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 6; ++j) {
+          const int e = ssa_pidx(i, j);
+          const double kt = ssa_fma(K[3 * i + 2], T[12 + j], ssa_fma(K[3 * i + 1], T[6 + j], ssa_mul(K[3 * i], T[j])));
+          p.P[e * ld + obj] = p.P[e * ld + obj] - kt;
+        }
+      if (p.y) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) p.y[obj * 3 + a] = yr[a];
+      }
+      if (p.S) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) p.S[obj * 9 + e] = Sm[e];
+      }
+      if (p.sigmas_h) {
+#pragma unroll 1
+        for (int e = 0; e < 39; ++e) p.sigmas_h[obj * 39 + e] = ZS[e * ld];
+      }
+      updated = 1;
+      if (!ok) code = SSA_ST_LINALG | SSA_ST_IN_UPDATE;
+      else if (nan) code = SSA_ST_NAN | SSA_ST_IN_UPDATE;
+    }
+    if (code) {
+      store_sentinel(p, obj);
+      st |= SSA_ST_FAILED | code;
+      p.status[obj] = st;
+    }
+  }
+  if (p.updated) p.updated[obj] = (uint8_t)updated;
+  (void)want_meas;
+  if (flags & SSA_STEP_EPILOGUE) {
+    double x[6], xt[6], dg[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { x[i] = p.x[i * ld + obj]; xt[i] = p.xt[i * ld + obj]; dg[i] = p.P[ssa_pidx(i, i) * ld + obj]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { p.obs[obj * 12 + i] = x[i]; p.obs[obj * 12 + 6 + i] = dg[i]; }
+    const double d0 = x[0] - xt[0], d1 = x[1] - xt[1], d2 = x[2] - xt[2];
+    const double d3 = x[3] - xt[3], d4 = x[4] - xt[4], d5 = x[5] - xt[5];
+    p.dpos[obj] = ssa_sqrt(ssa_fma(d2, d2, ssa_fma(d1, d1, ssa_mul(d0, d0))));
+    p.dvel[obj] = ssa_sqrt(ssa_fma(d5, d5, ssa_fma(d4, d4, ssa_mul(d3, d3))));
+    p.spos[obj] = ssa_sqrt((dg[0] + dg[1]) + dg[2]);
+    p.svel[obj] = ssa_sqrt((dg[3] + dg[4]) + dg[5]);
+    p.trace[obj] = ((((dg[0] + dg[1]) + dg[2]) + dg[3]) + dg[4]) + dg[5];
+  }
+}
+
 // ---- per-environment reductions: reward/done and greedy taskers ------------------------------------
 struct EnvParams {
   const double* dpos; const double* dvel; const double* spos; const double* trace;
@@ -668,6 +1052,9 @@ struct ssa_ukf {
   double *obs, *z_noise, *z_true, *y, *S, *sigmas_h, *scores, *reward, *env_stats;
   double* stage;  // staging for AoS<->SoA conversion ([N][39] doubles)
   double* qr;     // packed Q (21) + R (9)
+  double* scratch;  // U[21] F[78] ZS[39] UVW[39] ZT[3] rows of ld doubles
+  int32_t *code, *exc;
+  int use_team;   // SSA_UKF_KERNEL=team selects the fused 16-lane team kernel instead of the split pipeline
   int32_t *status, *infl, *actions, *greedy;
   uint8_t *visible, *updated, *done;
   size_t stage_bytes;
@@ -738,14 +1125,25 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
   }
   h->stage_bytes = (size_t)N * 39 * sizeof(double);
   if ((e = cudaMalloc(&h->stage, h->stage_bytes)) != cudaSuccess) { ssa_ukf_destroy(h); return set_err("cudaMalloc(stage)", e); }
-  if ((e = cudaMalloc(&h->status, sizeof(int32_t) * (2 * ld + E + E * SSA_N_TASKERS))) != cudaSuccess) {
+  if ((e = cudaMalloc(&h->status, sizeof(int32_t) * (4 * ld + E + E * SSA_N_TASKERS))) != cudaSuccess) {
     ssa_ukf_destroy(h);
     return set_err("cudaMalloc(int)", e);
   }
-  cudaMemset(h->status, 0, sizeof(int32_t) * (2 * ld + E + E * SSA_N_TASKERS));
+  cudaMemset(h->status, 0, sizeof(int32_t) * (4 * ld + E + E * SSA_N_TASKERS));
   h->infl = h->status + ld;
-  h->actions = h->infl + ld;
+  h->code = h->infl + ld;
+  h->exc = h->code + ld;
+  h->actions = h->exc + ld;
   h->greedy = h->actions + E;
+  if ((e = cudaMalloc(&h->scratch, sizeof(double) * (size_t)(21 + 78 + 39 + 39 + 3) * ld)) != cudaSuccess) {
+    ssa_ukf_destroy(h);
+    return set_err("cudaMalloc(scratch)", e);
+  }
+  cudaMemset(h->scratch, 0, sizeof(double) * (size_t)(21 + 78 + 39 + 39 + 3) * ld);
+  {
+    const char* kv = getenv("SSA_UKF_KERNEL");
+    h->use_team = (kv && strcmp(kv, "team") == 0) ? 1 : 0;
+  }
   if ((e = cudaMalloc(&h->visible, 2 * ld + E)) != cudaSuccess) { ssa_ukf_destroy(h); return set_err("cudaMalloc(u8)", e); }
   cudaMemset(h->visible, 0, 2 * ld + E);
   h->updated = h->visible + ld;
@@ -759,6 +1157,7 @@ int ssa_ukf_destroy(ssa_ukf* h) {
   cudaSetDevice(h->device);
   cudaFree(h->slab);
   cudaFree(h->stage);
+  cudaFree(h->scratch);
   cudaFree(h->status);
   cudaFree(h->visible);
   delete h;
@@ -919,6 +1318,8 @@ int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
   p.obs = h->obs; p.dpos = h->dpos; p.dvel = h->dvel; p.spos = h->spos; p.svel = h->svel; p.trace = h->trace;
   if (flags & SSA_STEP_RECORD) { p.z_true = h->z_true; p.y = h->y; p.S = h->S; p.sigmas_h = h->sigmas_h; }
   p.visible = h->visible; p.updated = h->updated;
+  p.U = h->scratch; p.F = p.U + 21 * h->ld; p.ZS = p.F + 78 * h->ld; p.UVW = p.ZS + 39 * h->ld; p.ZT = p.UVW + 39 * h->ld;
+  p.code = h->code; p.exc = h->exc; p.E = c.n_envs;
   p.ld = h->ld; p.N = c.n_objects; p.m = c.m; p.flags = flags; p.obs_type = c.obs_type; p.resample = c.resample_after_predict;
   p.dt = c.dt; p.lam = c.lam_plus_n; p.obs_limit = c.obs_limit;
   memcpy(p.Wm, c.Wm, sizeof(p.Wm)); memcpy(p.Wc, c.Wc, sizeof(p.Wc));
@@ -926,9 +1327,21 @@ int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
   if (M) memcpy(p.ob.M, M, sizeof(p.ob.M));
   memcpy(p.ob.obs_itrs, c.obs_itrs, sizeof(p.ob.obs_itrs));
   memcpy(p.ob.T, c.T, sizeof(p.ob.T));
-  const unsigned grid = (unsigned)((c.n_objects + kTeamsPerCta - 1) / kTeamsPerCta);
-  ssa_step_kernel<<<grid, kCtaThreads, 0, st>>>(p);
-  h->launches++;
+  if (h->use_team) {
+    const unsigned grid = (unsigned)((c.n_objects + kTeamsPerCta - 1) / kTeamsPerCta);
+    ssa_step_kernel<<<grid, kCtaThreads, 0, st>>>(p);
+    h->launches++;
+    CK(cudaGetLastError());
+    return SSA_OK;
+  }
+  const unsigned gobj = (unsigned)((c.n_objects + kSplitThreads - 1) / kSplitThreads);
+  const bool predict = flags & SSA_STEP_PREDICT, truth = flags & SSA_STEP_TRUTH;
+  const bool update = flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT), epi = flags & SSA_STEP_EPILOGUE;
+  if (predict || update) { k_factor<<<gobj, kSplitThreads, 0, st>>>(p); h->launches++; }
+  if (predict || truth) { k_fx<<<dim3(gobj, 14), kSplitThreads, 0, st>>>(p); h->launches++; }
+  if (predict) { k_ut<<<gobj, kSplitThreads, 0, st>>>(p); h->launches++; }
+  if (update || epi) { k_hx<<<dim3(gobj, 14), kSplitThreads, 0, st>>>(p); h->launches++; }
+  if (update || epi) { k_update<<<gobj, kSplitThreads, 0, st>>>(p); h->launches++; }
   CK(cudaGetLastError());
   return SSA_OK;
 }

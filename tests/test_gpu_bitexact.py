@@ -13,6 +13,14 @@ from ssa_gym_b200.ukf import BatchedUKF
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(params=["split", "team"], autouse=False)
+def kernel(request, monkeypatch):
+    """Both device implementations of the step: the split five-kernel pipeline (default) and the fused
+    16-lane team kernel (SSA_UKF_KERNEL=team).  The handle reads the variable at creation."""
+    monkeypatch.setenv("SSA_UKF_KERNEL", request.param)
+    return request.param
+
 F = _lib
 FULL = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE | F.STEP_RECORD
 
@@ -101,7 +109,7 @@ def _compare_all(ukf, st, check_update_outputs=True):
 
 
 @pytest.mark.parametrize("obs_limit_deg", [-90.0, 15.0])
-def test_fused_step_bitexact_c2(obs_limit_deg):
+def test_fused_step_bitexact_c2(obs_limit_deg, kernel):
     """C2: 20 000 objects, fused truth+predict+update+epilogue, 4 steps, all outputs bit-equal to the twin."""
     N, steps = 20000, 4
     cat, x, P0, zn = H.c2_inputs(N, steps)
@@ -115,7 +123,7 @@ def test_fused_step_bitexact_c2(obs_limit_deg):
     ukf.close()
 
 
-def test_split_predict_update_equals_fused():
+def test_split_predict_update_equals_fused(kernel):
     """predict() then update() as two launches (the reference's call structure) == the fused launch."""
     N, steps = 4096, 3
     cat, x, P0, zn = H.c2_inputs(N, steps)
@@ -132,7 +140,7 @@ def test_split_predict_update_equals_fused():
     ukf.close()
 
 
-def test_rl_mode_actions_bitexact():
+def test_rl_mode_actions_bitexact(kernel):
     """E envs x m objects, one tasked object per env (SS2:292-315), ragged N (not a multiple of 8/32)."""
     E, m, steps = 1037, 10, 5
     N = E * m
@@ -153,7 +161,7 @@ def test_rl_mode_actions_bitexact():
 
 
 @pytest.mark.parametrize("obs_type,resample", [("xyz", True), ("aer", False), ("xyz", False)])
-def test_variants_bitexact(obs_type, resample):
+def test_variants_bitexact(obs_type, resample, kernel):
     N, steps = 2048, 3
     cat, x, P0, zn = H.c2_inputs(N, steps)
     R = np.diag([125.0] * 3) if obs_type == "xyz" else None
