@@ -30,6 +30,67 @@
 #define SSA_TWOPI   6.28318530717958623200e+00  /* 2*RN(pi), == 2*numpy.pi */
 #define SSA_PIO2    1.57079632679489655800e+00
 
+
+// ---------------------------------------------------------------------------------------------
+// constant table
+// ---------------------------------------------------------------------------------------------
+// sm_100a has no 64-bit immediates: a double literal costs two UMOV/IMAD.MOV instructions every time it
+// is used (measured: ~30 % of the instructions of the first propagation kernel).  Constants of the hot
+// functions therefore live in one __constant__ table and are fetched two at a time by LDCU.128; the host
+// build reads the same values from a static array, so both sides see identical bits.
+#define SSA_KLIST(X)                                                                                   \
+  X(INVPIO2, 6.36619772367581382433e-01) X(RMAGIC, 6755399441055744.0)                                 \
+  X(PIO2_A, 1.57079632679489655800e+00) X(PIO2_B, 6.12323399573676603587e-17)                          \
+  X(PIO2_C, -1.49738490485916983800e-33) X(HALF, 0.5)                                                  \
+  X(S6, 1.58969099521155010221e-10) X(S5, -2.50507602534068634195e-08)                                 \
+  X(S4, 2.75573137070700676789e-06) X(S3, -1.98412698298579493134e-04)                                 \
+  X(S2, 8.33333333332248946124e-03) X(S1, -1.66666666666666324348e-01)                                 \
+  X(C6, -1.13596475577881948265e-11) X(C5, 2.08757232129817482790e-09)                                 \
+  X(C4, -2.75573143513906633035e-07) X(C3, 2.48015872894767294178e-05)                                 \
+  X(C2, -1.38888888888741095749e-03) X(C1, 4.16666666666666019037e-02)                                 \
+  X(AT10, 1.62858201153657823623e-02) X(AT8, 4.97687799461593236017e-02)                               \
+  X(AT6, 6.66107313738753120669e-02) X(AT4, 9.09088713343650656196e-02)                                \
+  X(AT2, 1.42857142725034663711e-01) X(AT0, 3.33333333333329318027e-01)                                \
+  X(AT9, -3.65315727442169155270e-02) X(AT7, -5.83357013379057348645e-02)                              \
+  X(AT5, -7.69187620504482999495e-02) X(AT3, -1.11111104054623557880e-01)                              \
+  X(AT1, -1.99999999998764832476e-01) X(PI_LO, 1.2246467991473531772e-16)                              \
+  X(ATHI0, 4.63647609000806093515e-01) X(ATLO0, 2.26987774529616870924e-17)                            \
+  X(ATHI1, 7.85398163397448278999e-01) X(ATLO1, 3.06161699786838301793e-17)                            \
+  X(ATHI2, 9.82793723247329054082e-01) X(ATLO2, 1.39033110312309984516e-17)                            \
+  X(PI, 3.14159265358979311600e+00) X(TWOPI, 6.28318530717958623200e+00)                               \
+  X(PS5, 3.47933107596021167570e-05) X(PS4, 7.91534994289814532176e-04)                                \
+  X(PS3, -4.00555345006794114027e-02) X(PS2, 2.01212532134862925881e-01)                               \
+  X(PS1, -3.25565818622400915405e-01) X(PS0, 1.66666666666666657415e-01)                               \
+  X(QS4, 7.70381505559019352791e-02) X(QS3, -6.88283971605453293030e-01)                               \
+  X(QS2, 2.02094576023350569471e+00) X(QS1, -2.40339491173441421878e+00)                               \
+  X(PIO4_HI, 7.85398163397448278999e-01) X(ONE, 1.0)                                                   \
+  X(MU, 398600441800000.0) X(MU_INV, 1.0 / 398600441800000.0)                                          \
+  X(TOL8, 1e-8) X(NEWTON_TOL, 1.48e-08) X(P2_52, 4503599627370496.0) X(DELTA99, 1.0 - 1e-2)
+
+enum {
+#define SSA_X(n, v) SSA_K_##n,
+  SSA_KLIST(SSA_X)
+#undef SSA_X
+  SSA_K_COUNT
+};
+#if defined(__CUDACC__)
+static __constant__ double ssa_kdev[SSA_K_COUNT] = {
+#define SSA_X(n, v) v,
+    SSA_KLIST(SSA_X)
+#undef SSA_X
+};
+#endif
+static const double ssa_khost[SSA_K_COUNT] = {
+#define SSA_X(n, v) v,
+    SSA_KLIST(SSA_X)
+#undef SSA_X
+};
+#if defined(__CUDA_ARCH__)
+#define SSA_C(n) ssa_kdev[SSA_K_##n]
+#else
+#define SSA_C(n) ssa_khost[SSA_K_##n]
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // primitives
 // ---------------------------------------------------------------------------------------------
@@ -54,16 +115,25 @@ SSA_HD double ssa_add(double a, double b) {
   return a + b;
 #endif
 }
+// Division and square root are real function calls on the device: nvcc expands each `/` and sqrt into
+// ~30 inline instructions plus an out-of-line slow path, and the propagation kernel has dozens of them
+// on its hot path — inlined, the kernel's hot footprint (measured 1.7-6.7 k instructions) overflows the
+// instruction cache and `no_instruction` becomes the top stall reason.  One shared copy keeps the hot
+// code resident.  Both are IEEE-754 correctly rounded, so the host's `/` and sqrt return the same bits.
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ double ssa_div_dev(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __noinline__ double ssa_sqrt_dev(double a) { return __dsqrt_rn(a); }
+#endif
 SSA_HD double ssa_sqrt(double a) {
 #if defined(__CUDA_ARCH__)
-  return __dsqrt_rn(a);
+  return ssa_sqrt_dev(a);
 #else
   return __builtin_sqrt(a);
 #endif
 }
 SSA_HD double ssa_div(double a, double b) {
 #if defined(__CUDA_ARCH__)
-  return __ddiv_rn(a, b);
+  return ssa_div_dev(a, b);
 #else
   return a / b;
 #endif
@@ -104,7 +174,7 @@ SSA_HD double ssa_copysign(double mag, double sgn) {
 // |a/b| >= 2^52 or anything is non-finite.  Checked against numpy.fmod in tests/test_math_accuracy.py.
 SSA_HD double ssa_fmod_pos(double a, double b) {
   const double q0 = ssa_div(a, b);
-  if (!(ssa_fabs(q0) < 4503599627370496.0)) return fmod(a, b);
+  if (!(ssa_fabs(q0) < SSA_C(P2_52))) return fmod(a, b);
   const double q = trunc(q0);
   double r = ssa_fma(-q, b, a);
   if (a >= 0.0) {
@@ -140,29 +210,29 @@ typedef struct { double s, c; } ssa_sc;
 // from ~60 sites and would otherwise exceed the instruction cache several times over.  Results are
 // returned by value so they travel in registers.
 SSA_HD_NOINLINE ssa_sc ssa_sincos_v(double x) {
-  double t = ssa_fma(x, SSA_INVPIO2, SSA_RMAGIC);
+  double t = ssa_fma(x, SSA_C(INVPIO2), SSA_C(RMAGIC));
   int32_t q = ssa_lo32(t);
-  double n = t - SSA_RMAGIC;
-  double r = ssa_fma(-n, SSA_PIO2_A, x);
-  r = ssa_fma(-n, SSA_PIO2_B, r);
-  r = ssa_fma(-n, SSA_PIO2_C, r);
+  double n = t - SSA_C(RMAGIC);
+  double r = ssa_fma(-n, SSA_C(PIO2_A), x);
+  r = ssa_fma(-n, SSA_C(PIO2_B), r);
+  r = ssa_fma(-n, SSA_C(PIO2_C), r);
   double z = ssa_mul(r, r);
   // sin kernel: r + r^3 (S1 + z S2 + ... )
-  double ps = ssa_fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-  ps = ssa_fma(z, ps, 2.75573137070700676789e-06);
-  ps = ssa_fma(z, ps, -1.98412698298579493134e-04);
-  ps = ssa_fma(z, ps, 8.33333333332248946124e-03);
-  ps = ssa_fma(z, ps, -1.66666666666666324348e-01);
+  double ps = ssa_fma(z, SSA_C(S6), SSA_C(S5));
+  ps = ssa_fma(z, ps, SSA_C(S4));
+  ps = ssa_fma(z, ps, SSA_C(S3));
+  ps = ssa_fma(z, ps, SSA_C(S2));
+  ps = ssa_fma(z, ps, SSA_C(S1));
   double sr = ssa_fma(ssa_mul(r, z), ps, r);
   // cos kernel: 1 - z/2 + z^2 (C1 + z C2 + ...)
-  double pc = ssa_fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-  pc = ssa_fma(z, pc, -2.75573143513906633035e-07);
-  pc = ssa_fma(z, pc, 2.48015872894767294178e-05);
-  pc = ssa_fma(z, pc, -1.38888888888741095749e-03);
-  pc = ssa_fma(z, pc, 4.16666666666666019037e-02);
-  double hz = ssa_mul(0.5, z);
-  double w = 1.0 - hz;
-  double cr = w + (((1.0 - w) - hz) + ssa_mul(ssa_mul(z, z), pc));
+  double pc = ssa_fma(z, SSA_C(C6), SSA_C(C5));
+  pc = ssa_fma(z, pc, SSA_C(C4));
+  pc = ssa_fma(z, pc, SSA_C(C3));
+  pc = ssa_fma(z, pc, SSA_C(C2));
+  pc = ssa_fma(z, pc, SSA_C(C1));
+  double hz = ssa_mul(SSA_C(HALF), z);
+  double w = SSA_C(ONE) - hz;
+  double cr = w + (((SSA_C(ONE) - w) - hz) + ssa_mul(ssa_mul(z, z), pc));
   // quadrant
   double s_ = (q & 1) ? cr : sr;
   double c_ = (q & 1) ? sr : cr;
@@ -190,21 +260,22 @@ SSA_HD double ssa_tan(double x) { double s, c; ssa_sincos(x, &s, &c); return ssa
 // ---------------------------------------------------------------------------------------------
 SSA_HD_NOINLINE double ssa_atan2(double y, double x) {
   const double ax = ssa_fabs(x), ay = ssa_fabs(y);
+  const double ay16 = ssa_mul(16.0, ay);
   double num, den, hi, lo;
-  if (ssa_mul(16.0, ay) < ssa_mul(7.0, ax)) {
+  if (ay16 < ssa_mul(7.0, ax)) {
     num = ay; den = ax; hi = 0.0; lo = 0.0;
-  } else if (ssa_mul(16.0, ay) < ssa_mul(11.0, ax)) {
+  } else if (ay16 < ssa_mul(11.0, ax)) {
     num = ssa_fma(2.0, ay, -ax); den = ssa_fma(2.0, ax, ay);
-    hi = 4.63647609000806093515e-01; lo = 2.26987774529616870924e-17;
-  } else if (ssa_mul(16.0, ay) < ssa_mul(19.0, ax)) {
+    hi = SSA_C(ATHI0); lo = SSA_C(ATLO0);
+  } else if (ay16 < ssa_mul(19.0, ax)) {
     num = ay - ax; den = ax + ay;
-    hi = 7.85398163397448278999e-01; lo = 3.06161699786838301793e-17;
-  } else if (ssa_mul(16.0, ay) < ssa_mul(39.0, ax)) {
+    hi = SSA_C(ATHI1); lo = SSA_C(ATLO1);
+  } else if (ay16 < ssa_mul(39.0, ax)) {
     num = ssa_fma(-1.5, ax, ay); den = ssa_fma(1.5, ay, ax);
-    hi = 9.82793723247329054082e-01; lo = 1.39033110312309984516e-17;
+    hi = SSA_C(ATHI2); lo = SSA_C(ATLO2);
   } else {
     num = -ax; den = ay;
-    hi = 1.57079632679489655800e+00; lo = 6.12323399573676603587e-17;
+    hi = SSA_C(PIO2_A); lo = SSA_C(PIO2_B);
   }
   double z;
   if (den == 0.0) {
@@ -213,22 +284,21 @@ SSA_HD_NOINLINE double ssa_atan2(double y, double x) {
     const double t = ssa_div(num, den);
     const double t2 = ssa_mul(t, t);
     const double t4 = ssa_mul(t2, t2);
-    double s1 = ssa_fma(t4, 1.62858201153657823623e-02, 4.97687799461593236017e-02);
-    s1 = ssa_fma(t4, s1, 6.66107313738753120669e-02);
-    s1 = ssa_fma(t4, s1, 9.09088713343650656196e-02);
-    s1 = ssa_fma(t4, s1, 1.42857142725034663711e-01);
-    s1 = ssa_fma(t4, s1, 3.33333333333329318027e-01);
+    double s1 = ssa_fma(t4, SSA_C(AT10), SSA_C(AT8));
+    s1 = ssa_fma(t4, s1, SSA_C(AT6));
+    s1 = ssa_fma(t4, s1, SSA_C(AT4));
+    s1 = ssa_fma(t4, s1, SSA_C(AT2));
+    s1 = ssa_fma(t4, s1, SSA_C(AT0));
     s1 = ssa_mul(t2, s1);
-    double s2 = ssa_fma(t4, -3.65315727442169155270e-02, -5.83357013379057348645e-02);
-    s2 = ssa_fma(t4, s2, -7.69187620504482999495e-02);
-    s2 = ssa_fma(t4, s2, -1.11111104054623557880e-01);
-    s2 = ssa_fma(t4, s2, -1.99999999998764832476e-01);
+    double s2 = ssa_fma(t4, SSA_C(AT9), SSA_C(AT7));
+    s2 = ssa_fma(t4, s2, SSA_C(AT5));
+    s2 = ssa_fma(t4, s2, SSA_C(AT3));
+    s2 = ssa_fma(t4, s2, SSA_C(AT1));
     s2 = ssa_mul(t4, s2);
     // hi - ((t*(s1+s2) - lo) - t)
     z = hi - ((ssa_mul(t, s1 + s2) - lo) - t);
   }
-  const double pi_lo = 1.2246467991473531772e-16;
-  if (ssa_signbit(x)) z = SSA_PI - (z - pi_lo);
+  if (ssa_signbit(x)) z = SSA_C(PI) - (z - SSA_C(PI_LO));
   return ssa_signbit(y) ? -z : z;
 }
 SSA_HD double ssa_atan(double x) { return ssa_atan2(x, 1.0); }
@@ -237,35 +307,33 @@ SSA_HD double ssa_atan(double x) { return ssa_atan2(x, 1.0); }
 // asin / acos — fdlibm rational kernel R(t) = t*P(t)/Q(t)
 // ---------------------------------------------------------------------------------------------
 SSA_HD double ssa_asin_R(double t) {
-  double p = ssa_fma(t, 3.47933107596021167570e-05, 7.91534994289814532176e-04);
-  p = ssa_fma(t, p, -4.00555345006794114027e-02);
-  p = ssa_fma(t, p, 2.01212532134862925881e-01);
-  p = ssa_fma(t, p, -3.25565818622400915405e-01);
-  p = ssa_fma(t, p, 1.66666666666666657415e-01);
+  double p = ssa_fma(t, SSA_C(PS5), SSA_C(PS4));
+  p = ssa_fma(t, p, SSA_C(PS3));
+  p = ssa_fma(t, p, SSA_C(PS2));
+  p = ssa_fma(t, p, SSA_C(PS1));
+  p = ssa_fma(t, p, SSA_C(PS0));
   p = ssa_mul(t, p);
-  double q = ssa_fma(t, 7.70381505559019352791e-02, -6.88283971605453293030e-01);
-  q = ssa_fma(t, q, 2.02094576023350569471e+00);
-  q = ssa_fma(t, q, -2.40339491173441421878e+00);
-  q = ssa_fma(t, q, 1.0);
+  double q = ssa_fma(t, SSA_C(QS4), SSA_C(QS3));
+  q = ssa_fma(t, q, SSA_C(QS2));
+  q = ssa_fma(t, q, SSA_C(QS1));
+  q = ssa_fma(t, q, SSA_C(ONE));
   return ssa_div(p, q);
 }
 SSA_HD_NOINLINE double ssa_asin(double x) {
   const double ax = ssa_fabs(x);
   double res;
-  if (ax < 0.5) {
+  if (ax < SSA_C(HALF)) {
     res = ssa_fma(ax, ssa_asin_R(ssa_mul(ax, ax)), ax);
-  } else if (ax <= 1.0) {
-    // asin(x) = pi/2 - 2*asin(sqrt((1-x)/2)); the sqrt is split s = f + c (f exact in 26 bits... replaced
-    // by an FMA residual) so that pi/2 - 2s is formed without losing the low part of s.
-    const double t = ssa_mul(0.5, 1.0 - ax);
+  } else if (ax <= SSA_C(ONE)) {
+    // asin(x) = pi/2 - 2 asin(sqrt((1-x)/2)); c = (t - s*s)/(2s) is the FMA residual of the square root,
+    // folded in so that pi/2 - 2(s + c)(1 + r) does not lose the low part of s.
+    const double t = ssa_mul(SSA_C(HALF), SSA_C(ONE) - ax);
     const double s = ssa_sqrt(t);
     const double r = ssa_asin_R(t);
-    // c = (t - s*s) / (2s) : correction that makes s+c the sqrt to ~106 bits
     const double c = (s == 0.0) ? 0.0 : ssa_div(ssa_fma(-s, s, t), ssa_add(s, s));
-    // result = pio2_hi - (2*(s + s*r) - pio2_lo) with the correction folded in
-    const double p = ssa_fma(2.0, ssa_mul(s, r), -(6.12323399573676603587e-17 - ssa_mul(2.0, c)));
-    const double q = 7.85398163397448278999e-01 - ssa_mul(2.0, s);
-    res = 7.85398163397448278999e-01 - (p - q);
+    const double p = ssa_fma(2.0, ssa_mul(s, r), -(SSA_C(PIO2_B) - ssa_mul(2.0, c)));
+    const double q = SSA_C(PIO4_HI) - ssa_mul(2.0, s);
+    res = SSA_C(PIO4_HI) - (p - q);
   } else {
     res = ssa_nan();
   }
@@ -273,21 +341,19 @@ SSA_HD_NOINLINE double ssa_asin(double x) {
 }
 SSA_HD_NOINLINE double ssa_acos(double x) {
   const double ax = ssa_fabs(x);
-  if (ax < 0.5) {
+  if (ax < SSA_C(HALF)) {
     const double r = ssa_asin_R(ssa_mul(x, x));
-    return 1.57079632679489655800e+00 - (x - (6.12323399573676603587e-17 - ssa_mul(x, r)));
-  } else if (ax <= 1.0) {
-    const double t = ssa_mul(0.5, 1.0 - ax);
+    return SSA_C(PIO2_A) - (x - (SSA_C(PIO2_B) - ssa_mul(x, r)));
+  } else if (ax <= SSA_C(ONE)) {
+    const double t = ssa_mul(SSA_C(HALF), SSA_C(ONE) - ax);
     const double s = ssa_sqrt(t);
     const double r = ssa_asin_R(t);
     const double c = (s == 0.0) ? 0.0 : ssa_div(ssa_fma(-s, s, t), ssa_add(s, s));
     if (x > 0.0) {
-      // 2*(s + (s*r + c))
-      return ssa_mul(2.0, s + ssa_fma(s, r, c));
+      return ssa_mul(2.0, s + ssa_fma(s, r, c));  // 2*(s + (s*r + c))
     }
-    // pi - 2*(s + (s*r + c)) with pio2_lo folded
-    const double w = ssa_fma(s, r, c) - 6.12323399573676603587e-17;
-    return SSA_PI - ssa_mul(2.0, s + w);
+    const double w = ssa_fma(s, r, c) - SSA_C(PIO2_B);
+    return SSA_C(PI) - ssa_mul(2.0, s + w);
   }
   return ssa_nan();
 }

@@ -36,7 +36,7 @@ SSA_HD void ssa_hx_aer(const double* x, const ssa_obs* o, double* out) {
     e[i] = ssa_fma(o->T[6 + i], d[2], ssa_fma(o->T[3 + i], d[1], ssa_mul(o->T[i], d[0])));
   const double r = ssa_sqrt(ssa_fma(d[2], d[2], ssa_fma(d[1], d[1], ssa_mul(d[0], d[0]))));
   double az = ssa_atan2(e[1], e[0]);
-  if (az < 0.0) az = az + SSA_TWOPI;
+  if (az < 0.0) az = az + SSA_C(TWOPI);
   out[0] = az;
   out[1] = ssa_asin(ssa_div(e[2], r));
   out[2] = r;
@@ -55,7 +55,7 @@ SSA_HD void ssa_aer2uvw(const double* aer, double* uvw) {
 SSA_HD void ssa_uvw2aer(const double* uvw, double* aer) {
   const double r = ssa_sqrt(ssa_fma(uvw[2], uvw[2], ssa_fma(uvw[1], uvw[1], ssa_mul(uvw[0], uvw[0]))));
   double az = ssa_atan2(uvw[1], uvw[0]);
-  if (az < 0.0) az = az + SSA_TWOPI;
+  if (az < 0.0) az = az + SSA_C(TWOPI);
   aer[0] = az;
   aer[1] = ssa_asin(ssa_div(uvw[2], r));
   aer[2] = r;

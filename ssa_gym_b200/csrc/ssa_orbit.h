@@ -65,7 +65,7 @@ SSA_HD double ssa_newton_elliptic(double E0, double M, double ecc) {
     const double fval = ssa_fma(-ecc, s, p0) - M;
     const double fder = ssa_fma(-ecc, c, 1.0);
     const double p = p0 - ssa_div(fval, fder);
-    if (ssa_fabs(p - p0) < 1.48e-08) return p;
+    if (ssa_fabs(p - p0) < SSA_C(NEWTON_TOL)) return p;
     p0 = p;
   }
   return ssa_nan();
@@ -82,10 +82,10 @@ SSA_HD double ssa_newton_hyperbolic(double F0, double M, double ecc) {
   return ssa_nan();
 }
 SSA_HD double ssa_M_to_E(double M, double ecc, int* exc) {
-  if (!(-SSA_PI <= M && M <= SSA_PI)) { *exc = SSA_FX_EXC; return ssa_nan(); }  // assert, l.595
+  if (!(-SSA_C(PI) <= M && M <= SSA_C(PI))) { *exc = SSA_FX_EXC; return ssa_nan(); }  // assert, l.595
   double E0;
   if (ecc < 0.8) E0 = M;
-  else E0 = (M > 0.0) ? SSA_PI : ((M < 0.0) ? -SSA_PI : ssa_mul(SSA_PI, M));  // pi*sign(M); sign(0)=0
+  else E0 = (M > 0.0) ? SSA_C(PI) : ((M < 0.0) ? -SSA_C(PI) : ssa_mul(SSA_C(PI), M));  // pi*sign(M); sign(0)=0
   return ssa_newton_elliptic(E0, M, ecc);
 }
 SSA_HD double ssa_M_to_F(double M, double ecc) {
@@ -138,7 +138,7 @@ SSA_HD double ssa_M_to_D_near_parabolic(double M, double ecc, int* exc) {
 // --- time since periapsis <-> true anomaly (farnocchia.py:846-1006) ---------------------------
 SSA_HD double ssa_delta_t_from_nu(double nu, double ecc, double k, double q, int* exc) {
   const double delta = 1e-2;
-  if (!(-SSA_PI <= nu && nu < SSA_PI)) { *exc = SSA_FX_EXC; return ssa_nan(); }  // assert, l.870
+  if (!(-SSA_C(PI) <= nu && nu < SSA_C(PI))) { *exc = SSA_FX_EXC; return ssa_nan(); }  // assert, l.870
   const double q3 = ssa_mul(ssa_mul(q, q), q);
   double M, n;
   if (ecc < 1.0 - delta) {
@@ -187,7 +187,7 @@ SSA_HD double ssa_delta_t_from_nu(double nu, double ecc, double k, double q, int
   return ssa_div(M, n);
 }
 
-SSA_HD double ssa_wrap_pi(double a) { return ssa_pymod(a + SSA_PI, SSA_TWOPI) - SSA_PI; }
+SSA_HD double ssa_wrap_pi(double a) { return ssa_pymod(a + SSA_C(PI), SSA_C(TWOPI)) - SSA_C(PI); }
 
 SSA_HD double ssa_nu_from_delta_t(double delta_t, double ecc, double k, double q, int* exc) {
   const double delta = 1e-2;
@@ -240,9 +240,9 @@ SSA_HD double ssa_nu_from_delta_t(double delta_t, double ecc, double k, double q
 // --- the propagator -----------------------------------------------------------------------------
 // coe[6] = p, ecc, inc, raan, argp, nu  (farnocchia.py:164-313)
 SSA_HD int ssa_rv2coe(const double* x, double* coe) {
-  const double k = SSA_MU;
-  const double kinv = 1.0 / SSA_MU;
-  const double tol = 1e-8;
+  const double k = SSA_C(MU);
+  const double kinv = SSA_C(MU_INV);
+  const double tol = SSA_C(TOL8);
   const double* r = x;
   const double* v = x + 3;
   double h[3];
@@ -270,7 +270,7 @@ SSA_HD int ssa_rv2coe(const double* x, double* coe) {
   double raan, argp, nu;
   if (equatorial && !circular) {
     raan = 0.0;
-    argp = ssa_pymod(ssa_atan2(e[1], e[0]), SSA_TWOPI);
+    argp = ssa_pymod(ssa_atan2(e[1], e[0]), SSA_C(TWOPI));
     // h . cross(e, r) / |h|
     double c[3];
     c[0] = ssa_fma(e[1], r[2], -ssa_mul(e[2], r[1]));
@@ -278,7 +278,7 @@ SSA_HD int ssa_rv2coe(const double* x, double* coe) {
     c[2] = ssa_fma(e[0], r[1], -ssa_mul(e[1], r[0]));
     nu = ssa_atan2(ssa_div(ssa_dot3(h, c), hn), ssa_dot3(r, e));
   } else if (!equatorial && circular) {
-    raan = ssa_pymod(ssa_atan2(nvec1, nvec0), SSA_TWOPI);
+    raan = ssa_pymod(ssa_atan2(nvec1, nvec0), SSA_C(TWOPI));
     argp = 0.0;
     double c[3];  // cross(h, n) = (-hz*hx, -hz*hy, hx^2+hy^2)
     c[0] = -ssa_mul(h[2], h[0]);
@@ -288,7 +288,7 @@ SSA_HD int ssa_rv2coe(const double* x, double* coe) {
   } else if (equatorial && circular) {
     raan = 0.0;
     argp = 0.0;
-    nu = ssa_pymod(ssa_atan2(r[1], r[0]), SSA_TWOPI);
+    nu = ssa_pymod(ssa_atan2(r[1], r[0]), SSA_C(TWOPI));
   } else {
     const double ome2 = ssa_fma(-ecc, ecc, 1.0);
     if (ome2 == 0.0) return SSA_FX_EXC;  // ZeroDivisionError (l.295)
@@ -304,14 +304,14 @@ SSA_HD int ssa_rv2coe(const double* x, double* coe) {
       if (e_ch - e_sh == 0.0) return SSA_FX_EXC;
       nu = ssa_F_to_nu(ssa_mul(ssa_log(ssa_div(e_ch + e_sh, e_ch - e_sh)), 0.5), ecc);
     }
-    raan = ssa_pymod(ssa_atan2(nvec1, nvec0), SSA_TWOPI);
+    raan = ssa_pymod(ssa_atan2(nvec1, nvec0), SSA_C(TWOPI));
     const double px = ssa_fma(r[1], nvec1, ssa_mul(r[0], nvec0));
     double c[3];
     c[0] = -ssa_mul(h[2], h[0]);
     c[1] = -ssa_mul(h[2], h[1]);
     c[2] = ssa_fma(h[1], h[1], ssa_mul(h[0], h[0]));
     const double py = ssa_div(ssa_dot3(r, c), hn);
-    argp = ssa_pymod(ssa_atan2(py, px) - nu, SSA_TWOPI);
+    argp = ssa_pymod(ssa_atan2(py, px) - nu, SSA_C(TWOPI));
   }
   nu = ssa_wrap_pi(nu);
   coe[0] = p; coe[1] = ecc; coe[2] = inc; coe[3] = raan; coe[4] = argp; coe[5] = nu;
@@ -320,7 +320,7 @@ SSA_HD int ssa_rv2coe(const double* x, double* coe) {
 
 // farnocchia.py:100-161 (rv_pqw 14-73, rotation matrices 76-97)
 SSA_HD void ssa_coe2rv(const double* coe, double* out) {
-  const double k = SSA_MU;
+  const double k = SSA_C(MU);
   const double p = coe[0], ecc = coe[1];
   double snu, cnu, sO, cO, si, ci, sw, cw;
   ssa_sincos(coe[5], &snu, &cnu);
@@ -356,9 +356,9 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   }
   const double ecc = coe[1];
   const double q = ssa_div(coe[0], 1.0 + ecc);
-  const double dt0 = ssa_delta_t_from_nu(coe[5], ecc, SSA_MU, q, &exc);
+  const double dt0 = ssa_delta_t_from_nu(coe[5], ecc, SSA_C(MU), q, &exc);
   const double dt1 = dt0 + tof;
-  coe[5] = ssa_nu_from_delta_t(dt1, ecc, SSA_MU, q, &exc);
+  coe[5] = ssa_nu_from_delta_t(dt1, ecc, SSA_C(MU), q, &exc);
   ssa_coe2rv(coe, out);
   return exc;
 }
