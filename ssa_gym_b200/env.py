@@ -1,0 +1,320 @@
+"""Drop-in `SSA_Tasker_Env`: the reference's gym environment with the estimation hot path on the GPU.
+
+Same constructor (`SSA_Tasker_Env(config)`), same `seed / reset / step` API (old 4-tuple gym step), same
+observation / reward / done semantics, same public attributes the agents and scripts read
+(`i, n, m, dt, P_filter, x_filter, x_true, delta_pos, delta_vel, sigma_pos, sigma_vel, rewards, actions,
+failed_filters_id, visible_objects(), action_space, init_seed, ...`) — reference: envs/
+ssa_tasker_simple_2.py:72-434, 834-840.  What changed is WHERE the work runs: the per-RSO Python loop over
+filterpy objects (SS2:265-315) is one fused launch sequence of `libssa_ukf.so` over all m objects
+(ssa_gym_b200/csrc/ssa_ukf.cu); RNG, configuration, failure bookkeeping, reward logic and the history arrays
+stay on the host exactly as in the reference.
+
+The plug points `fx, hx, mean_z, residual_z, msqrt` of env_config are accepted by identity/name and mapped
+to the built-in device operators (ssa_gym_b200/dynamics.py); anything else raises — there is no CPU
+fallback and no per-sigma-point Python callback.
+"""
+import time
+from copy import copy
+from datetime import datetime
+
+import numpy as np
+
+from . import _lib, dynamics
+from .gym_shim import Env, seeding, spaces
+from .transformations import arcsec2rad, deg2rad, gcrs2irts_matrix_b, lla2ecef, load_eop_c04, time_table
+from .ukf import BatchedUKF, Q_discrete_white_noise_block
+
+F = _lib
+
+
+class SSA_Tasker_Env(Env):
+    metadata = {"render.modes": ["live", "none"]}
+    visualization = None
+
+    def __init__(self, config=None):
+        s = time.time()
+        if config is None:
+            from . import env_config
+            config = env_config
+        self.runtime = {'__init__': 0, 'reset': 0, 'step': 0, 'step prep': 0, 'propagate next true state': 0,
+                        'perform predictions': 0, 'update with observation': 0, 'Observations and Reward': 0,
+                        'filter_error': 0, 'visible_objects': 0, 'object_visibility': 0, 'anees': 0,
+                        'failed_filters': 0, 'plot_sigma_delta': 0, 'plot_rewards': 0, 'plot_anees': 0,
+                        'plot_actions': 0, 'all_true_obs': 0, 'plot_visibility': 0, 'predict method': 0}
+        self.t_0 = config.get('t_0', datetime(2020, 5, 4, 0, 0, 0))
+        self.dt = config['time_step']
+        self.n = config['steps']
+        self.m = config['rso_count']
+        self.obs_limit = np.radians(config['obs_limit'])
+        self.obs_returned = config['obs_returned']
+        self.reward_type = config['reward_type']
+        self.orbits = np.asarray(config['orbits'] if config.get('orbits') is not None else _default_orbits())
+        self.obs_lla = np.array(config['observer']) * [deg2rad, deg2rad, 1]
+        self.obs_itrs = lla2ecef(self.obs_lla)
+        self.update_interval = config['update_interval']
+        self.i = 0
+        self.obs_type = config['obs_type']
+        if self.obs_type == 'aer':
+            self.z_sigma = config['z_sigma'] * np.array([arcsec2rad, arcsec2rad, 1])
+        elif self.obs_type == 'xyz':
+            self.z_sigma = np.asarray(config['z_sigma'])
+        else:
+            raise ValueError('Invalid Observation Type: ' + str(config['obs_type']))
+        self.x_sigma = np.array(config['x_sigma'])
+        self.Q = Q_discrete_white_noise_block(self.dt, config['q_sigma'] ** 2, 3)
+        # operator plug points: resolved to device implementations, never called from the hot path
+        self.fx, self.hx = config.get('fx', dynamics.fx_xyz_farnocchia), config.get('hx')
+        self.mean_z, self.residual_z = config.get('mean_z'), config.get('residual_z')
+        self.msqrt = config.get('msqrt', dynamics.robust_cholesky)
+        if self.hx is None:
+            self.hx = dynamics.hx_aer_erfa if self.obs_type == 'aer' else dynamics.hx_xyz
+        dynamics.resolve_operator('fx', self.fx)
+        hx_name = dynamics.resolve_operator('hx', self.hx)
+        dynamics.resolve_operator('mean_z', self.mean_z)
+        dynamics.resolve_operator('residual_z', self.residual_z)
+        dynamics.resolve_operator('msqrt', self.msqrt)
+        if (hx_name == 'hx_xyz') != (self.obs_type == 'xyz'):
+            raise ValueError("env_config['hx'] and env_config['obs_type'] disagree")
+        self.alpha, self.beta, self.kappa = config['alpha'], config['beta'], config['kappa']
+
+        x_dim, z_dim = 6, 3
+        self.P_0 = np.copy(np.diag(self.x_sigma ** 2)) if config.get('P_0') is None else np.copy(config['P_0'])
+        self.R = np.diag(self.z_sigma ** 2) if config.get('R') is None else np.copy(config['R'])
+        n, m = self.n, self.m
+        self.x_true = np.empty((n, m, x_dim))
+        self.x_filter = np.empty((n, m, x_dim))
+        self.P_filter = np.empty((n, m, x_dim, x_dim))
+        self.obs = np.empty((n, m, x_dim * 2))
+        self.time = time_table(self.t_0, self.dt, n)
+        if config.get('trans_matrix') is not None:
+            self.trans_matrix = np.ascontiguousarray(config['trans_matrix'], dtype=np.float64)
+            assert self.trans_matrix.shape == (n, 3, 3), "trans_matrix must be [steps, 3, 3]"
+        else:
+            self.eops = load_eop_c04(config['eop_file']) if config.get('eop_file') else None
+            self.trans_matrix = np.ascontiguousarray(gcrs2irts_matrix_b(self.time, self.eops))
+        self.z_noise = np.empty((n, m, z_dim))
+        self.z_true = np.empty((n, m, z_dim))
+        self.y = np.empty((n, m, z_dim))
+        self.S = np.empty((n, m, z_dim, z_dim))
+        self.x_noise = np.empty((m, x_dim))
+        self.delta_pos = np.empty((n, m))
+        self.delta_vel = np.empty((n, m))
+        self.sigma_pos = np.empty((n, m))
+        self.sigma_vel = np.empty((n, m))
+        self.scores = np.empty((n, m))
+        self.rewards = np.empty(n)
+        self.failed_filters_id = []
+        self.failed_filters_msg = ["None"] * m
+        self.actions = np.empty(n, dtype=int)
+        self.obs_taken = np.empty(n, dtype=bool)
+        self.x_failed = np.array([1e20, 1e20, 1e20, 1e12, 1e12, 1e12])
+        self.P_failed = np.diag([1e20, 1e20, 1e20, 1e12, 1e12, 1e12])
+        self.nees = np.empty((n, m))
+        self.visibility = []
+        self.sigmas_h = np.empty((n, x_dim * 2 + 1, z_dim))
+        self._visible_now = np.zeros(m, dtype=bool)
+
+        self.action_space = spaces.Discrete(m)
+        if self.obs_returned == 'flatten':
+            self.observation_space = spaces.Box(low=np.tile(-np.inf, (m * 12)), high=np.tile(np.inf, (m * 12)), dtype=np.float64)
+        elif self.obs_returned == 'aer':
+            self.observation_space = spaces.Box(low=np.tile(-np.inf, (m * 4)), high=np.tile(np.inf, (m * 4)), dtype=np.float64)
+            self.observation = np.zeros(m * 4)
+        else:
+            self.observation_space = spaces.Box(low=np.tile(-np.inf, (m, 12)), high=np.tile(np.inf, (m, 12)), dtype=np.float64)
+
+        # the device-resident filters: one handle for the m RSOs of this environment
+        self.ukf = BatchedUKF(n_envs=1, m=m, dt=self.dt, Q=self.Q, R=self.R, obs_lla=self.obs_lla,
+                              obs_limit_rad=self.obs_limit, alpha=self.alpha, beta=self.beta, kappa=self.kappa,
+                              obs_type=self.obs_type, reward_type=self.reward_type, n_steps=n,
+                              resample_after_predict=config.get('resample_after_predict', True),
+                              device=config.get('device', 0))
+        self.np_random = None
+        self.init_seed = self.seed()
+        self.reset()
+        self.runtime['__init__'] += time.time() - s
+
+    # ------------------------------------------------------------------------------------------------
+    def seed(self, seed=None):
+        self.np_random, seed = seeding.np_random(seed)
+        self.init_seed = seed
+        return [seed]
+
+    def reset(self):
+        s = time.time()
+        self.x_true[:], self.x_filter[:], self.P_filter[:], self.obs[:], self.sigmas_h[:] = [0] * 5
+        self.z_true[:], self.y[:], self.S[:] = np.nan, np.nan, np.nan
+        for j in range(self.m):  # RNG draw order of SS2:206-209
+            self.x_true[0][j] = self.orbits[self.np_random.randint(low=0, high=self.orbits.shape[0]), :]
+            self.x_noise[j] = self.np_random.normal(size=6) * self.x_sigma
+            self.x_filter[0][j] = np.copy(self.x_true[0][j] + self.x_noise[j])
+            self.P_filter[0][j] = np.copy(self.P_0)
+        for i in range(self.n):  # SS2:219-221
+            for j in range(self.m):
+                self.z_noise[i, j] = self.np_random.normal(size=3) * self.z_sigma
+        self.scores[:], self.delta_pos[:], self.delta_vel[:], self.sigma_pos[:], self.sigma_vel[:] = [np.nan] * 5
+        self.actions[:], self.obs_taken[:], self.failed_filters_id, self.visibility = 0, False, [], []
+        self.failed_filters_msg = ["None"] * self.m
+        self.ukf.reset(self.x_true[0], self.x_filter[0], self.P_0)
+        # obs[0], error(x_true[0], obs[0]) and the visibility at step 0: one epilogue-only launch
+        self.ukf.step(self.trans_matrix[0], F.STEP_EPILOGUE)
+        self._pull(0)
+        self.rewards[:] = 0
+        self.i = 0
+        self.runtime['reset'] += time.time() - s
+        if self.obs_returned == 'flatten':
+            return self.obs[0].flatten()
+        elif self.obs_returned == 'aer':
+            self.observation = self.aer_obs(np.zeros(self.m * 4))
+            return self.observation
+        return self.obs[0]
+
+    def _pull(self, i):
+        d = self.ukf.download
+        self.x_true[i] = d(F.F_X_TRUE)
+        self.x_filter[i] = d(F.F_X_FILTER)
+        self.P_filter[i] = d(F.F_P_FILTER)
+        self.obs[i] = d(F.F_OBS)
+        self.delta_pos[i], self.delta_vel[i] = d(F.F_DELTA_POS), d(F.F_DELTA_VEL)
+        self.sigma_pos[i], self.sigma_vel[i] = d(F.F_SIGMA_POS), d(F.F_SIGMA_VEL)
+        self._visible_now = d(F.F_VISIBLE).astype(bool)
+
+    def step(self, a):
+        step_s = time.time()
+        assert self.action_space.contains(a), "%r (%s) invalid" % (a, type(a))
+        self.i += 1
+        i = self.i
+        self.actions[i] = np.copy(a)
+        flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_EPILOGUE | F.STEP_RECORD
+        do_update = (i % self.update_interval) == 0
+        if do_update:
+            flags |= F.STEP_UPDATE_ACT
+        s = time.time()
+        self.ukf.upload(F.F_ACTIONS, np.array([a], dtype=np.int32))
+        self.ukf.upload(F.F_Z_NOISE, self.z_noise[i])
+        self.ukf.step(self.trans_matrix[i], flags)
+        self._pull(i)
+        status = self.ukf.download(F.F_STATUS)
+        self.runtime['perform predictions'] += time.time() - s
+        if np.any(status & F.ST_TRUTHEXC):
+            # the reference propagates an uncaught numba exception out of step() here (SS2:266)
+            raise ArithmeticError("fx raised while propagating a true state")
+        if do_update and not (a in self.failed_filters_id):
+            if not (status[a] & F.ST_FAILED) or (status[a] & F.ST_IN_UPDATE):
+                self.z_true[i, a] = self.ukf.download(F.F_Z_TRUE)[a]
+            if self.ukf.download(F.F_UPDATED)[a]:
+                self.y[i, a] = self.ukf.download(F.F_Y)[a]
+                self.S[i, a] = self.ukf.download(F.F_S)[a]
+                self.sigmas_h[i] = self.ukf.download(F.F_SIGMAS_H)[a]
+                self.obs_taken[i] = True
+        for j in np.where(status & F.ST_FAILED)[0]:
+            if j not in self.failed_filters_id:
+                self.filter_error(int(j), int(status[j]))
+        s = time.time()
+        done = False
+        if self.reward_type == 'jones':
+            if np.max(self.delta_pos[i]) > 5e6:
+                done = True
+                self.rewards[i] = 0
+            elif np.max(self.delta_pos[i]) < 3e4:
+                done = True
+                self.rewards[i] = 1
+            elif i + 1 >= self.n:
+                done = True
+                self.rewards[i] = 0
+            else:
+                done = False
+                self.rewards[i] = 0
+        elif self.reward_type == 'trinary':
+            self.rewards[i] = np.mean(((self.delta_pos[i] < 1e4) * 1 + (self.delta_pos[i] < 1e7) * 1)) / 2
+        elif self.reward_type == 'shaped':
+            if np.max(self.delta_pos[i]) > 5e6:
+                done = True
+                self.rewards[i] = 0
+            elif np.max(self.delta_pos[i]) < 3e4:
+                done = True
+                self.rewards[i] = 1 - np.sum(self.rewards[:i])
+            elif a == np.argmax(self.sigma_pos[i - 1]):
+                self.rewards[i] = 1 / self.n
+            else:
+                self.rewards[i] = -1 / self.n
+        if i + 1 >= self.n:
+            done = True
+        self.runtime['Observations and Reward'] += time.time() - s
+        self.runtime['step'] += time.time() - step_s
+        if self.obs_returned == 'flatten':
+            return self.obs[i].flatten(), self.rewards[i], done, {}
+        elif self.obs_returned == 'aer':
+            self.observation = self.aer_obs(self.observation)
+            return self.observation, np.nan_to_num(self.rewards[i], copy=False, nan=0.5, posinf=0.5, neginf=0.5), done, {}
+        return self.obs[i], np.nan_to_num(self.rewards[i], copy=False, nan=0.5, posinf=0.5, neginf=0.5), done, {}
+
+    def filter_error(self, object_id, status):
+        s = time.time()
+        activity = 'update' if status & F.ST_IN_UPDATE else 'predict'
+        kind = (', LinAlgError. ' if status & F.ST_LINALG else ', %s returned nan. ' % activity if status & F.ST_NAN
+                else ', Unknown. ')
+        prev = max(self.i - 1, 0)
+        err = np.array([np.sqrt(np.sum((self.x_filter[prev, object_id, :3] - self.x_true[prev, object_id, :3]) ** 2)),
+                        np.sqrt(np.sum((self.x_filter[prev, object_id, 3:] - self.x_true[prev, object_id, 3:]) ** 2)),
+                        np.sqrt(np.sum(np.diag(self.P_filter[prev, object_id])[:3])),
+                        np.sqrt(np.sum(np.diag(self.P_filter[prev, object_id])[3:]))])
+        msg = ["".join(['Object ', str(object_id), ' failed on ', activity, ' step ', str(self.i), kind, str(np.round(err, 2))])]
+        self.failed_filters_msg[object_id] = copy(msg)
+        self.failed_filters_id.append(object_id)
+        self.runtime['filter_error'] += time.time() - s
+
+    def render(self, mode='live'):
+        return None  # plotting is out of scope
+
+    def visible_objects(self):
+        s = time.time()
+        viz = np.where(self._visible_now)[0]
+        self.runtime['visible_objects'] += time.time() - s
+        return viz
+
+    def object_visible(self, RSO_ID=[]):
+        if not RSO_ID:
+            print('RSO ID expected, but not supplied')
+            return RSO_ID
+        return self._visible_now[np.asarray(RSO_ID)]
+
+    def object_visibility(self):
+        return self._visible_now.copy()
+
+    def failed_filters(self):
+        if not self.failed_filters_id:
+            print("No failed Objects")
+        else:
+            for rso_id in self.failed_filters_id:
+                print(self.failed_filters_msg[rso_id])
+
+    def aer_obs(self, obs):
+        i = self.i
+        aer = dynamics.hx_aer_erfa(self.x_filter[i], self.trans_matrix[i], self.obs_lla, self.obs_itrs)
+        for j in range(self.m):
+            obs[4 * j: 4 * j + 3] = aer[j]
+            obs[4 * j + 3] = np.trace(self.P_filter[i, j])
+        return np.nan_to_num(obs, copy=False, nan=0.001, posinf=0.001, neginf=0.001)
+
+    def anees(self):
+        delta = self.x_true - self.x_filter
+        for i in range(self.n):
+            for j in range(self.m):
+                self.nees[i, j] = delta[i, j] @ np.linalg.inv(self.P_filter[i, j]) @ delta[i, j]
+        return np.mean(self.nees)
+
+    def close(self):
+        if getattr(self, "ukf", None) is not None:
+            self.ukf.close()
+            self.ukf = None
+
+
+_orbits_cache = {}
+
+
+def _default_orbits():
+    if "o" not in _orbits_cache:
+        from .catalog import synthetic_catalog
+        _orbits_cache["o"] = synthetic_catalog(20000, 0)
+    return _orbits_cache["o"]

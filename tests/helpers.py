@@ -238,3 +238,69 @@ def gpu_available():
         return _lib.load().ssa_ukf_device_count() > 0
     except Exception:
         return False
+
+
+class TwinBackedUKF:
+    """Same interface as ssa_gym_b200.ukf.BatchedUKF, executed by the host twin (tests only).  Lets the tests run
+    the SAME environment code once on the GPU and once on the twin and demand equality of whole episodes."""
+
+    def __init__(self, n_envs, m, dt, Q, R, obs_lla, obs_limit_rad, alpha=1e-4, beta=2.0, kappa=-3.0, obs_type="aer",
+                 reward_type="jones", n_steps=480, resample_after_predict=True, device=0):
+        from ssa_gym_b200 import _lib as F
+        self.F = F
+        self.N, self.m, self.n_envs = n_envs * m, m, n_envs
+        Wm, Wc, lam = merwe_weights(6, alpha, beta, kappa)
+        c = _lib.SsaUkfCfg()
+        c.abi_version, c.n_objects, c.n_envs, c.m = 1, self.N, n_envs, m
+        c.obs_type = {"aer": 0, "xyz": 1}[obs_type]
+        c.resample_after_predict = 1 if resample_after_predict else 0
+        c.reward_type, c.n_steps, c.dt, c.lam_plus_n = 0, n_steps, dt, lam
+        for i in range(13):
+            c.Wm[i], c.Wc[i] = Wm[i], Wc[i]
+        for i, v in enumerate(np.asarray(Q, dtype=float).ravel()):
+            c.Q[i] = v
+        R = np.asarray(R, dtype=float)
+        if R.ndim == 1:
+            R = np.tile(R, (3, 1))
+        for i, v in enumerate(R.ravel()):
+            c.R[i] = v
+        lla = np.asarray(obs_lla, dtype=float)
+        for i, v in enumerate(lla2ecef(lla)):
+            c.obs_itrs[i] = v
+        for i, v in enumerate(np.asarray(trans_uvw_ecef(lla[0], lla[1]), dtype=float).ravel()):
+            c.T[i] = v
+        c.obs_limit = obs_limit_rad
+        self.cfg = c
+        self.st = None
+        self.actions = np.zeros(n_envs, np.int32)
+        self.z_noise = np.zeros((self.N, 3))
+
+    def reset(self, x_true, x_filter, P0, stream=None):
+        self.st = HostState(np.reshape(x_true, (self.N, 6)), np.reshape(x_filter, (self.N, 6)), P0)
+
+    def upload(self, field, arr, stream=None):
+        F = self.F
+        if field == F.F_ACTIONS:
+            self.actions = np.ascontiguousarray(arr, dtype=np.int32).reshape(self.n_envs)
+        elif field == F.F_Z_NOISE:
+            self.z_noise = np.ascontiguousarray(arr, dtype=np.float64).reshape(self.N, 3)
+        else:
+            raise NotImplementedError
+
+    def step(self, M, flags, stream=None):
+        cpu_step("twin", self.cfg, self.st, np.asarray(M, dtype=float).reshape(3, 3), flags, actions=self.actions,
+                 z_noise=self.z_noise)
+
+    def download(self, field, out=None, stream=None):
+        F, st = self.F, self.st
+        m = {F.F_X_TRUE: st.x_true, F.F_X_FILTER: st.x, F.F_P_FILTER: st.P, F.F_OBS: st.obs, F.F_DELTA_POS: st.dpos,
+             F.F_DELTA_VEL: st.dvel, F.F_SIGMA_POS: st.spos, F.F_SIGMA_VEL: st.svel, F.F_TRACE: st.trace,
+             F.F_Z_TRUE: st.z_true, F.F_Y: st.y, F.F_S: st.S, F.F_SIGMAS_H: st.sigmas_h, F.F_VISIBLE: st.visible,
+             F.F_UPDATED: st.updated, F.F_STATUS: st.status, F.F_INFLATIONS: st.infl}
+        return m[field].copy()
+
+    def sync(self, stream=None):
+        pass
+
+    def close(self):
+        pass

@@ -1,0 +1,114 @@
+"""-m gpu: the drop-in environment (ssa_gym_b200.env.SSA_Tasker_Env) — C1 of BASELINE.json.
+
+1. GPU env == the same env class driven by the host twin: whole default episodes (480 steps, m = 10, seed 0,
+   agent_visible_greedy): every action, visibility mask, observation, reward, done and history array EQUAL.
+   This is the bit-exact statement for the integer work (tasking argmax, visibility masks).
+2. GPU env replays the golden episodes built from the reference's own functions (teacher forced; decisions that
+   the reference itself takes on rounding noise are identified as such — see test_oracle_golden.py).
+3. API surface of the reference env: spaces, seed(), reset()/step() return layout, attributes, error behaviour.
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+import ssa_gym_b200
+from ssa_gym_b200 import agents
+from ssa_gym_b200 import env as envmod
+from ssa_gym_b200.transformations import gcrs2irts_matrix_approx, time_table
+
+pytestmark = pytest.mark.gpu
+
+
+def make_env(backend, **over):
+    cfg = dict(ssa_gym_b200.env_config)
+    cfg.update(over)
+    if backend == "twin":
+        real = envmod.BatchedUKF
+        envmod.BatchedUKF = H.TwinBackedUKF
+        try:
+            return envmod.SSA_Tasker_Env(cfg)
+        finally:
+            envmod.BatchedUKF = real
+    return envmod.SSA_Tasker_Env(cfg)
+
+
+def run_episode(env, agent, seed, max_steps=None):
+    env.seed(seed)
+    env.action_space.seed(seed)
+    obs = env.reset()
+    log = {"a": [], "r": [], "d": [], "obs": [obs.copy()], "vis": [env.visible_objects().copy()]}
+    done = False
+    while not done and (max_steps is None or env.i < max_steps):
+        a = int(agent(obs, env))
+        obs, r, done, _ = env.step(a)
+        log["a"].append(a); log["r"].append(float(r)); log["d"].append(bool(done)); log["obs"].append(np.array(obs, copy=True))
+        log["vis"].append(env.visible_objects().copy())
+    return log
+
+
+@pytest.mark.parametrize("over,agent,seed", [
+    ({}, agents.agent_visible_greedy, 0),
+    ({"reward_type": "trinary", "obs_limit": 15, "steps": 480}, agents.agent_visible_greedy, 1),
+    ({"reward_type": "trinary", "obs_limit": 15, "steps": 200, "rso_count": 40}, agents.agent_pos_error_greedy, 2),
+    ({"reward_type": "shaped", "steps": 120, "rso_count": 5, "obs_returned": "aer"}, agents.agent_naive_greedy, 3),
+    ({"reward_type": "trinary", "steps": 100, "rso_count": 20, "obs_returned": "2d", "update_interval": 3}, agents.agent_vel_error_greedy, 4),
+])
+def test_gpu_env_equals_twin_env_full_episode(over, agent, seed):
+    tm = gcrs2irts_matrix_approx(time_table(ssa_gym_b200.env_config["t_0"], 20.0, over.get("steps", 480)))
+    eg = make_env("gpu", trans_matrix=tm, **over)
+    et = make_env("twin", trans_matrix=tm, **over)
+    lg, lt = run_episode(eg, agent, seed), run_episode(et, agent, seed)
+    assert lg["a"] == lt["a"] and lg["d"] == lt["d"]                      # tasking decisions: bit-exact
+    assert all(np.array_equal(u, v) for u, v in zip(lg["vis"], lt["vis"]))  # visibility masks: bit-exact
+    assert H.bits_equal(np.array(lg["r"]), np.array(lt["r"]))
+    assert all(H.bits_equal(u, v) for u, v in zip(lg["obs"], lt["obs"]))
+    k = eg.i + 1
+    for name in ("x_true", "x_filter", "P_filter", "obs", "delta_pos", "delta_vel", "sigma_pos", "sigma_vel"):
+        assert H.bits_equal(getattr(eg, name)[:k], getattr(et, name)[:k]), name
+    assert eg.failed_filters_id == et.failed_filters_id
+    assert np.array_equal(eg.obs_taken[:k], et.obs_taken[:k])
+    assert len(lg["a"]) >= 5
+    eg.close()
+
+
+def test_gpu_env_replays_reference_built_golden_episodes():
+    from test_oracle_golden import _env_cfg, load, replay_golden_episode
+    for name, agent in (("default", agents.agent_visible_greedy), ("mask15_trinary", agents.agent_visible_greedy),
+                        ("naive_greedy", agents.agent_naive_greedy)):
+        g = load(f"golden_env_{name}.npz")
+        cfg = dict(ssa_gym_b200.env_config)
+        cfg.update({k: v for k, v in _env_cfg(g).items()})
+        cfg["trans_matrix"] = g["trans_matrix"]
+        env = envmod.SSA_Tasker_Env(cfg)
+        env.seed(0)
+        env.action_space.seed(0)
+        flips = replay_golden_episode(env, g, agent, lambda e: np.array([np.trace(P) for P in e.P_filter[e.i]]))
+        assert flips <= max(2, len(g["actions"]) // 3), (name, flips)
+        env.close()
+
+
+def test_env_api_surface():
+    cfg = dict(ssa_gym_b200.env_config, steps=30, rso_count=6)
+    env = envmod.SSA_Tasker_Env(cfg)
+    assert env.action_space.n == 6 and env.observation_space.shape == (72,)
+    assert env.seed(5) == [5] and env.init_seed == 5
+    obs = env.reset()
+    assert obs.shape == (72,) and obs.dtype == np.float64
+    assert np.array_equal(obs.reshape(6, 12)[:, :6], env.x_filter[0]) and np.all(obs.reshape(6, 12)[:, 6:] == [1e10] * 3 + [1e4] * 3)
+    out = env.step(env.action_space.sample())
+    assert len(out) == 4 and out[3] == {} and isinstance(out[2], bool)
+    with pytest.raises(AssertionError):
+        env.step(6)
+    with pytest.raises(AssertionError):
+        env.step(2.5)
+    for attr in ("i", "n", "m", "dt", "t_0", "P_filter", "x_filter", "x_true", "delta_pos", "delta_vel", "rewards", "actions",
+                 "failed_filters_id", "init_seed", "z_noise", "trans_matrix", "obs_lla", "obs_itrs", "runtime"):
+        assert hasattr(env, attr)
+    assert env.P_filter.shape == (30, 6, 6, 6) and env.trans_matrix.shape == (30, 3, 3)
+    env.close()
+    for kind, shape in (("aer", (24,)), ("2d", (6, 12))):
+        e2 = envmod.SSA_Tasker_Env(dict(cfg, obs_returned=kind))
+        assert e2.reset().shape == shape and e2.step(1)[0].shape == shape
+        e2.close()
+    with pytest.raises(NotImplementedError):
+        envmod.SSA_Tasker_Env(dict(cfg, fx=lambda x, dt: x))
