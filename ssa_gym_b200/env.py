@@ -246,8 +246,8 @@ class SSA_Tasker_Env(Env):
             return self.obs[i].flatten(), self.rewards[i], done, {}
         elif self.obs_returned == 'aer':
             self.observation = self.aer_obs(self.observation)
-            return self.observation, np.nan_to_num(self.rewards[i], copy=False, nan=0.5, posinf=0.5, neginf=0.5), done, {}
-        return self.obs[i], np.nan_to_num(self.rewards[i], copy=False, nan=0.5, posinf=0.5, neginf=0.5), done, {}
+            return self.observation, np.nan_to_num(self.rewards[i], nan=0.5, posinf=0.5, neginf=0.5), done, {}
+        return self.obs[i], np.nan_to_num(self.rewards[i], nan=0.5, posinf=0.5, neginf=0.5), done, {}
 
     def filter_error(self, object_id, status):
         s = time.time()
