@@ -86,6 +86,8 @@ typedef struct ssa_ukf ssa_ukf; /* opaque handle, owns all device buffers */
  *   Z_TRUE, Y, Z_NOISE double[N][3]      S double[N][3][3]   SIGMAS_H double[N][13][3]
  *   VISIBLE uint8[N] (SS2:418-425)       STATUS int32[N]     INFLATIONS int32[N]
  *   ACTIONS int32[E]  REWARD double[E]  DONE uint8[E]  GREEDY int32[E][SSA_N_TASKERS]
+ *   TRANS_ENV double[E][9] per-env trans_matrix  STEP_INDEX int32[E] per-env step counter i
+ *   ENV_STATS double[E][4] = [max delta_pos, trinary reward, argmax sigma_pos, #visible]
  * Device layouts are struct-of-arrays with leading dimension ssa_ukf_ld(h).        */
 enum ssa_field {
   SSA_F_X_TRUE = 0, SSA_F_X_FILTER = 1, SSA_F_P_FILTER = 2, SSA_F_OBS = 3,
@@ -93,7 +95,7 @@ enum ssa_field {
   SSA_F_Z_TRUE = 9, SSA_F_Y = 10, SSA_F_S = 11, SSA_F_SIGMAS_H = 12, SSA_F_Z_NOISE = 13,
   SSA_F_VISIBLE = 14, SSA_F_STATUS = 15, SSA_F_INFLATIONS = 16,
   SSA_F_ACTIONS = 17, SSA_F_REWARD = 18, SSA_F_DONE = 19, SSA_F_GREEDY = 20, SSA_F_SCORES = 21,
-  SSA_F_UPDATED = 22, SSA_F_COUNT_
+  SSA_F_UPDATED = 22, SSA_F_TRANS_ENV = 23, SSA_F_STEP_INDEX = 24, SSA_F_ENV_STATS = 25, SSA_F_COUNT_
 };
 
 /* heuristic taskers evaluated on the device by ssa_ukf_env_reduce (agents.py) */
@@ -112,6 +114,8 @@ enum ssa_field {
 #define SSA_STEP_UPDATE_ACT 0x8   /* RL mode: update object actions[e] of each env e (SS2:292-315) */
 #define SSA_STEP_EPILOGUE 0x10    /* obs / error / trace / visibility (SS2:320-322, 410-425) */
 #define SSA_STEP_RECORD 0x20      /* also store z_true, y, S, sigmas_h of updated objects (SS2:298-304) */
+#define SSA_STEP_M_PER_ENV 0x40   /* vectorised envs at different step indices: use the uploaded SSA_F_TRANS_ENV
+                                     table (double[E][9], one trans_matrix per environment) instead of M      */
 
 int ssa_ukf_abi_version(void);
 const char* ssa_ukf_last_error(void);
@@ -138,7 +142,9 @@ int ssa_ukf_predict(ssa_ukf* h, void* stream);                      /* truth + p
 int ssa_ukf_update(ssa_ukf* h, const double M[9], int all, void* stream); /* update (all | actions[e]) + epilogue */
 
 /* per-environment reductions: reward / done (SS2:324-354) and the greedy taskers (agents.py).
- * step_index = i after the increment of SS2:259; prev_sigma_argmax is kept on the device for 'shaped'. */
+ * step_index = i after the increment of SS2:259; a negative step_index selects the uploaded per-env
+ * SSA_F_STEP_INDEX table.  'shaped' rewards need the reward history: the device returns ENV_STATS and the
+ * host finishes them (SS2:339-351).                                                                       */
 int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stream);
 /* reward.py score terms from the current covariances: out double[N][6] =
  * [score_scaled_trace_P, score_trace_P, score_scaled_det_P(dt), score_det_P, score_det_pos_P, |dpos|] */

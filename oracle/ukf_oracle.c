@@ -602,7 +602,7 @@ int oracle_step(const ssa_ukf_cfg* cfg, const double* M, int flags, double* x_tr
     o.visible = visible ? visible + n : NULL;
     o.updated = updated ? updated + n : NULL;
     int tasked = actions && (actions[n / m] == (n % m));
-    object_step(cfg, M, flags, tasked, &o);
+    object_step(cfg, (flags & SSA_STEP_M_PER_ENV) ? M + (size_t)(n / m) * 9 : M, flags, tasked, &o);
   }
   return 0;
 }

@@ -64,6 +64,7 @@ struct KParams {
   // inputs
   const int32_t* actions;  // [E]
   const double* z_noise;   // [N][3] AoS
+  const double* Menv;      // [E][9] per-env trans_matrix (SSA_STEP_M_PER_ENV) or null
   // outputs
   double* obs;             // [N][12] AoS
   double* dpos; double* dvel; double* spos; double* svel; double* trace;  // [ld]
@@ -231,7 +232,12 @@ __global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) 
     const bool sigma_lane = do_upd && lane < 13;
 #pragma unroll
     for (int i = 0; i < 6; ++i) hin[i] = sigma_lane ? sg[i] : xt[i];
-    ssa_hx_aer(hin, &p.ob, zk);
+    ssa_obs ob = p.ob;
+    if (p.Menv) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(obj / p.m) * 9 + i];
+    }
+    ssa_hx_aer(hin, &ob, zk);
     // broadcast the truth measurement of lane 13
     double zt[3];
 #pragma unroll
@@ -573,7 +579,12 @@ __global__ void __launch_bounds__(kSplitThreads) k_hx(const KParams p) {
     double xt[3], zt[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) xt[i] = p.xt[i * ld + idx];
-    ssa_hx_aer(xt, &p.ob, zt);
+    ssa_obs ob = p.ob;
+    if (p.Menv) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(idx / p.m) * 9 + i];
+    }
+    ssa_hx_aer(xt, &ob, zt);
 #pragma unroll
     for (int a = 0; a < 3; ++a) p.ZT[a * ld + idx] = zt[a];
     p.visible[idx] = (uint8_t)(zt[1] >= p.obs_limit);
@@ -595,7 +606,12 @@ __global__ void __launch_bounds__(kSplitThreads) k_hx(const KParams p) {
   double z[3];
   if (p.obs_type == SSA_OBS_AER) {
     double uvw[3];
-    ssa_hx_aer(s, &p.ob, z);
+    ssa_obs ob = p.ob;
+    if (p.Menv) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(obj / p.m) * 9 + i];
+    }
+    ssa_hx_aer(s, &ob, z);
     ssa_aer2uvw(z, uvw);
 #pragma unroll
     for (int a = 0; a < 3; ++a) p.UVW[(k * 3 + a) * ld + obj] = uvw[a];
@@ -782,6 +798,7 @@ struct EnvParams {
   const double* dpos; const double* dvel; const double* spos; const double* trace;
   const uint8_t* visible;
   double* reward; uint8_t* done; int32_t* greedy; double* env_stats;  // env_stats[E][4]: max dpos, trinary, argmax spos, n_visible
+  const int32_t* step_idx;  // per-env step counters (used when step_index < 0)
   int E, m, reward_type, n_steps, step_index;
 };
 
@@ -845,6 +862,7 @@ __global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) 
     for (int q = 0; q < 6; ++q) for (int k = 1; k < nw; ++k) sm[q][0] = am_better(sm[q][0], sm[q][k]);
     for (int k = 1; k < nw; ++k) { si[0][0] += si[0][k]; si[1][0] += si[1][k]; si[2][0] |= si[2][k]; }
     const double max_dpos = sm[5][0].v;
+    const int step_i = p.step_index >= 0 ? p.step_index : p.step_idx[e];
     // `if not np.any(visible)` tests the INDEX array: it is also false-y when the only visible
     // object is index 0 (agents.py:37) -> the reference samples a random action; we return -1.
     const int any_vis = si[2][0];
@@ -862,14 +880,14 @@ __global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) 
     if (p.reward_type == SSA_REWARD_JONES) {  // SS2:324-336
       if (max_dpos > 5e6) { done = 1; reward = 0.0; }
       else if (max_dpos < 3e4) { done = 1; reward = 1.0; }
-      else if (p.step_index + 1 >= p.n_steps) { done = 1; reward = 0.0; }
+      else if (step_i + 1 >= p.n_steps) { done = 1; reward = 0.0; }
     } else if (p.reward_type == SSA_REWARD_TRINARY) {  // SS2:337-338
       reward = trinary;
     } else {  // 'shaped' needs the reward history: finished on the host from env_stats (SS2:339-351)
       if (max_dpos > 5e6) { done = 1; reward = 0.0; }
       else if (max_dpos < 3e4) { done = 1; reward = 1.0; }
     }
-    if (p.step_index + 1 >= p.n_steps) done = 1;  // SS2:353-354
+    if (step_i + 1 >= p.n_steps) done = 1;  // SS2:353-354
     p.reward[e] = reward;
     p.done[e] = (uint8_t)done;
   }
@@ -1053,6 +1071,8 @@ struct ssa_ukf {
   double* stage;  // staging for AoS<->SoA conversion ([N][39] doubles)
   double* qr;     // packed Q (21) + R (9)
   double* scratch;  // U[21] F[78] ZS[39] UVW[39] ZT[3] rows of ld doubles
+  double* Menv;     // [E][9]
+  int32_t* step_idx;  // [E]
   int32_t *code, *exc;
   int use_team;   // SSA_UKF_KERNEL=team selects the fused 16-lane team kernel instead of the split pipeline
   int32_t *status, *infl, *actions, *greedy;
@@ -1096,7 +1116,7 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
   const long ld = h->ld;
   // fp64 slab: xt 6, x 6, P 21, dpos dvel spos svel trace 5 (SoA rows of ld) + AoS outputs
   const size_t n_soa = (size_t)(6 + 6 + 21 + 5) * ld;
-  const size_t n_aos = (size_t)N * (12 + 3 + 3 + 3 + 9 + 39 + 6) + (size_t)E * (1 + 4) + 32;
+  const size_t n_aos = (size_t)N * (12 + 3 + 3 + 3 + 9 + 39 + 6) + (size_t)E * (1 + 4 + 9) + 32;
   cudaError_t e = cudaMalloc(&h->slab, (n_soa + n_aos) * sizeof(double));
   if (e != cudaSuccess) { delete h; return set_err("cudaMalloc(slab)", e); }
   cudaMemset(h->slab, 0, (n_soa + n_aos) * sizeof(double));
@@ -1115,6 +1135,7 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
   h->reward = q; q += E;
   h->env_stats = q; q += E * 4;
   h->qr = q; q += 32;
+  h->Menv = q; q += E * 9;
   {
     double qr[30];
     int e2 = 0;
@@ -1125,16 +1146,17 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
   }
   h->stage_bytes = (size_t)N * 39 * sizeof(double);
   if ((e = cudaMalloc(&h->stage, h->stage_bytes)) != cudaSuccess) { ssa_ukf_destroy(h); return set_err("cudaMalloc(stage)", e); }
-  if ((e = cudaMalloc(&h->status, sizeof(int32_t) * (4 * ld + E + E * SSA_N_TASKERS))) != cudaSuccess) {
+  if ((e = cudaMalloc(&h->status, sizeof(int32_t) * (4 * ld + 2 * E + E * SSA_N_TASKERS))) != cudaSuccess) {
     ssa_ukf_destroy(h);
     return set_err("cudaMalloc(int)", e);
   }
-  cudaMemset(h->status, 0, sizeof(int32_t) * (4 * ld + E + E * SSA_N_TASKERS));
+  cudaMemset(h->status, 0, sizeof(int32_t) * (4 * ld + 2 * E + E * SSA_N_TASKERS));
   h->infl = h->status + ld;
   h->code = h->infl + ld;
   h->exc = h->code + ld;
   h->actions = h->exc + ld;
   h->greedy = h->actions + E;
+  h->step_idx = h->greedy + E * SSA_N_TASKERS;
   if ((e = cudaMalloc(&h->scratch, sizeof(double) * (size_t)(21 + 78 + 39 + 39 + 3) * ld)) != cudaSuccess) {
     ssa_ukf_destroy(h);
     return set_err("cudaMalloc(scratch)", e);
@@ -1227,6 +1249,9 @@ static int field_info(ssa_ukf* h, int field, void** p, size_t* bytes, int* soa_c
     case SSA_F_DONE: *p = h->done; *bytes = E; break;
     case SSA_F_GREEDY: *p = h->greedy; *bytes = E * SSA_N_TASKERS * 4; break;
     case SSA_F_SCORES: *p = h->scores; *bytes = N * 6 * 8; break;
+    case SSA_F_TRANS_ENV: *p = h->Menv; *bytes = E * 9 * 8; break;
+    case SSA_F_STEP_INDEX: *p = h->step_idx; *bytes = E * 4; break;
+    case SSA_F_ENV_STATS: *p = h->env_stats; *bytes = E * 4 * 8; break;
     default: snprintf(g_err, sizeof(g_err), "unknown field %d", field); return SSA_EINVAL;
   }
   return SSA_OK;
@@ -1304,7 +1329,7 @@ int ssa_ukf_download(ssa_ukf* h, int field, void* host, size_t bytes, void* stre
 
 int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
   if (!h) return SSA_EINVAL;
-  if ((flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE)) && !M) {
+  if ((flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE)) && !M && !(flags & SSA_STEP_M_PER_ENV)) {
     snprintf(g_err, sizeof(g_err), "trans_matrix required for update/epilogue");
     return SSA_EINVAL;
   }
@@ -1315,6 +1340,7 @@ int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
   const ssa_ukf_cfg& c = h->cfg;
   p.xt = h->xt; p.x = h->x; p.P = h->P; p.status = h->status; p.infl = h->infl;
   p.actions = h->actions; p.z_noise = h->z_noise;
+  p.Menv = (flags & SSA_STEP_M_PER_ENV) ? h->Menv : nullptr;
   p.obs = h->obs; p.dpos = h->dpos; p.dvel = h->dvel; p.spos = h->spos; p.svel = h->svel; p.trace = h->trace;
   if (flags & SSA_STEP_RECORD) { p.z_true = h->z_true; p.y = h->y; p.S = h->S; p.sigmas_h = h->sigmas_h; }
   p.visible = h->visible; p.updated = h->updated;
@@ -1363,6 +1389,7 @@ int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stre
   p.reward = h->reward; p.done = h->done; p.greedy = h->greedy; p.env_stats = h->env_stats;
   p.E = h->cfg.n_envs; p.m = h->cfg.m; p.reward_type = h->cfg.reward_type; p.n_steps = h->cfg.n_steps;
   p.step_index = step_index;
+  p.step_idx = h->step_idx;
   ssa_env_reduce_kernel<<<(unsigned)p.E, 128, 0, st>>>(p);
   h->launches++;
   CK(cudaGetLastError());

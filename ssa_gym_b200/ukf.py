@@ -99,7 +99,8 @@ class BatchedUKF:
             _lib.F_STATUS: ((self.N,), np.int32), _lib.F_INFLATIONS: ((self.N,), np.int32),
             _lib.F_ACTIONS: ((self.n_envs,), np.int32), _lib.F_REWARD: ((self.n_envs,), np.float64),
             _lib.F_DONE: ((self.n_envs,), np.uint8), _lib.F_GREEDY: ((self.n_envs, _lib.N_TASKERS), np.int32),
-            _lib.F_SCORES: ((self.N, 6), np.float64),
+            _lib.F_SCORES: ((self.N, 6), np.float64), _lib.F_TRANS_ENV: ((self.n_envs, 3, 3), np.float64),
+            _lib.F_STEP_INDEX: ((self.n_envs,), np.int32), _lib.F_ENV_STATS: ((self.n_envs, 4), np.float64),
         }
 
     # -- lifetime ---------------------------------------------------------------------------------

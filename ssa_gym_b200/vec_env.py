@@ -1,0 +1,194 @@
+"""Vectorised environments: E independent copies of the reference env advanced by ONE device step.
+
+BASELINE.json config 3 ("4 096 parallel envs x default RSO count feeding an RLlib PPO rollout").  The reference
+has no in-process vectorisation (one env per Ray worker); the shape of the API follows RLlib's
+`VectorEnv` (`vector_reset`, `reset_at`, `vector_step`).  Each environment keeps the reference's semantics exactly:
+its own seeded generator with the reference's draw order (SS2:206-221), its own step counter and therefore its own
+`trans_matrix[i]` (shipped as a per-env table, SSA_STEP_M_PER_ENV), reward / done from `ssa_ukf_env_reduce`
+(SS2:324-354), auto-reset on done.  Environment e of a `VecSSATaskerEnv` seeded with `seeds[e]` produces the same
+episode as a single `SSA_Tasker_Env` seeded the same way (tests/test_gpu_vec_env.py).
+"""
+import numpy as np
+
+from . import _lib, dynamics
+from .gym_shim import seeding, spaces
+from .transformations import arcsec2rad, deg2rad, gcrs2irts_matrix_b, lla2ecef, load_eop_c04, time_table
+from .ukf import BatchedUKF, Q_discrete_white_noise_block
+
+F = _lib
+
+
+class VecSSATaskerEnv:
+    def __init__(self, config, num_envs, seeds=None, device=0, auto_reset=True):
+        self.E = int(num_envs)
+        self.n, self.m, self.dt = config['steps'], config['rso_count'], config['time_step']
+        self.N = self.E * self.m
+        self.obs_limit = np.radians(config['obs_limit'])
+        self.reward_type = config['reward_type']
+        self.obs_type = config['obs_type']
+        self.update_interval = config['update_interval']
+        self.auto_reset = auto_reset
+        if config.get('orbits') is not None:
+            self.orbits = np.asarray(config['orbits'])
+        else:
+            from .env import _default_orbits
+            self.orbits = _default_orbits()
+        self.obs_lla = np.array(config['observer']) * [deg2rad, deg2rad, 1]
+        self.obs_itrs = lla2ecef(self.obs_lla)
+        self.z_sigma = (config['z_sigma'] * np.array([arcsec2rad, arcsec2rad, 1]) if self.obs_type == 'aer'
+                        else np.asarray(config['z_sigma'], dtype=float))
+        self.x_sigma = np.array(config['x_sigma'])
+        self.Q = Q_discrete_white_noise_block(self.dt, config['q_sigma'] ** 2, 3)
+        for role in ('fx', 'hx', 'mean_z', 'residual_z', 'msqrt'):
+            if role in config and not (role in ('mean_z', 'residual_z') and config[role] is None):
+                dynamics.resolve_operator(role, config[role])
+        self.P_0 = np.copy(np.diag(self.x_sigma ** 2)) if config.get('P_0') is None else np.copy(config['P_0'])
+        self.R = np.diag(self.z_sigma ** 2) if config.get('R') is None else np.copy(config['R'])
+        if config.get('trans_matrix') is not None:
+            self.trans_matrix = np.ascontiguousarray(config['trans_matrix'], dtype=np.float64)
+        else:
+            eops = load_eop_c04(config['eop_file']) if config.get('eop_file') else None
+            self.trans_matrix = np.ascontiguousarray(gcrs2irts_matrix_b(time_table(config['t_0'], self.dt, self.n), eops))
+        self.ukf = BatchedUKF(n_envs=self.E, m=self.m, dt=self.dt, Q=self.Q, R=self.R, obs_lla=self.obs_lla,
+                              obs_limit_rad=self.obs_limit, alpha=config['alpha'], beta=config['beta'], kappa=config['kappa'],
+                              obs_type=self.obs_type, reward_type=self.reward_type, n_steps=self.n,
+                              resample_after_predict=config.get('resample_after_predict', True), device=device)
+        self.action_spaces = [spaces.Discrete(self.m) for _ in range(self.E)]
+        self.observation_space = spaces.Box(low=np.tile(-np.inf, (self.m * 12)), high=np.tile(np.inf, (self.m * 12)), dtype=np.float64)
+        self.np_randoms = [None] * self.E
+        self.i = np.zeros(self.E, dtype=np.int32)
+        self.z_noise = np.empty((self.E, self.n, self.m, 3))
+        self.x_true0 = np.empty((self.E, self.m, 6))
+        self.x_filter0 = np.empty((self.E, self.m, 6))
+        self.reward_sum = np.zeros(self.E)           # for 'shaped' (SS2:345)
+        self.prev_spos_argmax = np.zeros(self.E, dtype=np.int64)
+        self.episodes = np.zeros(self.E, dtype=np.int64)
+        self._P0_packed = self.P_0[np.triu_indices(6)]
+        self._views = None
+        self.seed(seeds)
+        self.obs = self.vector_reset()
+
+    # -- seeding / reset --------------------------------------------------------------------------------
+    def seed(self, seeds=None):
+        if seeds is None:
+            seeds = [None] * self.E
+        out = []
+        for e in range(self.E):
+            self.np_randoms[e], s = seeding.np_random(seeds[e])
+            out.append(s)
+        self.init_seeds = out
+        return out
+
+    def _draw(self, e):
+        """The RNG draw sequence of SS2:206-221 for environment e."""
+        rng = self.np_randoms[e]
+        for j in range(self.m):
+            self.x_true0[e, j] = self.orbits[rng.randint(low=0, high=self.orbits.shape[0]), :]
+            noise = rng.normal(size=6) * self.x_sigma
+            self.x_filter0[e, j] = self.x_true0[e, j] + noise
+        # n*m successive normal(size=3) draws consume the stream exactly like one normal(size=(n, m, 3))
+        self.z_noise[e] = rng.normal(size=(self.n, self.m, 3)) * self.z_sigma
+        self.i[e] = 0
+        self.reward_sum[e] = 0.0
+
+    def _dev_views(self):
+        if self._views is None:
+            tv = self.ukf.torch_view
+            self._views = {k: tv(f) for k, f in (("xt", F.F_X_TRUE), ("x", F.F_X_FILTER), ("P", F.F_P_FILTER),
+                                                  ("status", F.F_STATUS), ("infl", F.F_INFLATIONS))}
+        return self._views
+
+    def vector_reset(self):
+        for e in range(self.E):
+            self._draw(e)
+        self.ukf.reset(self.x_true0.reshape(self.N, 6), self.x_filter0.reshape(self.N, 6), self.P_0)
+        self._epilogue_only()
+        return self.ukf.download(F.F_OBS).reshape(self.E, self.m * 12)
+
+    def _epilogue_only(self):
+        self.ukf.upload(F.F_TRANS_ENV, self.trans_matrix[self.i])
+        self.ukf.step(None, F.STEP_EPILOGUE | F.STEP_M_PER_ENV)
+
+    def reset_at(self, e):
+        """Reset environment e only (device state of the other environments is untouched)."""
+        import torch
+        self._draw(e)
+        v = self._dev_views()
+        lo, hi = e * self.m, (e + 1) * self.m
+        dev = v["x"].device
+        v["xt"][:, lo:hi] = torch.from_numpy(np.ascontiguousarray(self.x_true0[e].T)).to(dev)
+        v["x"][:, lo:hi] = torch.from_numpy(np.ascontiguousarray(self.x_filter0[e].T)).to(dev)
+        v["P"][:, lo:hi] = torch.from_numpy(self._P0_packed.copy()).to(dev)[:, None]
+        v["status"][lo:hi] = 0
+        v["infl"][lo:hi] = 0
+        self.episodes[e] += 1
+
+    # -- step ---------------------------------------------------------------------------------------------
+    def vector_step(self, actions):
+        actions = np.ascontiguousarray(actions, dtype=np.int32).reshape(self.E)
+        assert np.all((actions >= 0) & (actions < self.m)), "invalid action"
+        self.i += 1
+        idx = self.i
+        ar = np.arange(self.E)
+        self.ukf.upload(F.F_ACTIONS, actions)
+        self.ukf.upload(F.F_Z_NOISE, self.z_noise[ar, idx].reshape(self.N, 3))
+        self.ukf.upload(F.F_TRANS_ENV, self.trans_matrix[idx])
+        self.ukf.upload(F.F_STEP_INDEX, idx)
+        flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_EPILOGUE | F.STEP_M_PER_ENV
+        if self.update_interval == 1:
+            flags |= F.STEP_UPDATE_ACT
+        elif np.any(idx % self.update_interval == 0):
+            # envs off their update step get an out-of-range action = "task nothing" (upd_object returns -1)
+            a2 = np.where(idx % self.update_interval == 0, actions, -1).astype(np.int32)
+            self.ukf.upload(F.F_ACTIONS, a2)
+            flags |= F.STEP_UPDATE_ACT
+        self.ukf.step(None, flags)
+        self.ukf.env_reduce(step_index=-1)
+        obs = self.ukf.download(F.F_OBS).reshape(self.E, self.m * 12)
+        rewards = self.ukf.download(F.F_REWARD)
+        dones = self.ukf.download(F.F_DONE).astype(bool)
+        if self.reward_type == 'shaped':  # SS2:339-351 needs the reward history: finished on the host
+            stats = self.ukf.download(F.F_ENV_STATS)
+            for e in range(self.E):
+                if stats[e, 0] > 5e6:
+                    rewards[e] = 0
+                elif stats[e, 0] < 3e4:
+                    rewards[e] = 1 - self.reward_sum[e]
+                elif actions[e] == self.prev_spos_argmax[e]:
+                    rewards[e] = 1 / self.n
+                else:
+                    rewards[e] = -1 / self.n
+                self.reward_sum[e] += rewards[e]
+            self.prev_spos_argmax = stats[:, 2].astype(np.int64)
+        infos = [{} for _ in range(self.E)]
+        if self.auto_reset and dones.any():
+            for e in np.where(dones)[0]:
+                infos[e]["terminal_observation"] = obs[e].copy()
+                self.reset_at(int(e))
+            self._epilogue_only()
+            fresh = self.ukf.download(F.F_OBS).reshape(self.E, self.m * 12)
+            obs[dones] = fresh[dones]
+        self.obs = obs
+        return obs, rewards, dones, infos
+
+    # -- device taskers --------------------------------------------------------------------------------------
+    def greedy_actions(self, tasker=F.TASKER_VISIBLE_GREEDY):
+        """agents.py argmax rules evaluated on the device for every env (valid after a step / reset); where the
+        reference would fall back to `env.action_space.sample()` the env's own Discrete space is sampled."""
+        self.ukf.upload(F.F_STEP_INDEX, self.i)
+        self.ukf.env_reduce(step_index=-1)
+        a = self.ukf.download(F.F_GREEDY)[:, tasker].astype(np.int64)
+        for e in np.where(a < 0)[0]:
+            a[e] = self.action_spaces[e].sample()
+        return a
+
+    def visible(self):
+        return self.ukf.download(F.F_VISIBLE).reshape(self.E, self.m).astype(bool)
+
+    def get_unwrapped(self):
+        return [self]
+
+    def close(self):
+        if self.ukf is not None:
+            self.ukf.close()
+            self.ukf = None

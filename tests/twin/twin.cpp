@@ -201,12 +201,14 @@ int twin_step(const ssa_ukf_cfg* cfg, const double* M, int flags, double* x_true
               int32_t* status, int32_t* infl, const int32_t* actions, const double* z_noise, double* obs,
               double* dpos, double* dvel, double* spos, double* svel, double* trace, double* z_true, double* y,
               double* S, double* sigmas_h, uint8_t* visible, uint8_t* updated) {
-  ssa_obs ob;
-  for (int i = 0; i < 9; ++i) { ob.M[i] = M[i]; ob.T[i] = cfg->T[i]; }
-  for (int i = 0; i < 3; ++i) ob.obs_itrs[i] = cfg->obs_itrs[i];
+  ssa_obs ob0;
+  for (int i = 0; i < 9; ++i) { ob0.M[i] = M[i]; ob0.T[i] = cfg->T[i]; }
+  for (int i = 0; i < 3; ++i) ob0.obs_itrs[i] = cfg->obs_itrs[i];
   const int N = cfg->n_objects, m = cfg->m;
 #pragma omp parallel for schedule(dynamic, 64)
   for (int n = 0; n < N; ++n) {
+    ssa_obs ob = ob0;
+    if (flags & SSA_STEP_M_PER_ENV) for (int i = 0; i < 9; ++i) ob.M[i] = M[(size_t)(n / m) * 9 + i];  // M is [E][9]
     ObjIO o;
     o.x_true = x_true + 6 * (size_t)n; o.x = x + 6 * (size_t)n; o.P = P + SSA_NP * (size_t)n;
     o.status = status + n; o.infl = infl + n;
