@@ -60,7 +60,7 @@ class VecSSATaskerEnv:
         self.z_noise = np.empty((self.E, self.n, self.m, 3))
         self.x_true0 = np.empty((self.E, self.m, 6))
         self.x_filter0 = np.empty((self.E, self.m, 6))
-        self.reward_sum = np.zeros(self.E)           # for 'shaped' (SS2:345)
+        self.rewards_hist = np.zeros((self.E, self.n))  # for 'shaped': 1 - np.sum(rewards[:i]) (SS2:345)
         self.prev_spos_argmax = np.zeros(self.E, dtype=np.int64)
         self.episodes = np.zeros(self.E, dtype=np.int64)
         self._P0_packed = self.P_0[np.triu_indices(6)]
@@ -89,7 +89,8 @@ class VecSSATaskerEnv:
         # n*m successive normal(size=3) draws consume the stream exactly like one normal(size=(n, m, 3))
         self.z_noise[e] = rng.normal(size=(self.n, self.m, 3)) * self.z_sigma
         self.i[e] = 0
-        self.reward_sum[e] = 0.0
+        self.rewards_hist[e] = 0.0
+        self.prev_spos_argmax[e] = 0  # argmax of the (all equal) sigma_pos[0]
 
     def _dev_views(self):
         if self._views is None:
@@ -153,12 +154,12 @@ class VecSSATaskerEnv:
                 if stats[e, 0] > 5e6:
                     rewards[e] = 0
                 elif stats[e, 0] < 3e4:
-                    rewards[e] = 1 - self.reward_sum[e]
+                    rewards[e] = 1 - np.sum(self.rewards_hist[e, :idx[e]])
                 elif actions[e] == self.prev_spos_argmax[e]:
                     rewards[e] = 1 / self.n
                 else:
                     rewards[e] = -1 / self.n
-                self.reward_sum[e] += rewards[e]
+                self.rewards_hist[e, idx[e]] = rewards[e]
             self.prev_spos_argmax = stats[:, 2].astype(np.int64)
         infos = [{} for _ in range(self.E)]
         if self.auto_reset and dones.any():
