@@ -117,6 +117,7 @@ def run_oracle_steps(cfg, cat, x, P0, zn, n_steps, budget_s=None):
     """Time the CPU oracle (all host threads) on the workload.  Returns (units/s, steps run, threads)."""
     L = oracle_lib()
     L.oracle_num_threads.restype = ctypes.c_int
+    L.oracle_set_threads(ctypes.c_int(os.cpu_count() or 1))  # torchrun exports OMP_NUM_THREADS=1: use all host threads
     N = len(cat)
     vp = ctypes.c_void_p
     ptr = lambda a: a.ctypes.data_as(vp)
@@ -265,6 +266,15 @@ def main():
     status = ukf.download(F.F_STATUS)
     n_failed = int((status & 1).sum())
 
+    # per-kernel durations of the step (CUDA events between the launches, L2 flushed before each step)
+    kms = []
+    for s in range(min(a.steps, 20)):
+        load_noise(s)
+        flush.fill_(s & 0xFF)
+        torch.cuda.synchronize()
+        kms.append(ukf.step_profile(M, flags, stream=sp))
+    kms = np.mean(np.array(kms), axis=0)
+
     # back-to-back (no flush) for reference
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -320,16 +330,26 @@ def main():
         kern_ms = float(np.mean(step_ms))
         ach_tf = FLOP_PER_UNIT * n_obj / (kern_ms * 1e-3) / 1e12
         ach_gb = BYTES_PER_UNIT * n_obj / (kern_ms * 1e-3) / 1e9
+        team = os.environ.get("SSA_UKF_KERNEL") == "team"
+        # dominant kernel: k_fx = 14 fx per object x 1.85 kflop = 25.9 kflop per object per launch
+        fx_ms = float(kms[0] if team else kms[1])
+        fx_flop = (FLOP_PER_UNIT if team else 14 * 1.85e3) * n_obj
+        fx_tf = fx_flop / (fx_ms * 1e-3) / 1e12
         line = {
             "metric": "RSO UKF predict+update per second", "value": value, "unit": "object-updates/s",
             "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
-            "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                         "traffic": None,
-                         "note": "kernel ssa_step_kernel; achieved = 39 kflop/object (SURVEY 8d convention) x objects / mean "
-                                 "CUDA-event launch time; peak = DFMA microbenchmark measured live in this run "
-                                 "(ssa_ukf_fp64_peak; FP64 is not in MEASURED_PEAKS.json)",
+            "roofline": {"bound": "fp64", "kernel": "ssa_step_kernel" if team else "k_fx",
+                         "achieved": fx_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": fx_tf / peak_tf,
+                         "traffic": None, "kernel_ms": fx_ms, "kernel_share_of_step": fx_ms / float(np.sum(kms)),
+                         "step_kernels_ms": {"factor": float(kms[0]), "fx": float(kms[1]), "ut": float(kms[2]),
+                                             "hx": float(kms[3]), "update": float(kms[4])},
+                         "whole_step": {"achieved": ach_tf, "frac": ach_tf / peak_tf, "flop_per_object": FLOP_PER_UNIT},
+                         "note": "dominant kernel k_fx (14 two-body propagations per object): achieved = 14 x 1.85 kflop "
+                                 "(SURVEY 8d convention) x objects / mean CUDA-event duration of that kernel; peak = DFMA "
+                                 "microbenchmark measured live in this run (ssa_ukf_fp64_peak; FP64 is not in "
+                                 "MEASURED_PEAKS.json, 'of measured'); whole_step = 39 kflop/object over all 5 kernels",
                          "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"}},
             "e2e": {"value": e2e_val, "unit": "object-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

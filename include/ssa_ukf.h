@@ -137,6 +137,10 @@ int ssa_ukf_device_ptr(ssa_ukf* h, int field, void** dptr, size_t* bytes);
 
 /* The hot path.  M = trans_matrix[i] (row-major GCRS->ITRS).  `flags` selects the fused stages.  */
 int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream);
+/* Same as ssa_ukf_step but brackets each kernel of the step with CUDA events on `stream`, synchronises, and
+ * returns the per-kernel durations in milliseconds: ms[0..4] = factor, fx, ut, hx, update (split pipeline) or
+ * ms[0] = the fused team kernel.  For measurement only (bench.py roofline of the dominant kernel).            */
+int ssa_ukf_step_profile(ssa_ukf* h, const double M[9], int flags, void* stream, double ms[5]);
 /* Convenience wrappers with the reference's call structure */
 int ssa_ukf_predict(ssa_ukf* h, void* stream);                      /* truth + predict              */
 int ssa_ukf_update(ssa_ukf* h, const double M[9], int all, void* stream); /* update (all | actions[e]) + epilogue */

@@ -630,6 +630,13 @@ void oracle_robust_chol(const double* A, double* U, int32_t* ret, int n) {
 void oracle_inv3(const double* S, double* SI, int32_t* ok, int n) {
   for (int i = 0; i < n; ++i) ok[i] = inv3((const double(*)[3])(S + 9 * i), (double(*)[3])(SI + 9 * i));
 }
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int oracle_num_threads(void) {
   int n = 1;
 #ifdef _OPENMP

@@ -1327,7 +1327,7 @@ int ssa_ukf_download(ssa_ukf* h, int field, void* host, size_t bytes, void* stre
   return SSA_OK;
 }
 
-int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
+static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cudaEvent_t* ev) {
   if (!h) return SSA_EINVAL;
   if ((flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE)) && !M && !(flags & SSA_STEP_M_PER_ENV)) {
     snprintf(g_err, sizeof(g_err), "trans_matrix required for update/epilogue");
@@ -1353,10 +1353,12 @@ int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
   if (M) memcpy(p.ob.M, M, sizeof(p.ob.M));
   memcpy(p.ob.obs_itrs, c.obs_itrs, sizeof(p.ob.obs_itrs));
   memcpy(p.ob.T, c.T, sizeof(p.ob.T));
+  if (ev) CK(cudaEventRecord(ev[0], st));
   if (h->use_team) {
     const unsigned grid = (unsigned)((c.n_objects + kTeamsPerCta - 1) / kTeamsPerCta);
     ssa_step_kernel<<<grid, kCtaThreads, 0, st>>>(p);
     h->launches++;
+    if (ev) for (int i = 1; i <= 5; ++i) CK(cudaEventRecord(ev[i], st));
     CK(cudaGetLastError());
     return SSA_OK;
   }
@@ -1364,12 +1366,37 @@ int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
   const bool predict = flags & SSA_STEP_PREDICT, truth = flags & SSA_STEP_TRUTH;
   const bool update = flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT), epi = flags & SSA_STEP_EPILOGUE;
   if (predict || update) { k_factor<<<gobj, kSplitThreads, 0, st>>>(p); h->launches++; }
+  if (ev) CK(cudaEventRecord(ev[1], st));
   if (predict || truth) { k_fx<<<dim3(gobj, 14), kSplitThreads, 0, st>>>(p); h->launches++; }
+  if (ev) CK(cudaEventRecord(ev[2], st));
   if (predict) { k_ut<<<gobj, kSplitThreads, 0, st>>>(p); h->launches++; }
+  if (ev) CK(cudaEventRecord(ev[3], st));
   if (update || epi) { k_hx<<<dim3(gobj, 14), kSplitThreads, 0, st>>>(p); h->launches++; }
+  if (ev) CK(cudaEventRecord(ev[4], st));
   if (update || epi) { k_update<<<gobj, kSplitThreads, 0, st>>>(p); h->launches++; }
+  if (ev) CK(cudaEventRecord(ev[5], st));
   CK(cudaGetLastError());
   return SSA_OK;
+}
+
+int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) { return step_impl(h, M, flags, stream, nullptr); }
+
+int ssa_ukf_step_profile(ssa_ukf* h, const double M[9], int flags, void* stream, double ms[5]) {
+  if (!h || !ms) return SSA_EINVAL;
+  CK(cudaSetDevice(h->device));
+  cudaEvent_t ev[6];
+  for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&ev[i]));
+  int rc = step_impl(h, M, flags, stream, ev);
+  if (rc == SSA_OK) {
+    CK(cudaEventSynchronize(ev[5]));
+    for (int i = 0; i < 5; ++i) {
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+      ms[i] = t;
+    }
+  }
+  for (int i = 0; i < 6; ++i) cudaEventDestroy(ev[i]);
+  return rc;
 }
 
 int ssa_ukf_predict(ssa_ukf* h, void* stream) {

@@ -168,6 +168,13 @@ class BatchedUKF:
         M = np.ascontiguousarray(M, dtype=np.float64).reshape(9) if M is not None else None
         _lib.check(self.lib.ssa_ukf_step(self.h, _ptr(M) if M is not None else None, int(flags), stream), "ssa_ukf_step")
 
+    def step_profile(self, M, flags, stream=None):
+        """One step with CUDA events around each kernel; returns ms per kernel [factor, fx, ut, hx, update]."""
+        M = np.ascontiguousarray(M, dtype=np.float64).reshape(9)
+        ms = (ctypes.c_double * 5)()
+        _lib.check(self.lib.ssa_ukf_step_profile(self.h, _ptr(M), int(flags), stream, ms), "ssa_ukf_step_profile")
+        return np.array(ms[:])
+
     def predict(self, stream=None):
         _lib.check(self.lib.ssa_ukf_predict(self.h, stream), "ssa_ukf_predict")
 

@@ -223,13 +223,17 @@ def c2_inputs(N=20000, steps=1, catalog=None):
 
 
 def bits_equal(a, b):
-    """Bit-for-bit equality of float arrays (NaN == NaN when the payload matches)."""
+    """Bit-for-bit equality of float arrays.  NaNs must sit in the same places; their sign/payload is not
+    compared (an x86 SSE operation generates the 'indefinite' NaN 0xFFF8..., an sm_100a one 0x7FF8...)."""
     a = np.ascontiguousarray(a)
     b = np.ascontiguousarray(b)
     if a.shape != b.shape:
         return False
     if a.dtype.kind == "f":
-        return np.array_equal(a.view(np.uint64), b.view(np.uint64))
+        na, nb = np.isnan(a), np.isnan(b)
+        if not np.array_equal(na, nb):
+            return False
+        return np.array_equal(np.where(na, 0.0, a).view(np.uint64), np.where(nb, 0.0, b).view(np.uint64))
     return np.array_equal(a, b)
 
 
