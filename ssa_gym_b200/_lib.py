@@ -82,7 +82,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("SSA_UKF_LIB") or _build.LIB  # SSA_UKF_LIB: alternative in-tree build (tuning experiments)
     if not os.path.isfile(path):
         path = _build.build()
     try:

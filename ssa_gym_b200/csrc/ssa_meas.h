@@ -61,10 +61,18 @@ SSA_HD void ssa_uvw2aer(const double* uvw, double* aer) {
   aer[2] = r;
 }
 
+// residual_z_aer.  The reference wraps the azimuth difference through atan2(sin d, cos d)
+// (dynamics.py:263).  For |d| < pi that expression IS d (to within an ulp of d, and d is the exact value), so
+// the wrap — one sincos and one atan2, 13 times per update — is only evaluated when it does something.
 SSA_HD void ssa_residual_aer(const double* a, const double* b, double* c) {
-  double s, co;
-  ssa_sincos(a[0] - b[0], &s, &co);
-  c[0] = ssa_atan2(s, co);
+  const double d = a[0] - b[0];
+  if (ssa_fabs(d) < SSA_C(PI)) {
+    c[0] = d;
+  } else {
+    double s, co;
+    ssa_sincos(d, &s, &co);
+    c[0] = ssa_atan2(s, co);
+  }
   c[1] = a[1] - b[1];
   c[2] = a[2] - b[2];
 }

@@ -347,7 +347,8 @@ SSA_HD void ssa_coe2rv(const double* coe, double* out) {
   out[5] = ssa_fma(vx, a20, ssa_mul(vy, a21));
 }
 
-SSA_HD int ssa_fx(const double* x, double tof, double* out) {
+// The literal restatement: rv2coe -> time since periapsis -> true anomaly -> coe2rv, every regime.
+SSA_HD_NOINLINE int ssa_fx_general(const double* x, double tof, double* out) {
   double coe[6];
   int exc = ssa_rv2coe(x, coe);
   if (exc) {
@@ -360,5 +361,97 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   const double dt1 = dt0 + tof;
   coe[5] = ssa_nu_from_delta_t(dt1, ecc, SSA_C(MU), q, &exc);
   ssa_coe2rv(coe, out);
+  return exc;
+}
+
+// fx.  The overwhelmingly common case — a strong-elliptic (1e-8 <= e < 0.99), non-equatorial orbit, i.e. the
+// "general" branch of rv2coe (farnocchia.py:294-309) followed by the strong-elliptic regime (:871-875,
+// :948-955) — is evaluated in a streamlined, mathematically identical form; every other case goes through
+// ssa_fx_general.  What the fast path changes relative to the literal sequence (all at the last-ulp level,
+// pinned against the reference's numba function in tests/test_oracle_golden.py):
+//   * the classical angles raan, inc, argp are never formed: the reference only uses them through sin/cos
+//     in coe2rv's rotation matrix, and those follow directly from the vectors
+//       cos(raan) = -h_y/h_xy   sin(raan) = h_x/h_xy   cos(inc) = h_z/|h|   sin(inc) = h_xy/|h|
+//       argp = u0 - nu0  ->  cos/sin(argp) by the angle-difference formulas, u0 = atan2(py, px);
+//   * the E0 -> nu0 -> E round trip (E_to_nu then nu_to_E, :300 and :873) is the identity up to rounding:
+//     M0 = E0 - e sin E0 is taken from E0 directly, and cos/sin of nu0 and of the propagated nu come from
+//     cos nu = (cos E - e)/(1 - e cos E), sin nu = sqrt(1 - e^2) sin E/(1 - e cos E) instead of two
+//     half-angle tangent/arctangent conversions;
+//   * `equatorial` (|acos(h_z/|h|)| < 1e-8) is decided as h_z/|h| == 1.0 — the only double whose acos is
+//     below 1e-8 (acos(1 - 2^-53) = 1.49e-8).
+// 1 atan2 + ~5.5 sincos + ~15 divisions instead of 7 atan2 + acos + 11 sincos + ~30 divisions.
+SSA_HD int ssa_fx(const double* x, double tof, double* out) {
+  const double k = SSA_C(MU), kinv = SSA_C(MU_INV);
+  const double* r = x;
+  const double* v = x + 3;
+  double h[3];
+  h[0] = ssa_fma(r[1], v[2], -ssa_mul(r[2], v[1]));
+  h[1] = ssa_fma(r[2], v[0], -ssa_mul(r[0], v[2]));
+  h[2] = ssa_fma(r[0], v[1], -ssa_mul(r[1], v[0]));
+  const double rr = ssa_dot3(r, r), vv = ssa_dot3(v, v), rv = ssa_dot3(r, v), hh = ssa_dot3(h, h);
+  const double rn = ssa_sqrt(rr), hn = ssa_sqrt(hh);
+  const double hxy2 = ssa_fma(h[1], h[1], ssa_mul(h[0], h[0]));
+  bool fast = (rn > 0.0) && (hn > 0.0) && (hxy2 > 0.0);
+  double ecc = 0.0, e_ce = 0.0, ci = 0.0, inv_hn = 0.0;
+  if (fast) {
+    const double c1 = vv - ssa_div(k, rn);
+    const double e0 = ssa_mul(ssa_fma(c1, r[0], -ssa_mul(rv, v[0])), kinv);
+    const double e1 = ssa_mul(ssa_fma(c1, r[1], -ssa_mul(rv, v[1])), kinv);
+    const double e2 = ssa_mul(ssa_fma(c1, r[2], -ssa_mul(rv, v[2])), kinv);
+    ecc = ssa_sqrt(ssa_fma(e2, e2, ssa_fma(e1, e1, ssa_mul(e0, e0))));
+    inv_hn = ssa_div(1.0, hn);
+    ci = ssa_div(h[2], hn);
+    e_ce = ssa_fma(ssa_mul(rn, vv), kinv, -1.0);
+    fast = (ecc >= SSA_C(TOL8)) && (ecc < SSA_C(DELTA99)) && (ci < 1.0);
+  }
+  if (!fast) return ssa_fx_general(x, tof, out);
+
+  const double p = ssa_mul(hh, kinv);
+  const double ome2 = ssa_fma(-ecc, ecc, 1.0);
+  const double a = ssa_div(p, ome2);
+  const double e_se = ssa_div(rv, ssa_sqrt(ssa_mul(k, a)));
+  const double E0 = ssa_atan2(e_se, e_ce);
+  const ssa_sc sc0 = ssa_sincos_v(E0);
+  const double sq = ssa_sqrt(ome2);
+  const double d0 = ssa_div(1.0, ssa_fma(-ecc, sc0.c, 1.0));
+  const double cnu0 = ssa_mul(sc0.c - ecc, d0), snu0 = ssa_mul(ssa_mul(sq, sc0.s), d0);
+  // mean motion and mean anomaly (farnocchia.py:874-875, 950-951)
+  const double q = ssa_div(p, 1.0 + ecc);
+  const double ome = 1.0 - ecc;
+  const double n = ssa_sqrt(ssa_div(ssa_mul(k, ssa_mul(ssa_mul(ome, ome), ome)), ssa_mul(ssa_mul(q, q), q)));
+  const double M0 = ssa_fma(-ecc, sc0.s, E0);
+  const double M = ssa_mul(n, ssa_div(M0, n) + tof);
+  int exc = 0;
+  const double E1 = ssa_M_to_E(ssa_wrap_pi(M), ecc, &exc);
+  const ssa_sc sc1 = ssa_sincos_v(E1);
+  const double d1 = ssa_div(1.0, ssa_fma(-ecc, sc1.c, 1.0));
+  const double cnu = ssa_mul(sc1.c - ecc, d1), snu = ssa_mul(ssa_mul(sq, sc1.s), d1);
+  // argument of latitude of the initial position: px = r.n, py = r.(h x n)/|h|, n = (-h_y, h_x, 0)
+  const double px = ssa_fma(r[1], h[0], -ssa_mul(r[0], h[1]));
+  const double py = ssa_mul(ssa_fma(r[2], hxy2, -ssa_mul(h[2], ssa_fma(r[1], h[1], ssa_mul(r[0], h[0])))), inv_hn);
+  const double inv_rho = ssa_div(1.0, ssa_sqrt(ssa_fma(py, py, ssa_mul(px, px))));
+  const double cu0 = ssa_mul(px, inv_rho), su0 = ssa_mul(py, inv_rho);
+  const double cw = ssa_fma(cu0, cnu0, ssa_mul(su0, snu0)), sw = ssa_fma(su0, cnu0, -ssa_mul(cu0, snu0));
+  // rotation (farnocchia.py:90-97) from the vectors
+  const double hxy = ssa_sqrt(hxy2);
+  const double inv_hxy = ssa_div(1.0, hxy);
+  const double cO = -ssa_mul(h[1], inv_hxy), sO = ssa_mul(h[0], inv_hxy);
+  const double si = ssa_mul(hxy, inv_hn);
+  // perifocal position / velocity (farnocchia.py:70-72)
+  const double rp = ssa_div(p, ssa_fma(ecc, cnu, 1.0));
+  const double vp = ssa_sqrt(ssa_div(k, p));
+  const double rx = ssa_mul(cnu, rp), ry = ssa_mul(snu, rp);
+  const double vx = ssa_mul(-snu, vp), vy = ssa_mul(ecc + cnu, vp);
+  const double m00 = cO, m01 = ssa_mul(-sO, ci);
+  const double m10 = sO, m11 = ssa_mul(cO, ci);
+  const double a00 = ssa_fma(m00, cw, ssa_mul(m01, sw)), a01 = ssa_fma(m01, cw, -ssa_mul(m00, sw));
+  const double a10 = ssa_fma(m10, cw, ssa_mul(m11, sw)), a11 = ssa_fma(m11, cw, -ssa_mul(m10, sw));
+  const double a20 = ssa_mul(si, sw), a21 = ssa_mul(si, cw);
+  out[0] = ssa_fma(rx, a00, ssa_mul(ry, a01));
+  out[1] = ssa_fma(rx, a10, ssa_mul(ry, a11));
+  out[2] = ssa_fma(rx, a20, ssa_mul(ry, a21));
+  out[3] = ssa_fma(vx, a00, ssa_mul(vy, a01));
+  out[4] = ssa_fma(vx, a10, ssa_mul(vy, a11));
+  out[5] = ssa_fma(vx, a20, ssa_mul(vy, a21));
   return exc;
 }

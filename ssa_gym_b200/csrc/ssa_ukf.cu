@@ -423,8 +423,23 @@ __global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) 
 // same sequence of rounded operations as in the team kernel and the host twin.
 // =====================================================================================================
 constexpr int kSplitThreads = 128;
+#ifndef SSA_LB_FX
+#define SSA_LB_FX 8
+#endif
+#ifndef SSA_LB_UT
+#define SSA_LB_UT 2
+#endif
+#ifndef SSA_LB_UPD
+#define SSA_LB_UPD 4
+#endif
+#ifndef SSA_LB_FAC
+#define SSA_LB_FAC 4
+#endif
+#ifndef SSA_LB_HX
+#define SSA_LB_HX 8
+#endif
 
-__global__ void __launch_bounds__(kSplitThreads) k_factor(const KParams p) {
+__global__ void __launch_bounds__(kSplitThreads, SSA_LB_FAC) k_factor(const KParams p) {
   const long obj = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (obj >= p.N) return;
   const long ld = p.ld;
@@ -460,7 +475,7 @@ __device__ __forceinline__ void load_sigma(const KParams& p, long obj, int k, co
   }
 }
 
-__global__ void __launch_bounds__(kSplitThreads) k_fx(const KParams p) {
+__global__ void __launch_bounds__(kSplitThreads, SSA_LB_FX) k_fx(const KParams p) {
   const long obj = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (obj >= p.N) return;
   const int k = blockIdx.y;  // uniform per block
@@ -499,7 +514,7 @@ __device__ __forceinline__ void store_sentinel(const KParams& p, long obj) {
       p.P[ssa_pidx(i, j) * ld + obj] = (i == j) ? (i < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL) : 0.0;
 }
 
-__global__ void __launch_bounds__(kSplitThreads) k_ut(const KParams p) {
+__global__ void __launch_bounds__(kSplitThreads, SSA_LB_UT) k_ut(const KParams p) {
   const long obj = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (obj >= p.N) return;
   if (!(p.flags & SSA_STEP_PREDICT)) return;
@@ -570,7 +585,7 @@ __device__ __forceinline__ long upd_object(const KParams& p, long idx) {
   return -1;
 }
 
-__global__ void __launch_bounds__(kSplitThreads) k_hx(const KParams p) {
+__global__ void __launch_bounds__(kSplitThreads, SSA_LB_HX) k_hx(const KParams p) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int k = blockIdx.y;
   const long ld = p.ld;
@@ -623,7 +638,7 @@ __global__ void __launch_bounds__(kSplitThreads) k_hx(const KParams p) {
   for (int a = 0; a < 3; ++a) p.ZS[(k * 3 + a) * ld + obj] = z[a];
 }
 
-__global__ void __launch_bounds__(kSplitThreads) k_update(const KParams p) {
+__global__ void __launch_bounds__(kSplitThreads, SSA_LB_UPD) k_update(const KParams p) {
   const long obj = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (obj >= p.N) return;
   const long ld = p.ld;
