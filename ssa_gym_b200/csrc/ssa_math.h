@@ -124,6 +124,22 @@ SSA_HD double ssa_add(double a, double b) {
 __device__ __noinline__ double ssa_div_dev(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __noinline__ double ssa_sqrt_dev(double a) { return __dsqrt_rn(a); }
 #endif
+// *_i: inlined variants for the (small) fast path of the propagation kernel, where the call overhead
+// (argument/result moves, CALL/RET) measured ~25 % of the issued instructions.
+SSA_HD double ssa_sqrt_i(double a) {
+#if defined(__CUDA_ARCH__)
+  return __dsqrt_rn(a);
+#else
+  return __builtin_sqrt(a);
+#endif
+}
+SSA_HD double ssa_div_i(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __ddiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
 SSA_HD double ssa_sqrt(double a) {
 #if defined(__CUDA_ARCH__)
   return ssa_sqrt_dev(a);
@@ -209,7 +225,7 @@ typedef struct { double s, c; } ssa_sc;
 // Real (non-inlined) device functions for the big kernels below: the fused step kernel calls them
 // from ~60 sites and would otherwise exceed the instruction cache several times over.  Results are
 // returned by value so they travel in registers.
-SSA_HD_NOINLINE ssa_sc ssa_sincos_v(double x) {
+SSA_HD ssa_sc ssa_sincos_i(double x) {
   double t = ssa_fma(x, SSA_C(INVPIO2), SSA_C(RMAGIC));
   int32_t q = ssa_lo32(t);
   double n = t - SSA_C(RMAGIC);
@@ -243,6 +259,7 @@ SSA_HD_NOINLINE ssa_sc ssa_sincos_v(double x) {
   out.c = c_;
   return out;
 }
+SSA_HD_NOINLINE ssa_sc ssa_sincos_v(double x) { return ssa_sincos_i(x); }
 SSA_HD void ssa_sincos(double x, double* sn, double* cs) {
   const ssa_sc r = ssa_sincos_v(x);
   *sn = r.s;
@@ -258,7 +275,7 @@ SSA_HD double ssa_tan(double x) { double s, c; ssa_sincos(x, &s, &c); return ssa
 // atan2 / atan  — one division: the fdlibm interval reduction (2t-1)/(2+t) etc. is applied to the
 // pair (|y|,|x|) directly, so t = |y|/|x| is never formed.
 // ---------------------------------------------------------------------------------------------
-SSA_HD_NOINLINE double ssa_atan2(double y, double x) {
+SSA_HD double ssa_atan2_i(double y, double x) {
   const double ax = ssa_fabs(x), ay = ssa_fabs(y);
   const double ay16 = ssa_mul(16.0, ay);
   double num, den, hi, lo;
@@ -281,7 +298,7 @@ SSA_HD_NOINLINE double ssa_atan2(double y, double x) {
   if (den == 0.0) {
     z = 0.0;  // atan2(+-0, +-0): fdlibm returns +-0 / +-pi through the quadrant logic below
   } else {
-    const double t = ssa_div(num, den);
+    const double t = ssa_div_i(num, den);
     const double t2 = ssa_mul(t, t);
     const double t4 = ssa_mul(t2, t2);
     double s1 = ssa_fma(t4, SSA_C(AT10), SSA_C(AT8));
@@ -301,6 +318,7 @@ SSA_HD_NOINLINE double ssa_atan2(double y, double x) {
   if (ssa_signbit(x)) z = SSA_C(PI) - (z - SSA_C(PI_LO));
   return ssa_signbit(y) ? -z : z;
 }
+SSA_HD_NOINLINE double ssa_atan2(double y, double x) { return ssa_atan2_i(y, x); }
 SSA_HD double ssa_atan(double x) { return ssa_atan2(x, 1.0); }
 
 // ---------------------------------------------------------------------------------------------

@@ -389,18 +389,18 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   h[1] = ssa_fma(r[2], v[0], -ssa_mul(r[0], v[2]));
   h[2] = ssa_fma(r[0], v[1], -ssa_mul(r[1], v[0]));
   const double rr = ssa_dot3(r, r), vv = ssa_dot3(v, v), rv = ssa_dot3(r, v), hh = ssa_dot3(h, h);
-  const double rn = ssa_sqrt(rr), hn = ssa_sqrt(hh);
+  const double rn = ssa_sqrt_i(rr), hn = ssa_sqrt_i(hh);
   const double hxy2 = ssa_fma(h[1], h[1], ssa_mul(h[0], h[0]));
   bool fast = (rn > 0.0) && (hn > 0.0) && (hxy2 > 0.0);
   double ecc = 0.0, e_ce = 0.0, ci = 0.0, inv_hn = 0.0;
   if (fast) {
-    const double c1 = vv - ssa_div(k, rn);
+    const double c1 = vv - ssa_div_i(k, rn);
     const double e0 = ssa_mul(ssa_fma(c1, r[0], -ssa_mul(rv, v[0])), kinv);
     const double e1 = ssa_mul(ssa_fma(c1, r[1], -ssa_mul(rv, v[1])), kinv);
     const double e2 = ssa_mul(ssa_fma(c1, r[2], -ssa_mul(rv, v[2])), kinv);
-    ecc = ssa_sqrt(ssa_fma(e2, e2, ssa_fma(e1, e1, ssa_mul(e0, e0))));
-    inv_hn = ssa_div(1.0, hn);
-    ci = ssa_div(h[2], hn);
+    ecc = ssa_sqrt_i(ssa_fma(e2, e2, ssa_fma(e1, e1, ssa_mul(e0, e0))));
+    inv_hn = ssa_div_i(1.0, hn);
+    ci = ssa_div_i(h[2], hn);
     e_ce = ssa_fma(ssa_mul(rn, vv), kinv, -1.0);
     fast = (ecc >= SSA_C(TOL8)) && (ecc < SSA_C(DELTA99)) && (ci < 1.0);
   }
@@ -408,38 +408,54 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
 
   const double p = ssa_mul(hh, kinv);
   const double ome2 = ssa_fma(-ecc, ecc, 1.0);
-  const double a = ssa_div(p, ome2);
-  const double e_se = ssa_div(rv, ssa_sqrt(ssa_mul(k, a)));
-  const double E0 = ssa_atan2(e_se, e_ce);
-  const ssa_sc sc0 = ssa_sincos_v(E0);
-  const double sq = ssa_sqrt(ome2);
-  const double d0 = ssa_div(1.0, ssa_fma(-ecc, sc0.c, 1.0));
+  const double a = ssa_div_i(p, ome2);
+  const double e_se = ssa_div_i(rv, ssa_sqrt_i(ssa_mul(k, a)));
+  const double E0 = ssa_atan2_i(e_se, e_ce);
+  const ssa_sc sc0 = ssa_sincos_i(E0);
+  const double sq = ssa_sqrt_i(ome2);
+  const double d0 = ssa_div_i(1.0, ssa_fma(-ecc, sc0.c, 1.0));
   const double cnu0 = ssa_mul(sc0.c - ecc, d0), snu0 = ssa_mul(ssa_mul(sq, sc0.s), d0);
   // mean motion and mean anomaly (farnocchia.py:874-875, 950-951)
-  const double q = ssa_div(p, 1.0 + ecc);
+  const double q = ssa_div_i(p, 1.0 + ecc);
   const double ome = 1.0 - ecc;
-  const double n = ssa_sqrt(ssa_div(ssa_mul(k, ssa_mul(ssa_mul(ome, ome), ome)), ssa_mul(ssa_mul(q, q), q)));
+  const double n = ssa_sqrt_i(ssa_div_i(ssa_mul(k, ssa_mul(ssa_mul(ome, ome), ome)), ssa_mul(ssa_mul(q, q), q)));
   const double M0 = ssa_fma(-ecc, sc0.s, E0);
-  const double M = ssa_mul(n, ssa_div(M0, n) + tof);
+  const double M = ssa_mul(n, ssa_div_i(M0, n) + tof);
   int exc = 0;
-  const double E1 = ssa_M_to_E(ssa_wrap_pi(M), ecc, &exc);
-  const ssa_sc sc1 = ssa_sincos_v(E1);
-  const double d1 = ssa_div(1.0, ssa_fma(-ecc, sc1.c, 1.0));
+  const double Mw = ssa_wrap_pi(M);
+  double E1;
+  if (!(-SSA_C(PI) <= Mw && Mw <= SSA_C(PI))) {  // assert of M_to_E (farnocchia.py:595): only a NaN gets here
+    exc = SSA_FX_EXC;
+    E1 = ssa_nan();
+  } else {
+    double p0 = (ecc < 0.8) ? Mw : ((Mw > 0.0) ? SSA_C(PI) : ((Mw < 0.0) ? -SSA_C(PI) : ssa_mul(SSA_C(PI), Mw)));
+    E1 = ssa_nan();
+    for (int it = 0; it < 50; ++it) {  // newton(), farnocchia.py:336-353
+      const ssa_sc sn = ssa_sincos_i(p0);
+      const double fval = ssa_fma(-ecc, sn.s, p0) - Mw;
+      const double fder = ssa_fma(-ecc, sn.c, 1.0);
+      const double pn = p0 - ssa_div_i(fval, fder);
+      if (ssa_fabs(pn - p0) < SSA_C(NEWTON_TOL)) { E1 = pn; break; }
+      p0 = pn;
+    }
+  }
+  const ssa_sc sc1 = ssa_sincos_i(E1);
+  const double d1 = ssa_div_i(1.0, ssa_fma(-ecc, sc1.c, 1.0));
   const double cnu = ssa_mul(sc1.c - ecc, d1), snu = ssa_mul(ssa_mul(sq, sc1.s), d1);
   // argument of latitude of the initial position: px = r.n, py = r.(h x n)/|h|, n = (-h_y, h_x, 0)
   const double px = ssa_fma(r[1], h[0], -ssa_mul(r[0], h[1]));
   const double py = ssa_mul(ssa_fma(r[2], hxy2, -ssa_mul(h[2], ssa_fma(r[1], h[1], ssa_mul(r[0], h[0])))), inv_hn);
-  const double inv_rho = ssa_div(1.0, ssa_sqrt(ssa_fma(py, py, ssa_mul(px, px))));
+  const double inv_rho = ssa_div_i(1.0, ssa_sqrt_i(ssa_fma(py, py, ssa_mul(px, px))));
   const double cu0 = ssa_mul(px, inv_rho), su0 = ssa_mul(py, inv_rho);
   const double cw = ssa_fma(cu0, cnu0, ssa_mul(su0, snu0)), sw = ssa_fma(su0, cnu0, -ssa_mul(cu0, snu0));
   // rotation (farnocchia.py:90-97) from the vectors
-  const double hxy = ssa_sqrt(hxy2);
-  const double inv_hxy = ssa_div(1.0, hxy);
+  const double hxy = ssa_sqrt_i(hxy2);
+  const double inv_hxy = ssa_div_i(1.0, hxy);
   const double cO = -ssa_mul(h[1], inv_hxy), sO = ssa_mul(h[0], inv_hxy);
   const double si = ssa_mul(hxy, inv_hn);
   // perifocal position / velocity (farnocchia.py:70-72)
-  const double rp = ssa_div(p, ssa_fma(ecc, cnu, 1.0));
-  const double vp = ssa_sqrt(ssa_div(k, p));
+  const double rp = ssa_div_i(p, ssa_fma(ecc, cnu, 1.0));
+  const double vp = ssa_sqrt_i(ssa_div_i(k, p));
   const double rx = ssa_mul(cnu, rp), ry = ssa_mul(snu, rp);
   const double vx = ssa_mul(-snu, vp), vy = ssa_mul(ecc + cnu, vp);
   const double m00 = cO, m01 = ssa_mul(-sO, ci);

@@ -75,7 +75,7 @@ def _interp_eop(eop, mjd_day, day_frac):
 # ---------------------------------------------------------------------------------------------
 def cal2jd(iy, im, id_):
     """(2400000.5, MJD at 0h) — same convention as eraCal2jd."""
-    my = (im - 14) // 12
+    my = int((im - 14) / 12)  # C integer division (truncation toward zero), as in eraCal2jd
     iypmy = iy + my
     djm = float((1461 * (iypmy + 4800)) // 4 + (367 * (im - 2 - 12 * my)) // 12
                 - (3 * ((iypmy + 4900) // 100)) // 4 + id_ - 2432076)

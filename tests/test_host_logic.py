@@ -1,0 +1,111 @@
+"""CPU: host-side logic of the path — sigma-point weights, process noise, gym seeding shim, the approximate
+trans-matrix generator against the SOFA golden matrix quoted by the reference, the synthetic catalog, the env
+configuration contract."""
+from datetime import datetime
+
+import numpy as np
+import pytest
+
+import helpers as H
+import ssa_gym_b200
+from ssa_gym_b200 import gym_shim, transformations as T
+from ssa_gym_b200.catalog import synthetic_catalog, tiled_catalog
+from ssa_gym_b200.ukf import Q_discrete_white_noise_block, merwe_weights
+
+
+def test_merwe_weights_reference_values():
+    """the reference's alpha=1e-4, beta=2, kappa=-3 weights; sum(Wm) != 1 is reproduced."""
+    Wm, Wc, lam = merwe_weights(6, 1e-4, 2.0, -3.0)
+    assert lam == 2.999999981767587e-08
+    assert Wm[0] == -200000000.21549422 and Wc[0] == -199999997.21549422
+    assert np.all(Wm[1:] == 16666666.76795785) and np.all(Wc[1:] == 16666666.76795785)
+    assert float(np.sum(Wm)) == 0.9999999813735485
+    from oracle.filterpy_restated import MerweScaledSigmaPoints
+    pts = MerweScaledSigmaPoints(6, 1e-4, 2.0, -3.0)
+    assert np.array_equal(pts.Wm, Wm) and np.array_equal(pts.Wc, Wc)
+
+
+def test_q_discrete_white_noise():
+    Q = Q_discrete_white_noise_block(20.0, 0.000025 ** 2)
+    assert np.allclose(np.diag(Q), [2.5e-5] * 3 + [2.5e-7] * 3) and np.allclose(Q[0, 3], 2.5e-6) and np.array_equal(Q, Q.T)
+    from oracle.filterpy_restated import Q_discrete_white_noise
+    assert np.array_equal(Q, Q_discrete_white_noise(dim=2, dt=20.0, var=0.000025 ** 2, block_size=3, order_by_dim=False))
+
+
+def test_gym_seeding_shim_matches_gym_0_17_algorithm():
+    rng, seed = gym_shim.np_random(0)
+    assert seed == 0
+    # SHA-512('0')[:8] little-endian words seed numpy's RandomState; stable known draws
+    assert rng.randint(0, 20000) == 2672
+    r1, _ = gym_shim.np_random(12345)
+    r2, _ = gym_shim.np_random(12345)
+    assert np.array_equal(r1.normal(size=5), r2.normal(size=5))
+    d = gym_shim.Discrete(10)
+    d.seed(3)
+    a = [d.sample() for _ in range(5)]
+    d.seed(3)
+    assert a == [d.sample() for _ in range(5)] and all(0 <= v < 10 for v in a)
+    assert d.contains(3) and d.contains(np.int64(9)) and not d.contains(10) and not d.contains(2.5)
+    with pytest.raises(ValueError):
+        gym_shim.np_random(-1)
+
+
+def test_normal_draw_order_equivalence():
+    """SS2:219-221 draws normal(size=3) n*m times; one normal(size=(n,m,3)) consumes the legacy stream identically."""
+    a, _ = gym_shim.np_random(7)
+    b, _ = gym_shim.np_random(7)
+    seq = np.array([[a.normal(size=3) for _ in range(4)] for _ in range(5)])
+    assert np.array_equal(seq, b.normal(size=(5, 4, 3)))
+
+
+def test_trans_matrix_generator_against_sofa_golden():
+    """tests.py:107-109 Cel2Ter06aXY: 2007-04-05 12:00 UTC, xp=0.0349282", yp=0.4833163", UT1-UTC=-0.072073685 s,
+    dX=0.1750 mas, dY=-0.2259 mas.  The ERFA-free generator is approximate by design (truncated X,Y series):
+    bound 5e-7 rad ~ 0.1 arcsec (20 m at GEO); it is an INPUT of the path, not graded arithmetic."""
+    t = datetime(2007, 4, 5, 12, 0, 0)
+    mjd = int(T.cal2jd(2007, 4, 5)[1])
+    eop = {mjd: (0.0349282, 0.4833163, -0.072073685, 0.1750e-3, -0.2259e-3),
+           mjd + 1: (0.0349282, 0.4833163, -0.072073685, 0.1750e-3, -0.2259e-3)}
+    M = T.gcrs2irts_matrix_approx(t, eop)
+    assert np.allclose(M @ M.T, np.eye(3), atol=1e-14) and abs(np.linalg.det(M) - 1) < 1e-14
+    assert np.max(np.abs(M - H.CEL2TER06AXY)) < 5e-7
+    assert T.cal2jd(2007, 4, 5) == (2400000.5, 54195.0) and T.dat(2007, 4) == 33.0 and T.dat(2020, 5) == 37.0
+    tab = T.gcrs2irts_matrix_approx(T.time_table(datetime(2020, 5, 4), 20.0, 5))
+    assert tab.shape == (5, 3, 3)
+    # consecutive matrices differ by the Earth rotation over 20 s
+    ang = np.arccos((np.trace(tab[1] @ tab[0].T) - 1) / 2)
+    assert abs(ang - 7.292115e-5 * 20.0) < 1e-9
+
+
+def test_geometry_constants_match_reference_values():
+    lla = np.array([np.radians(38.828198), np.radians(-77.305352), 20.0])
+    assert np.allclose(T.lla2ecef(lla), [1093352.569823721, -4853701.926649121, 3977489.550983512], rtol=0, atol=1e-9)
+    assert T.arcsec2rad == np.pi / 648000
+    Tm = T.trans_uvw_ecef(lla[0], lla[1])
+    assert np.allclose(Tm.T @ Tm, np.eye(3), atol=1e-15)
+
+
+def test_synthetic_catalog_properties():
+    c = synthetic_catalog(4000, 0)
+    assert c.shape == (4000, 6) and np.array_equal(c, synthetic_catalog(4000, 0))
+    r = np.linalg.norm(c[:, :3], axis=1)
+    assert r.min() > 5e6 and r.max() < 6e7  # the reference rule bounds the semi-minor axis, not the perigee
+    mu = 398600441800000.0
+    energy = 0.5 * np.sum(c[:, 3:] ** 2, 1) - mu / r
+    assert np.all(energy < 0)  # all bound orbits
+    # class mix like the reference fixture: exactly circular+equatorial GEO rows and Molniya rows exist
+    assert np.sum((c[:, 2] == 0) & (c[:, 5] == 0)) > 100
+    t = tiled_catalog(10000, c, seed=2)
+    assert t.shape == (10000, 6) and len(np.unique(t[:, 0])) == 10000
+
+
+def test_env_config_contract():
+    cfg = ssa_gym_b200.env_config
+    for k in ("steps", "rso_count", "time_step", "t_0", "obs_limit", "observer", "update_interval", "obs_type", "z_sigma",
+              "x_sigma", "q_sigma", "P_0", "R", "alpha", "beta", "kappa", "fx", "hx", "mean_z", "residual_z", "msqrt", "orbits",
+              "obs_returned", "reward_type"):
+        assert k in cfg, k
+    assert (cfg["steps"], cfg["rso_count"], cfg["time_step"], cfg["obs_limit"]) == (480, 10, 20.0, -90)
+    assert cfg["alpha"] == 0.0001 and cfg["beta"] == 2.0 and cfg["kappa"] == -3
+    assert cfg["fx"].__name__ == "fx_xyz_farnocchia" and cfg["msqrt"].__name__ == "robust_cholesky"
+    assert ssa_gym_b200.ENV_ID == "ssa_tasker_simple-v2"
