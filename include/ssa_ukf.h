@@ -141,6 +141,18 @@ int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream);
  * returns the per-kernel durations in milliseconds: ms[0..4] = factor, fx, ut, hx, update (split pipeline) or
  * ms[0] = the fused team kernel.  For measurement only (bench.py roofline of the dominant kernel).            */
 int ssa_ukf_step_profile(ssa_ukf* h, const double M[9], int flags, void* stream, double ms[5]);
+/* The reference-facing step with HOST buffers (the call an environment makes every step): uploads this step's
+ * inputs (actions int32[E] or NULL, z_noise double[N][3] or NULL), runs the step, and copies the step's results
+ * back (obs double[N][12], delta_pos double[N], status int32[N]; any may be NULL).  All three phases are
+ * asynchronous: inputs/outputs are double-buffered on the device and the copies run on two internal streams, so
+ * the H2D of step s+1 and the D2H of step s overlap the kernels of the other step when calls are issued back to
+ * back.  Host buffers should be pinned and must stay valid until ssa_ukf_host_join + a synchronize of `stream`
+ * (or ssa_ukf_sync).  Results are complete after ssa_ukf_host_join(h, stream) followed by a stream sync.      */
+int ssa_ukf_step_host(ssa_ukf* h, const double M[9], int flags, const int32_t* actions_host,
+                      const double* z_noise_host, double* obs_host, double* delta_pos_host,
+                      int32_t* status_host, void* stream);
+/* make `stream` wait for every outstanding internal copy of ssa_ukf_step_host */
+int ssa_ukf_host_join(ssa_ukf* h, void* stream);
 /* Convenience wrappers with the reference's call structure */
 int ssa_ukf_predict(ssa_ukf* h, void* stream);                      /* truth + predict              */
 int ssa_ukf_update(ssa_ukf* h, const double M[9], int all, void* stream); /* update (all | actions[e]) + epilogue */

@@ -73,6 +73,7 @@ struct KParams {
   double* S;               // [N][9]
   double* sigmas_h;        // [N][39]
   uint8_t* visible; uint8_t* updated;
+  int32_t* status_out;     // optional copy of the status word in the double-buffered output block (step_host)
   // scratch of the split pipeline (SoA, leading dimension ld)
   double* U;      // [21][ld] packed Cholesky factor of (lambda+n) P
   double* F;      // [13][6][ld] propagated sigma points
@@ -386,6 +387,7 @@ __global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) 
   if (lane < 5) p.P[(16 + lane) * ld + obj] = ws[WS_PN + 16 + lane];
   if (lane == 0) {
     p.status[obj] = status;
+    if (p.status_out) p.status_out[obj] = status;
     if (infl_count) p.infl[obj] += infl_count;
   }
 
@@ -791,6 +793,7 @@ __global__ void __launch_bounds__(kSplitThreads, SSA_LB_UPD) k_update(const KPar
     }
   }
   if (p.updated) p.updated[obj] = (uint8_t)updated;
+  if (p.status_out) p.status_out[obj] = st;
   (void)want_meas;
   if (flags & SSA_STEP_EPILOGUE) {
     double x[6], xt[6], dg[6];
@@ -1090,6 +1093,15 @@ struct ssa_ukf {
   int32_t* step_idx;  // [E]
   int32_t *code, *exc;
   int use_team;   // SSA_UKF_KERNEL=team selects the fused 16-lane team kernel instead of the split pipeline
+  // double-buffered host pipeline (ssa_ukf_step_host)
+  struct {
+    int init, parity;
+    long calls;
+    cudaStream_t up, dn;
+    cudaEvent_t e_up[2], e_c[2], e_dn[2];
+    double* block[2];   // [obs 12N][dpos dvel spos svel trace: 5 ld][z_noise 3N]
+    int32_t* iblock[2];  // [status_out ld][actions E]
+  } hp;
   int32_t *status, *infl, *actions, *greedy;
   uint8_t *visible, *updated, *done;
   size_t stage_bytes;
@@ -1193,6 +1205,14 @@ int ssa_ukf_destroy(ssa_ukf* h) {
   if (!h) return SSA_OK;
   cudaSetDevice(h->device);
   cudaFree(h->slab);
+  if (h->hp.init) {
+    cudaStreamSynchronize(h->hp.up); cudaStreamSynchronize(h->hp.dn);
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(h->hp.block[b]); cudaFree(h->hp.iblock[b]);
+      cudaEventDestroy(h->hp.e_up[b]); cudaEventDestroy(h->hp.e_c[b]); cudaEventDestroy(h->hp.e_dn[b]);
+    }
+    cudaStreamDestroy(h->hp.up); cudaStreamDestroy(h->hp.dn);
+  }
   cudaFree(h->stage);
   cudaFree(h->scratch);
   cudaFree(h->status);
@@ -1342,7 +1362,7 @@ int ssa_ukf_download(ssa_ukf* h, int field, void* host, size_t bytes, void* stre
   return SSA_OK;
 }
 
-static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cudaEvent_t* ev) {
+static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cudaEvent_t* ev, int hostbuf = -1) {
   if (!h) return SSA_EINVAL;
   if ((flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE)) && !M && !(flags & SSA_STEP_M_PER_ENV)) {
     snprintf(g_err, sizeof(g_err), "trans_matrix required for update/epilogue");
@@ -1365,6 +1385,14 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
   p.dt = c.dt; p.lam = c.lam_plus_n; p.obs_limit = c.obs_limit;
   memcpy(p.Wm, c.Wm, sizeof(p.Wm)); memcpy(p.Wc, c.Wc, sizeof(p.Wc));
   p.qr = h->qr;
+  if (hostbuf >= 0) {  // outputs / inputs of the double-buffered host pipeline
+    const long N_ = c.n_objects, ld_ = h->ld;
+    double* b = h->hp.block[hostbuf];
+    p.obs = b; p.dpos = b + 12 * N_; p.dvel = p.dpos + ld_; p.spos = p.dvel + ld_; p.svel = p.spos + ld_; p.trace = p.svel + ld_;
+    p.z_noise = p.trace + ld_;
+    p.status_out = h->hp.iblock[hostbuf];
+    p.actions = h->hp.iblock[hostbuf] + ld_;
+  }
   if (M) memcpy(p.ob.M, M, sizeof(p.ob.M));
   memcpy(p.ob.obs_itrs, c.obs_itrs, sizeof(p.ob.obs_itrs));
   memcpy(p.ob.T, c.T, sizeof(p.ob.T));
@@ -1395,6 +1423,69 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
 }
 
 int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) { return step_impl(h, M, flags, stream, nullptr); }
+
+static int hostpipe_init(ssa_ukf* h) {
+  if (h->hp.init) return SSA_OK;
+  const size_t N = h->cfg.n_objects, E = h->cfg.n_envs, ld = h->ld;
+  CK(cudaStreamCreateWithFlags(&h->hp.up, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->hp.dn, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaMalloc(&h->hp.block[b], sizeof(double) * (12 * N + 5 * ld + 3 * N)));
+    CK(cudaMemset(h->hp.block[b], 0, sizeof(double) * (12 * N + 5 * ld + 3 * N)));
+    CK(cudaMalloc(&h->hp.iblock[b], sizeof(int32_t) * (ld + E)));
+    CK(cudaMemset(h->hp.iblock[b], 0, sizeof(int32_t) * (ld + E)));
+    CK(cudaEventCreateWithFlags(&h->hp.e_up[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->hp.e_c[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->hp.e_dn[b], cudaEventDisableTiming));
+  }
+  h->hp.parity = 0;
+  h->hp.calls = 0;
+  h->hp.init = 1;
+  return SSA_OK;
+}
+
+int ssa_ukf_step_host(ssa_ukf* h, const double M[9], int flags, const int32_t* actions_host, const double* z_noise_host,
+                      double* obs_host, double* delta_pos_host, int32_t* status_host, void* stream) {
+  if (!h) return SSA_EINVAL;
+  CK(cudaSetDevice(h->device));
+  int rc = hostpipe_init(h);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t N = h->cfg.n_objects, E = h->cfg.n_envs, ld = h->ld;
+  const int b = h->hp.parity;
+  double* blk = h->hp.block[b];
+  int32_t* iblk = h->hp.iblock[b];
+  double* zn_dev = blk + 12 * N + 5 * ld;
+  // upload stream: buffer b is free once the compute of two calls ago has consumed it
+  if (h->hp.calls >= 2) CK(cudaStreamWaitEvent(h->hp.up, h->hp.e_c[b], 0));
+  if (z_noise_host) CK(cudaMemcpyAsync(zn_dev, z_noise_host, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, h->hp.up));
+  if (actions_host) CK(cudaMemcpyAsync(iblk + ld, actions_host, sizeof(int32_t) * E, cudaMemcpyHostToDevice, h->hp.up));
+  CK(cudaEventRecord(h->hp.e_up[b], h->hp.up));
+  // compute on the caller's stream: needs this step's inputs and a drained output buffer
+  CK(cudaStreamWaitEvent(st, h->hp.e_up[b], 0));
+  if (h->hp.calls >= 2) CK(cudaStreamWaitEvent(st, h->hp.e_dn[b], 0));
+  rc = step_impl(h, M, flags, stream, nullptr, b);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->hp.e_c[b], st));
+  // download stream
+  CK(cudaStreamWaitEvent(h->hp.dn, h->hp.e_c[b], 0));
+  if (obs_host) CK(cudaMemcpyAsync(obs_host, blk, sizeof(double) * 12 * N, cudaMemcpyDeviceToHost, h->hp.dn));
+  if (delta_pos_host) CK(cudaMemcpyAsync(delta_pos_host, blk + 12 * N, sizeof(double) * N, cudaMemcpyDeviceToHost, h->hp.dn));
+  if (status_host) CK(cudaMemcpyAsync(status_host, iblk, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, h->hp.dn));
+  CK(cudaEventRecord(h->hp.e_dn[b], h->hp.dn));
+  h->hp.parity ^= 1;
+  h->hp.calls++;
+  return SSA_OK;
+}
+
+int ssa_ukf_host_join(ssa_ukf* h, void* stream) {
+  if (!h) return SSA_EINVAL;
+  if (!h->hp.init) return SSA_OK;
+  CK(cudaSetDevice(h->device));
+  const long nb = h->hp.calls >= 2 ? 2 : h->hp.calls;
+  for (int b = 0; b < nb; ++b) CK(cudaStreamWaitEvent((cudaStream_t)stream, h->hp.e_dn[b], 0));
+  return SSA_OK;
+}
 
 int ssa_ukf_step_profile(ssa_ukf* h, const double M[9], int flags, void* stream, double ms[5]) {
   if (!h || !ms) return SSA_EINVAL;

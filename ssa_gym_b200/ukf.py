@@ -175,6 +175,20 @@ class BatchedUKF:
         _lib.check(self.lib.ssa_ukf_step_profile(self.h, _ptr(M), int(flags), stream, ms), "ssa_ukf_step_profile")
         return np.array(ms[:])
 
+    def step_host(self, M, flags, z_noise=None, obs_out=None, dpos_out=None, status_out=None, actions=None, stream=None):
+        """Asynchronous step with host buffers (pinned numpy arrays): H2D of the inputs, kernels, D2H of the
+        results, double-buffered and overlapped across consecutive calls.  Call host_join()+sync() before reading."""
+        M = np.ascontiguousarray(M, dtype=np.float64).reshape(9)
+        self._keep = (M, z_noise, actions)  # keep host inputs alive until consumed
+        _lib.check(self.lib.ssa_ukf_step_host(self.h, _ptr(M), int(flags), _ptr(actions) if actions is not None else None,
+                                              _ptr(z_noise) if z_noise is not None else None,
+                                              _ptr(obs_out) if obs_out is not None else None,
+                                              _ptr(dpos_out) if dpos_out is not None else None,
+                                              _ptr(status_out) if status_out is not None else None, stream), "ssa_ukf_step_host")
+
+    def host_join(self, stream=None):
+        _lib.check(self.lib.ssa_ukf_host_join(self.h, stream), "ssa_ukf_host_join")
+
     def predict(self, stream=None):
         _lib.check(self.lib.ssa_ukf_predict(self.h, stream), "ssa_ukf_predict")
 

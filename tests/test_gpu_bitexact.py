@@ -175,3 +175,28 @@ def test_variants_bitexact(obs_type, resample, kernel):
     ukf = _gpu_run(kw, cat, x, P0, zn, [FULL] * steps)
     _compare_all(ukf, st)
     ukf.close()
+
+
+def test_pipelined_host_step_equals_twin(kernel):
+    """ssa_ukf_step_host: double-buffered, asynchronous H2D / kernels / D2H.  Six pipelined steps with per-step
+    host result buffers must deliver exactly what the twin computes step by step."""
+    N, steps = 3000, 6
+    cat, x, P0, zn = H.c2_inputs(N, steps)
+    cfg = H.make_cfg(N)
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE
+    ukf = BatchedUKF(n_envs=1, m=N, dt=20.0, Q=np.array(cfg.Q).reshape(6, 6), R=np.array(cfg.R).reshape(3, 3),
+                     obs_lla=[np.radians(H.OBSERVER_DEG[0]), np.radians(H.OBSERVER_DEG[1]), H.OBSERVER_DEG[2]],
+                     obs_limit_rad=np.radians(-90.0))
+    ukf.reset(cat, x, P0)
+    obs = np.zeros((steps, N, 12)); dpos = np.zeros((steps, N)); stat = np.zeros((steps, N), np.int32)
+    zn = np.ascontiguousarray(zn)
+    for s in range(steps):
+        ukf.step_host(H.CEL2TER06AXY, flags, z_noise=zn[s], obs_out=obs[s], dpos_out=dpos[s], status_out=stat[s])
+    ukf.host_join()
+    ukf.sync()
+    st = H.HostState(cat, x, P0)
+    for s in range(steps):
+        H.cpu_step("twin", cfg, st, H.CEL2TER06AXY, flags, z_noise=zn[s])
+        assert H.bits_equal(obs[s], st.obs) and H.bits_equal(dpos[s], st.dpos) and np.array_equal(stat[s], st.status), s
+    assert H.bits_equal(ukf.download(F.F_X_FILTER), st.x)
+    ukf.close()
