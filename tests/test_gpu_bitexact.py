@@ -200,3 +200,32 @@ def test_pipelined_host_step_equals_twin(kernel):
         assert H.bits_equal(obs[s], st.obs) and H.bits_equal(dpos[s], st.dpos) and np.array_equal(stat[s], st.status), s
     assert H.bits_equal(ukf.download(F.F_X_FILTER), st.x)
     ukf.close()
+
+
+@pytest.mark.parametrize("chunk", ["640", "4000"])
+def test_chunked_execution_bitexact(chunk, monkeypatch):
+    """Large batches run in L2-sized chunks (SSA_UKF_CHUNK objects per chunk, env-aligned in RL mode).  Forcing
+    tiny chunks (ragged last chunk) must not change a single bit, in catalog mode and in RL mode."""
+    monkeypatch.setenv("SSA_UKF_KERNEL", "split")
+    monkeypatch.setenv("SSA_UKF_CHUNK", chunk)
+    N, steps = 9001, 3
+    cat, x, P0, zn = H.c2_inputs(N, steps)
+    cfg = H.make_cfg(N, obs_limit_deg=5.0)
+    st = H.HostState(cat, x, P0)
+    for s in range(steps):
+        H.cpu_step("twin", cfg, st, H.CEL2TER06AXY, FULL, z_noise=zn[s])
+    ukf = _gpu_run(dict(obs_limit_deg=5.0), cat, x, P0, zn, [FULL] * steps)
+    _compare_all(ukf, st)
+    ukf.close()
+    E, m = 903, 7
+    N = E * m
+    cat, x, P0, zn = H.c2_inputs(N, steps)
+    actions = np.random.RandomState(5).randint(0, m, size=(steps, E)).astype(np.int32)
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ACT | F.STEP_EPILOGUE | F.STEP_RECORD
+    cfg = H.make_cfg(N, E=E, m=m)
+    st = H.HostState(cat, x, P0)
+    for s in range(steps):
+        H.cpu_step("twin", cfg, st, H.CEL2TER06AXY, flags, actions=actions[s], z_noise=zn[s])
+    ukf = _gpu_run({}, cat, x, P0, zn, [flags] * steps, actions=actions, E=E, m=m)
+    _compare_all(ukf, st, check_update_outputs=False)
+    ukf.close()
