@@ -714,7 +714,12 @@ __global__ void __launch_bounds__(kSplitThreads, SSA_LB_UPD) k_update(const KPar
 #pragma unroll
       for (int e = 0; e < 18; ++e) Pxz[e] = 0.0;
       const bool from_f = !p.resample;
-#pragma unroll 1
+#ifndef SSA_UPD_UNROLL
+#define SSA_UPD_UNROLL 13
+#endif
+#define SSA_STR_(x) #x
+#define SSA_UNROLL_(n) _Pragma(SSA_STR_(unroll n))
+      SSA_UNROLL_(SSA_UPD_UNROLL)
       for (int k = 0; k < SSA_NSIG; ++k) {
         double zk[3], rz[3], sk[6];
 #pragma unroll
