@@ -14,11 +14,13 @@ from ssa_gym_b200.ukf import BatchedUKF
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["split", "team"], autouse=False)
+@pytest.fixture(params=["split", "split_teamsmall", "team"], autouse=False)
 def kernel(request, monkeypatch):
-    """Both device implementations of the step: the split five-kernel pipeline (default) and the fused
-    16-lane team kernel (SSA_UKF_KERNEL=team).  The handle reads the variable at creation."""
-    monkeypatch.setenv("SSA_UKF_KERNEL", request.param)
+    """Every device implementation of the step: the split five-kernel pipeline (default), the same pipeline with
+    the team-mapped UT/update kernels (SSA_UKF_TEAM_SMALL=1), and the fused 16-lane team kernel
+    (SSA_UKF_KERNEL=team).  The handle reads the variables at creation."""
+    monkeypatch.setenv("SSA_UKF_KERNEL", "team" if request.param == "team" else "split")
+    monkeypatch.setenv("SSA_UKF_TEAM_SMALL", "1" if request.param == "split_teamsmall" else "0")
     return request.param
 
 F = _lib
