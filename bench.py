@@ -29,12 +29,12 @@ sys.path.insert(0, ROOT)
 
 # Algorithmic cost per unit (one object: truth fx + predict + update + epilogue), DESIGN.md §3, under SURVEY 8(d)'s
 # counting convention (add/mul/cmp = 1, fma = 2, div = sqrt = 10, sin = cos = 40, atan2 = 80, asin = 70, mod = 10).
-# Two figures: the algorithm AS IMPLEMENTED here (streamlined fx: 0.966 kflop; update without the redundant
+# Two figures: the algorithm AS IMPLEMENTED here (streamlined fx: 0.90 kflop; update without the redundant
 # residual evaluations: 6.9 kflop; factorisations + UT: 1.7 kflop) and the reference's literal sequence (SURVEY: 1.85
 # kflop per fx, 39 kflop per unit).  `roofline.frac` uses the first (conservative, consistent with ncu's FP64 pipe
 # utilisation); the second is reported as `frac_reference_algorithm`.
-FLOP_FX = 0.966e3
-FLOP_PER_UNIT = 14 * FLOP_FX + 6.9e3 + 1.7e3      # 22.1 kflop
+FLOP_FX = 0.90e3
+FLOP_PER_UNIT = 14 * FLOP_FX + 6.9e3 + 1.7e3      # 21.2 kflop
 FLOP_FX_REF = 1.85e3
 FLOP_PER_UNIT_REF = 39.0e3
 BYTES_PER_UNIT = 48 + 168 + 48 + 24 + 4 + 48 + 168 + 48 + 96 + 40 + 4 + 2   # packed-P SoA layout: 698 B
@@ -369,6 +369,12 @@ def main():
         fx_flop = (FLOP_PER_UNIT if team else 14 * FLOP_FX) * n_obj
         fx_tf = fx_flop / (fx_ms * 1e-3) / 1e12
         fx_tf_ref = (FLOP_PER_UNIT_REF if team else 14 * FLOP_FX_REF) * n_obj / (fx_ms * 1e-3) / 1e12
+        traffic = None  # DRAM bytes per k_fx launch from the committed `ncu --set full` capture of this command
+        try:
+            if a.workload == "c2" and not a.objects and not team:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_c_ncu_full_c2_kernels.json")))["k_fx"]["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
         line = {
             "metric": "RSO UKF predict+update per second", "value": value, "unit": "object-updates/s",
             "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step,
@@ -376,18 +382,18 @@ def main():
             "config": config,
             "roofline": {"bound": "fp64", "kernel": "ssa_step_kernel" if team else "k_fx",
                          "achieved": fx_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": fx_tf / peak_tf,
-                         "traffic": None, "kernel_ms": fx_ms, "kernel_share_of_step": fx_ms / float(np.sum(kms)),
+                         "traffic": traffic, "algorithmic_bytes": 936 * n_obj, "kernel_ms": fx_ms, "kernel_share_of_step": fx_ms / float(np.sum(kms)),
                          "step_kernels_ms": {"factor": float(kms[0]), "fx": float(kms[1]), "ut": float(kms[2]),
                                              "hx": float(kms[3]), "update": float(kms[4])},
                          "frac_reference_algorithm": fx_tf_ref / peak_tf,
                          "whole_step": {"achieved": ach_tf, "frac": ach_tf / peak_tf, "flop_per_object": FLOP_PER_UNIT,
                                         "frac_reference_algorithm": ach_tf * FLOP_PER_UNIT_REF / FLOP_PER_UNIT / peak_tf},
-                         "note": "dominant kernel k_fx (14 two-body propagations per object): achieved = 14 x 0.966 kflop "
+                         "note": "dominant kernel k_fx (14 two-body propagations per object): achieved = 14 x 0.90 kflop "
                                  "(the streamlined fx as implemented, SURVEY 8d counting convention) x objects / mean "
                                  "CUDA-event duration of that kernel; frac_reference_algorithm prices the same launch at "
                                  "the reference's literal 1.85 kflop per fx / 39 kflop per unit; peak = DFMA microbenchmark "
                                  "measured live in this run (ssa_ukf_fp64_peak; FP64 is not in MEASURED_PEAKS.json) - "
-                                 "'of measured'; whole_step = all 5 kernels, 22.1 kflop/object",
+                                 "'of measured'; whole_step = all 5 kernels, 21.2 kflop/object",
                          "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"}},
             "e2e": {"value": e2e_val, "unit": "object-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

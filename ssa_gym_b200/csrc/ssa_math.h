@@ -65,7 +65,8 @@
   X(QS2, 2.02094576023350569471e+00) X(QS1, -2.40339491173441421878e+00)                               \
   X(PIO4_HI, 7.85398163397448278999e-01) X(ONE, 1.0)                                                   \
   X(MU, 398600441800000.0) X(MU_INV, 1.0 / 398600441800000.0)                                          \
-  X(TOL8, 1e-8) X(NEWTON_TOL, 1.48e-08) X(P2_52, 4503599627370496.0) X(DELTA99, 1.0 - 1e-2)
+  X(TOL8, 1e-8) X(NEWTON_TOL, 1.48e-08) X(P2_52, 4503599627370496.0) X(DELTA99, 1.0 - 1e-2)                        \
+  X(INV_TWOPI, 1.0 / 6.28318530717958623200e+00)
 
 enum {
 #define SSA_X(n, v) SSA_K_##n,
@@ -188,6 +189,22 @@ SSA_HD double ssa_copysign(double mag, double sgn) {
 // one (a/b is rounded once), r = fma(-q, b, a) is exact because the true remainder is representable,
 // and one conditional add repairs the off-by-one.  Falls back to the (exact) library fmod when
 // |a/b| >= 2^52 or anything is non-finite.  Checked against numpy.fmod in tests/test_math_accuracy.py.
+// Same with a pre-computed reciprocal of the divisor (binv ~ 1/b): q may now be off by one in either direction
+// more often, which the repair step handles identically, so the result is still the exact fmod.
+SSA_HD double ssa_fmod_pos_inv(double a, double b, double binv) {
+  const double q0 = ssa_mul(a, binv);
+  if (!(ssa_fabs(q0) < SSA_C(P2_52))) return fmod(a, b);
+  const double q = trunc(q0);
+  double r = ssa_fma(-q, b, a);
+  if (a >= 0.0) {
+    if (r < 0.0) r = ssa_add(r, b);
+    else if (r >= b) r = r - b;
+  } else {
+    if (r > 0.0) r = r - b;
+    else if (r <= -b) r = ssa_add(r, b);
+  }
+  return r;
+}
 SSA_HD double ssa_fmod_pos(double a, double b) {
   const double q0 = ssa_div(a, b);
   if (!(ssa_fabs(q0) < SSA_C(P2_52))) return fmod(a, b);

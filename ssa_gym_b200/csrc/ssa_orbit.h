@@ -187,7 +187,11 @@ SSA_HD double ssa_delta_t_from_nu(double nu, double ecc, double k, double q, int
   return ssa_div(M, n);
 }
 
-SSA_HD double ssa_wrap_pi(double a) { return ssa_pymod(a + SSA_C(PI), SSA_C(TWOPI)) - SSA_C(PI); }
+SSA_HD double ssa_wrap_pi(double a) {  // (a + pi) % (2 pi) - pi with python's % (farnocchia.py:311, 954, 967)
+  double m = ssa_fmod_pos_inv(a + SSA_C(PI), SSA_C(TWOPI), SSA_C(INV_TWOPI));
+  if (m != 0.0 && m < 0.0) m = ssa_add(m, SSA_C(TWOPI));
+  return m - SSA_C(PI);
+}
 
 SSA_HD double ssa_nu_from_delta_t(double delta_t, double ecc, double k, double q, int* exc) {
   const double delta = 1e-2;
@@ -379,7 +383,9 @@ SSA_HD_NOINLINE int ssa_fx_general(const double* x, double tof, double* out) {
 //     half-angle tangent/arctangent conversions;
 //   * `equatorial` (|acos(h_z/|h|)| < 1e-8) is decided as h_z/|h| == 1.0 — the only double whose acos is
 //     below 1e-8 (acos(1 - 2^-53) = 1.49e-8).
-// 1 atan2 + ~5.5 sincos + ~15 divisions instead of 7 atan2 + acos + 11 sincos + ~30 divisions.
+//   * algebraically equal forms that save divisions: n = sqrt(k/a^3), M = M0 + n dt, |r'| = a(1 - e cos E),
+//     sqrt(px^2 + py^2) = |r| h_xy, reciprocals of |r|, |h|, h_xy formed once.
+// 1 atan2 + ~5.5 sincos + ~11 divisions instead of 7 atan2 + acos + 11 sincos + ~30 divisions.
 SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   const double k = SSA_C(MU), kinv = SSA_C(MU_INV);
   const double* r = x;
@@ -392,15 +398,16 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   const double rn = ssa_sqrt_i(rr), hn = ssa_sqrt_i(hh);
   const double hxy2 = ssa_fma(h[1], h[1], ssa_mul(h[0], h[0]));
   bool fast = (rn > 0.0) && (hn > 0.0) && (hxy2 > 0.0);
-  double ecc = 0.0, e_ce = 0.0, ci = 0.0, inv_hn = 0.0;
+  double ecc = 0.0, e_ce = 0.0, ci = 0.0, inv_hn = 0.0, inv_rn = 0.0;
   if (fast) {
-    const double c1 = vv - ssa_div_i(k, rn);
+    inv_rn = ssa_div_i(1.0, rn);
+    const double c1 = vv - ssa_mul(k, inv_rn);
     const double e0 = ssa_mul(ssa_fma(c1, r[0], -ssa_mul(rv, v[0])), kinv);
     const double e1 = ssa_mul(ssa_fma(c1, r[1], -ssa_mul(rv, v[1])), kinv);
     const double e2 = ssa_mul(ssa_fma(c1, r[2], -ssa_mul(rv, v[2])), kinv);
     ecc = ssa_sqrt_i(ssa_fma(e2, e2, ssa_fma(e1, e1, ssa_mul(e0, e0))));
     inv_hn = ssa_div_i(1.0, hn);
-    ci = ssa_div_i(h[2], hn);
+    ci = ssa_mul(h[2], inv_hn);
     e_ce = ssa_fma(ssa_mul(rn, vv), kinv, -1.0);
     fast = (ecc >= SSA_C(TOL8)) && (ecc < SSA_C(DELTA99)) && (ci < 1.0);
   }
@@ -416,11 +423,10 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   const double d0 = ssa_div_i(1.0, ssa_fma(-ecc, sc0.c, 1.0));
   const double cnu0 = ssa_mul(sc0.c - ecc, d0), snu0 = ssa_mul(ssa_mul(sq, sc0.s), d0);
   // mean motion and mean anomaly (farnocchia.py:874-875, 950-951)
-  const double q = ssa_div_i(p, 1.0 + ecc);
-  const double ome = 1.0 - ecc;
-  const double n = ssa_sqrt_i(ssa_div_i(ssa_mul(k, ssa_mul(ssa_mul(ome, ome), ome)), ssa_mul(ssa_mul(q, q), q)));
+  // n = sqrt(k (1-e)^3 / q^3) with q = p/(1+e) = a (1-e)  ->  sqrt(k / a^3);  M = n (M0/n + tof) -> M0 + n tof
+  const double n = ssa_sqrt_i(ssa_div_i(k, ssa_mul(ssa_mul(a, a), a)));
   const double M0 = ssa_fma(-ecc, sc0.s, E0);
-  const double M = ssa_mul(n, ssa_div_i(M0, n) + tof);
+  const double M = ssa_fma(n, tof, M0);
   int exc = 0;
   const double Mw = ssa_wrap_pi(M);
   double E1;
@@ -445,16 +451,16 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   // argument of latitude of the initial position: px = r.n, py = r.(h x n)/|h|, n = (-h_y, h_x, 0)
   const double px = ssa_fma(r[1], h[0], -ssa_mul(r[0], h[1]));
   const double py = ssa_mul(ssa_fma(r[2], hxy2, -ssa_mul(h[2], ssa_fma(r[1], h[1], ssa_mul(r[0], h[0])))), inv_hn);
-  const double inv_rho = ssa_div_i(1.0, ssa_sqrt_i(ssa_fma(py, py, ssa_mul(px, px))));
+  const double hxy = ssa_sqrt_i(hxy2);
+  const double inv_hxy = ssa_div_i(1.0, hxy);
+  const double inv_rho = ssa_mul(inv_rn, inv_hxy);  // sqrt(px^2 + py^2) = |r| h_xy: r lies in the orbital plane
   const double cu0 = ssa_mul(px, inv_rho), su0 = ssa_mul(py, inv_rho);
   const double cw = ssa_fma(cu0, cnu0, ssa_mul(su0, snu0)), sw = ssa_fma(su0, cnu0, -ssa_mul(cu0, snu0));
   // rotation (farnocchia.py:90-97) from the vectors
-  const double hxy = ssa_sqrt_i(hxy2);
-  const double inv_hxy = ssa_div_i(1.0, hxy);
   const double cO = -ssa_mul(h[1], inv_hxy), sO = ssa_mul(h[0], inv_hxy);
   const double si = ssa_mul(hxy, inv_hn);
   // perifocal position / velocity (farnocchia.py:70-72)
-  const double rp = ssa_div_i(p, ssa_fma(ecc, cnu, 1.0));
+  const double rp = ssa_mul(a, ssa_fma(-ecc, sc1.c, 1.0));  // p/(1 + e cos nu) = a (1 - e cos E)
   const double vp = ssa_sqrt_i(ssa_div_i(k, p));
   const double rx = ssa_mul(cnu, rp), ry = ssa_mul(snu, rp);
   const double vx = ssa_mul(-snu, vp), vy = ssa_mul(ecc + cnu, vp);
