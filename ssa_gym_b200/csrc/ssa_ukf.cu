@@ -1,14 +1,14 @@
 // ssa_ukf.cu — sm_100a kernels and the C ABI (include/ssa_ukf.h) of the UKF hot path.
 //
-// Mapping: one object per 16-lane TEAM, two teams per warp, eight teams per
-// 128-thread CTA.  Lanes 0..12 of a team own the 13 sigma points, lane 13 owns the TRUE state,
-// lanes 14/15 shadow lane 13 (no divergence, no stores).  The propagation `fx` and the measurement
-// `hx` — >85 % of the fp64 work — therefore run with 14 of 16 lanes doing distinct useful work.  The
-// small linear algebra between them is spread over the lanes element by element through a 1.7 KB
-// shared-memory workspace per team (sigma set, deviations, cross terms); Cholesky and the 3x3
-// inverse are evaluated redundantly by every lane in registers (a redundant lane costs no issue
-// slots).  Reductions over the 13 sigma points are sequential k = 0..12 FMAs read from shared memory,
-// i.e. in a FIXED order, so the result is bit-identical to the host twin (tests/twin/twin.cpp).
+// Two device implementations of the step live here, both bit-identical to the host twin
+// (tests/twin/twin.cpp):
+//  * the SPLIT PIPELINE (default): five launches per step — k_factor, k_fx, k_ut, k_hx, k_update — one thread per
+//    object for the small linear algebra, one thread per (sigma point, object) for the propagation `fx` and the
+//    measurement `hx` (>85 % of the fp64 work), objects fastest-varying so every access is coalesced;
+//  * the TEAM KERNEL ssa_step_kernel (SSA_UKF_KERNEL=team): one launch, one object per 16-lane team (lanes 0..12
+//    own the sigma points, lane 13 the TRUE state), sigma set staged in a 1.7 KB shared-memory workspace per
+//    team, Cholesky / 3x3 inverse evaluated redundantly per lane.
+// Reductions over the 13 sigma points are sequential k = 0..12 FMAs in a FIXED order everywhere.
 //
 // HBM layout: struct-of-arrays fp64, leading dimension ld = N rounded up to 32:
 //   xt[6][ld]  x[6][ld]  P[21][ld] (packed upper triangle)  + per-object scalars [ld]
@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(kSplitThreads, SSA_LB_HX) k_hx(const KParams p
   const long loc = obj - p.obj0;
   if ((p.status[obj] & SSA_ST_FAILED) || p.code[obj]) return;
   double s[6];
-  if (p.resample || !(p.flags & SSA_STEP_PREDICT) && false) {
+  if (p.resample) {  // sigmas_f = points re-drawn around the prior; book version: the propagated points
     double x[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = p.x[i * ld + obj];
@@ -667,7 +667,6 @@ __global__ void __launch_bounds__(kSplitThreads, SSA_LB_UPD) k_update(const KPar
   int st = p.status[obj];
   bool want_upd = (flags & SSA_STEP_UPDATE_ALL) != 0;
   if (flags & SSA_STEP_UPDATE_ACT) want_upd = want_upd || (p.actions[obj / p.m] == (int)(obj % p.m));
-  const bool want_meas = want_upd || (flags & SSA_STEP_EPILOGUE);
   int updated = 0;
   int code = 0;
   if (want_upd && !(st & SSA_ST_FAILED)) {
@@ -818,7 +817,6 @@ __global__ void __launch_bounds__(kSplitThreads, SSA_LB_UPD) k_update(const KPar
   }
   if (p.updated) p.updated[obj] = (uint8_t)updated;
   if (p.status_out) p.status_out[obj] = st;
-  (void)want_meas;
   if (flags & SSA_STEP_EPILOGUE) {
     double x[6], xt[6], dg[6];
 #pragma unroll
@@ -1278,11 +1276,6 @@ __global__ void ssa_packed_to_pfull(const double* __restrict__ src, double* __re
   const int i = r < c ? r : c, j = r < c ? c : r;
   dst[t] = src[ssa_pidx(i, j) * ld + n];
 }
-__global__ void ssa_fill_i32(int32_t* p, long n, int v) {
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n) p[t] = v;
-}
-
 // FP64 pipe microbenchmark: 8 independent DFMA chains per thread.
 __global__ void __launch_bounds__(256) ssa_dfma_peak_kernel(double* out, int iters, double a, double b) {
   double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
