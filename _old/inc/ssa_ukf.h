@@ -1,0 +1,201 @@
+/* ssa_ukf.h — C ABI of libssa_ukf.so: the B200 (sm_100a) implementation of ssa-gym's per-step
+ * estimation hot path (UKF predict/update over every resident space object of every environment).
+ *
+ * This is the drop-in boundary.  Everything above it (gym.Env reset/step, RNG, failure messages,
+ * histories) stays Python; everything below is CUDA.  No torch types, only plain pointers/sizes.
+ * Every entry point returns 0 on success or a negative SSA_E* code; nothing throws.  All calls on
+ * one handle must come from one host thread; work is enqueued on the given CUDA stream and is
+ * asynchronous unless the function name says download/sync.
+ *
+ * Reference interfaces replaced (file:line in the read-only upstream AshHarvey/ssa-gym):
+ *   ssa_ukf_create        envs/ssa_tasker_simple_2.py:72-184  (__init__: dt, Q, R, observer, sigma-point
+ *                         parameters; filterpy MerweScaledSigmaPoints weights) and :211-218 (UKF objects)
+ *   ssa_ukf_reset         envs/ssa_tasker_simple_2.py:193-241 (reset: x_true[0], x_filter[0], P_0)
+ *   ssa_ukf_predict       envs/ssa_tasker_simple_2.py:265-287 (truth fx loop + filters[j].predict())
+ *                         -> filterpy UKF.predict -> envs/farnocchia.py:1053 fx, envs/dynamics.py:402 msqrt
+ *   ssa_ukf_update        envs/ssa_tasker_simple_2.py:292-315 (hx, visibility gate, filters[a].update(z))
+ *                         -> filterpy UKF.update -> envs/dynamics.py:219 hx, :342 mean_z, :260 residual_z
+ *   ssa_ukf_step          the whole of step(): SS2:243-367, fused (truth + predict + update + obs/error)
+ *   ssa_ukf_env_reduce    SS2:324-354 (reward / done), agents.py:7-9,35-42,66-81 (greedy taskers),
+ *                         SS2:410-425 (visible_objects)
+ *   ssa_ukf_scores        envs/reward.py:6-50
+ *   ssa_ukf_download      the numpy arrays the reference env exposes: x_true, x_filter, P_filter, obs,
+ *                         delta_pos, delta_vel, sigma_pos, sigma_vel, y, S, sigmas_h  (SS2:132-161)
+ */
+#ifndef SSA_UKF_H
+#define SSA_UKF_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSA_UKF_ABI_VERSION 1
+
+/* error codes */
+#define SSA_OK 0
+#define SSA_EINVAL (-1)  /* bad argument */
+#define SSA_ECUDA (-2)   /* CUDA runtime error; ssa_ukf_last_error() has the text */
+#define SSA_ENOMEM (-3)
+#define SSA_ENODEV (-4)  /* no CUDA device: there is no CPU fallback */
+
+/* obs_type (SS2:100-107) */
+#define SSA_OBS_AER 0
+#define SSA_OBS_XYZ 1
+/* reward_type (SS2:324-351) */
+#define SSA_REWARD_JONES 0
+#define SSA_REWARD_TRINARY 1
+#define SSA_REWARD_SHAPED 2
+
+/* Per-object status word (int32), also in ssa_gym_b200/csrc/ssa_ukf_core.h */
+#define SSA_STATUS_FAILED 0x1
+#define SSA_STATUS_LINALG 0x2
+#define SSA_STATUS_NAN 0x4
+#define SSA_STATUS_FXEXC 0x8
+#define SSA_STATUS_TRUTHEXC 0x10
+#define SSA_STATUS_IN_UPDATE 0x20
+
+typedef struct ssa_ukf_cfg {
+  int32_t abi_version;             /* SSA_UKF_ABI_VERSION */
+  int32_t n_objects;               /* N = n_envs * m */
+  int32_t n_envs;                  /* E; 1 for the drop-in env, N objects form E groups of m */
+  int32_t m;                       /* rso_count: objects per environment */
+  int32_t obs_type;                /* SSA_OBS_* */
+  int32_t resample_after_predict;  /* 1: filterpy >= 1.4.5 predict() re-draws sigmas_f from the prior */
+  int32_t reward_type;             /* SSA_REWARD_* (used by ssa_ukf_env_reduce) */
+  int32_t n_steps;                 /* n: episode length (done when i+1 >= n) */
+  double dt;                       /* time_step [s] */
+  double lam_plus_n;               /* (lambda + n) of MerweScaledSigmaPoints */
+  double Wm[13];                   /* mean weights, computed on the host with filterpy's expressions */
+  double Wc[13];                   /* covariance weights */
+  double Q[36];                    /* process noise, row-major 6x6 (Q_discrete_white_noise, SS2:110) */
+  double R[9];                     /* measurement noise, row-major 3x3, added element-wise to S */
+  double obs_itrs[3];              /* observer ECEF [m] (lla2ecef(obs_lla), SS2:94) */
+  double T[9];                     /* trans_uvw_ecef(lat,lon), row-major (transformations.py:341-343) */
+  double obs_limit;                /* elevation mask [rad] (SS2:85) */
+} ssa_ukf_cfg;
+
+typedef struct ssa_ukf ssa_ukf; /* opaque handle, owns all device buffers */
+
+/* fields for ssa_ukf_download / ssa_ukf_upload / ssa_ukf_device_ptr.
+ * Host layouts are the reference's numpy layouts (row-major):
+ *   X_TRUE, X_FILTER  double[N][6]       P_FILTER double[N][6][6] (symmetric, mirrored from the packed upper)
+ *   OBS               double[N][12] = [x(6), diag P(6)]  (results.py:60-72)
+ *   DELTA_POS/VEL, SIGMA_POS/VEL, TRACE   double[N]      (results.py:36-47; np.trace)
+ *   Z_TRUE, Y, Z_NOISE double[N][3]      S double[N][3][3]   SIGMAS_H double[N][13][3]
+ *   VISIBLE uint8[N] (SS2:418-425)       STATUS int32[N]     INFLATIONS int32[N]
+ *   ACTIONS int32[E]  REWARD double[E]  DONE uint8[E]  GREEDY int32[E][SSA_N_TASKERS]
+ *   TRANS_ENV double[E][9] per-env trans_matrix  STEP_INDEX int32[E] per-env step counter i
+ *   ENV_STATS double[E][4] = [max delta_pos, trinary reward, argmax sigma_pos, #visible]
+ * Device layouts are struct-of-arrays with leading dimension ssa_ukf_ld(h).        */
+enum ssa_field {
+  SSA_F_X_TRUE = 0, SSA_F_X_FILTER = 1, SSA_F_P_FILTER = 2, SSA_F_OBS = 3,
+  SSA_F_DELTA_POS = 4, SSA_F_DELTA_VEL = 5, SSA_F_SIGMA_POS = 6, SSA_F_SIGMA_VEL = 7, SSA_F_TRACE = 8,
+  SSA_F_Z_TRUE = 9, SSA_F_Y = 10, SSA_F_S = 11, SSA_F_SIGMAS_H = 12, SSA_F_Z_NOISE = 13,
+  SSA_F_VISIBLE = 14, SSA_F_STATUS = 15, SSA_F_INFLATIONS = 16,
+  SSA_F_ACTIONS = 17, SSA_F_REWARD = 18, SSA_F_DONE = 19, SSA_F_GREEDY = 20, SSA_F_SCORES = 21,
+  SSA_F_UPDATED = 22, SSA_F_TRANS_ENV = 23, SSA_F_STEP_INDEX = 24, SSA_F_ENV_STATS = 25, SSA_F_COUNT_
+};
+
+/* heuristic taskers evaluated on the device by ssa_ukf_env_reduce (agents.py) */
+#define SSA_TASKER_NAIVE_GREEDY 0     /* argmax trace P over all objects           agents.py:7-9   */
+#define SSA_TASKER_VISIBLE_GREEDY 1   /* argmax trace P over visible objects       agents.py:35-42 */
+#define SSA_TASKER_POS_ERROR_GREEDY 2 /* argmax delta_pos over visible objects     agents.py:66-72 */
+#define SSA_TASKER_VEL_ERROR_GREEDY 3 /* argmax delta_vel over visible objects     agents.py:75-81 */
+#define SSA_N_TASKERS 4
+/* a visible-* tasker returns -1 when the reference would fall back to action_space.sample()
+ * (`not np.any(visible)` — also true when the only visible index is 0, agents.py:37).            */
+
+/* flags for ssa_ukf_step */
+#define SSA_STEP_TRUTH 0x1        /* propagate the true states (SS2:265-266) */
+#define SSA_STEP_PREDICT 0x2      /* UKF predict on every non-failed object (SS2:271-287) */
+#define SSA_STEP_UPDATE_ALL 0x4   /* catalog mode: update every object with its z_noise */
+#define SSA_STEP_UPDATE_ACT 0x8   /* RL mode: update object actions[e] of each env e (SS2:292-315) */
+#define SSA_STEP_EPILOGUE 0x10    /* obs / error / trace / visibility (SS2:320-322, 410-425) */
+#define SSA_STEP_RECORD 0x20      /* also store z_true, y, S, sigmas_h of updated objects (SS2:298-304) */
+#define SSA_STEP_M_PER_ENV 0x40   /* vectorised envs at different step indices: use the uploaded SSA_F_TRANS_ENV
+                                     table (double[E][9], one trans_matrix per environment) instead of M      */
+
+int ssa_ukf_abi_version(void);
+const char* ssa_ukf_last_error(void);
+int ssa_ukf_device_count(void);
+
+int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out);
+int ssa_ukf_destroy(ssa_ukf* h);
+long ssa_ukf_ld(const ssa_ukf* h); /* leading dimension (padded N) of the device SoA arrays */
+
+/* reset(): host arrays in reference layout. P0 is one 6x6 (p0_per_object = 0) or N of them.     */
+int ssa_ukf_reset(ssa_ukf* h, const double* x_true, const double* x_filter, const double* P0,
+                  int p0_per_object, void* stream);
+
+/* per-step host inputs: actions int32[E] and/or z_noise double[N][3] (SS2:219-221 draws them at reset) */
+int ssa_ukf_upload(ssa_ukf* h, int field, const void* host, size_t bytes, void* stream);
+int ssa_ukf_download(ssa_ukf* h, int field, void* host, size_t bytes, void* stream); /* blocks until copied */
+/* raw device pointer of a field (device SoA layout) for zero-copy consumers (torch, NCCL) */
+int ssa_ukf_device_ptr(ssa_ukf* h, int field, void** dptr, size_t* bytes);
+
+/* The hot path.  M = trans_matrix[i] (row-major GCRS->ITRS).  `flags` selects the fused stages.  */
+int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream);
+/* Same as ssa_ukf_step but brackets each kernel of the step with CUDA events on `stream`, synchronises, and
+ * returns the per-kernel durations in milliseconds: ms[0..4] = factor, fx, ut, hx, update (split pipeline) or
+ * ms[0] = the fused team kernel.  For measurement only (bench.py roofline of the dominant kernel).            */
+int ssa_ukf_step_profile(ssa_ukf* h, const double M[9], int flags, void* stream, double ms[5]);
+/* The reference-facing step with HOST buffers (the call an environment makes every step): uploads this step's
+ * inputs (actions int32[E] or NULL, z_noise double[N][3] or NULL), runs the step, and copies the step's results
+ * back (obs double[N][12], delta_pos double[N], status int32[N]; any may be NULL).  All three phases are
+ * asynchronous: inputs/outputs are double-buffered on the device and the copies run on two internal streams, so
+ * the H2D of step s+1 and the D2H of step s overlap the kernels of the other step when calls are issued back to
+ * back.  Host buffers should be pinned and must stay valid until ssa_ukf_host_join + a synchronize of `stream`
+ * (or ssa_ukf_sync).  Results are complete after ssa_ukf_host_join(h, stream) followed by a stream sync.      */
+int ssa_ukf_step_host(ssa_ukf* h, const double M[9], int flags, const int32_t* actions_host,
+                      const double* z_noise_host, double* obs_host, double* delta_pos_host,
+                      int32_t* status_host, void* stream);
+/* make `stream` wait for every outstanding internal copy of ssa_ukf_step_host */
+int ssa_ukf_host_join(ssa_ukf* h, void* stream);
+/* Convenience wrappers with the reference's call structure */
+int ssa_ukf_predict(ssa_ukf* h, void* stream);                      /* truth + predict              */
+int ssa_ukf_update(ssa_ukf* h, const double M[9], int all, void* stream); /* update (all | actions[e]) + epilogue */
+
+/* per-environment reductions: reward / done (SS2:324-354) and the greedy taskers (agents.py).
+ * step_index = i after the increment of SS2:259; a negative step_index selects the uploaded per-env
+ * SSA_F_STEP_INDEX table.  'shaped' rewards need the reward history: the device returns ENV_STATS and the
+ * host finishes them (SS2:339-351).                                                                       */
+int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stream);
+/* reward.py score terms from the current covariances: out double[N][6] =
+ * [score_scaled_trace_P, score_trace_P, score_scaled_det_P(dt), score_det_P, score_det_pos_P, |dpos|] */
+int ssa_ukf_scores(ssa_ukf* h, void* stream);
+
+int ssa_ukf_sync(ssa_ukf* h, void* stream);
+/* number of kernel launches issued through this handle so far (bench.py `gpu_launches`) */
+long ssa_ukf_launch_count(const ssa_ukf* h);
+
+/* FP64 pipe microbenchmark (dependent DFMA chains on every SM) used as the roofline denominator:
+ * returns achieved TFLOP/s (2 flop per DFMA), timed with CUDA events on `stream`.                  */
+int ssa_ukf_fp64_peak(int device, void* stream, double* tflops);
+
+/* ---- operator-level entry points -----------------------------------------------------------------
+ * The reference's plug points are Python callables handed to filterpy through env_config
+ * (envs/__init__.py:27-28: fx, hx, mean_z, residual_z, msqrt).  These evaluate the DEVICE build of
+ * the same operators on host arrays (synchronous; n independent evaluations, one GPU thread each), so
+ * that calling an operator directly runs the code the fused kernel runs.  Also used by the parity
+ * tests to compare sm_100a with the host twin function by function.                                  */
+/* op: 0 sin 1 cos 2 tan 3 atan 4 asin 5 acos 6 exp 7 log 8 sinh 9 cosh 10 tanh 11 atanh 12 asinh
+ *     13 acosh 14 x^(2/3) 15 atan2(a,b) 16 python a%b 17 a/b 18 sqrt                                  */
+int ssa_unit_math(int op, const double* a, const double* b, double* out, int n, int device);
+/* fx_xyz_farnocchia (envs/farnocchia.py:1053): x[n][6] -> out[n][6]; exc[n] != 0 where numba would raise */
+int ssa_unit_fx(const double* x, double dt, double* out, int32_t* exc, int n, int device);
+/* hx_aer_erfa (envs/dynamics.py:219): x[n][stride] (first 3 used) -> out[n][3] = az, el, range      */
+int ssa_unit_hx_aer(const double* x, int stride, const double M[9], const double obs_itrs[3], const double T[9],
+                    double* out, int n, int device);
+/* op 0: aer2uvw  1: uvw2aer  2: residual_z_aer(a, b)   (transformations.py:283-316, dynamics.py:260) */
+int ssa_unit_aer(int op, const double* a, const double* b, double* out, int n, int device);
+/* robust_cholesky(lam * P) (envs/dynamics.py:402): packed upper [n][21] in/out; ret = attempt or -1  */
+int ssa_unit_robust_chol(const double* P_packed, double lam, double* U_packed, int32_t* ret, int n, int device);
+/* numpy.linalg.inv of 3x3 (filterpy UKF.update SI = inv(S))                                          */
+int ssa_unit_inv3(const double* S, double* SI, int32_t* ok, int n, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSA_UKF_H */

@@ -1,0 +1,78 @@
+// ssa_meas.h — measurement model of the UKF: GCRS state -> ITRS -> topocentric az/el/range, the
+// Cartesian (uvw) mean of angular measurements and the wrapped residual.  Host+device, see
+// ssa_math.h for the bit-exactness contract.
+//
+// Reference behaviour reproduced (file:line in the read-only upstream):
+//   envs/dynamics.py:219-231          hx_aer_erfa : x_itrs = trans_matrix @ x[:3]; ecef2aer(...)
+//   envs/transformations.py:329-352   ecef2aer    : T(lat,lon)^T (x_itrs - obs_itrs); az = atan2(E1,E0) (+2pi if <0);
+//                                                   el = asin(E2/r); r = |x_itrs - obs_itrs|
+//   envs/transformations.py:283-297   aer2uvw     : (r cos el cos az, r cos el sin az, r sin el)
+//   envs/transformations.py:300-316   uvw2aer
+//   envs/dynamics.py:342-354          mean_z_uvw  : uvw2aer(Wm . aer2uvw(sigmas))
+//   envs/dynamics.py:260-267          residual_z_aer : [atan2(sin d, cos d), d_el, d_r]
+//   envs/dynamics.py:207-217,270-278  hx_xyz / residual_xyz / mean_xyz (Cartesian variant, tests.py Test 6/7)
+//
+// The observer rotation T (transformations.py:341-343) only depends on the observer latitude and
+// longitude; the reference rebuilds it on every call, here the host computes its nine entries once
+// with the same expressions and ships them in the constant block (`ssa_obs`).
+#pragma once
+#include "ssa_math.h"
+
+typedef struct {
+  double M[9];         // GCRS -> ITRS rotation for the current step (row-major), host input (SS2:137)
+  double obs_itrs[3];  // observer ECEF [m]  (lla2ecef, transformations.py:216-235)
+  double T[9];         // trans_uvw_ecef, row-major, as in transformations.py:341-343
+} ssa_obs;
+
+// hx for the 'aer' observation type.  out = [az, el, range]
+SSA_HD void ssa_hx_aer(const double* x, const ssa_obs* o, double* out) {
+  // x_itrs = M @ x[:3]
+  double xi[3], d[3], e[3];
+  for (int i = 0; i < 3; ++i)
+    xi[i] = ssa_fma(o->M[3 * i + 2], x[2], ssa_fma(o->M[3 * i + 1], x[1], ssa_mul(o->M[3 * i], x[0])));
+  for (int i = 0; i < 3; ++i) d[i] = xi[i] - o->obs_itrs[i];
+  // R_enz = T^T @ delta
+  for (int i = 0; i < 3; ++i)
+    e[i] = ssa_fma(o->T[6 + i], d[2], ssa_fma(o->T[3 + i], d[1], ssa_mul(o->T[i], d[0])));
+  const double r = ssa_sqrt(ssa_fma(d[2], d[2], ssa_fma(d[1], d[1], ssa_mul(d[0], d[0]))));
+  double az = ssa_atan2(e[1], e[0]);
+  if (az < 0.0) az = az + SSA_C(TWOPI);
+  out[0] = az;
+  out[1] = ssa_asin(ssa_div(e[2], r));
+  out[2] = r;
+}
+
+SSA_HD void ssa_aer2uvw(const double* aer, double* uvw) {
+  double sa, ca, se, ce;
+  ssa_sincos(aer[0], &sa, &ca);
+  ssa_sincos(aer[1], &se, &ce);
+  const double rc = ssa_mul(aer[2], ce);
+  uvw[0] = ssa_mul(rc, ca);
+  uvw[1] = ssa_mul(rc, sa);
+  uvw[2] = ssa_mul(aer[2], se);
+}
+
+SSA_HD void ssa_uvw2aer(const double* uvw, double* aer) {
+  const double r = ssa_sqrt(ssa_fma(uvw[2], uvw[2], ssa_fma(uvw[1], uvw[1], ssa_mul(uvw[0], uvw[0]))));
+  double az = ssa_atan2(uvw[1], uvw[0]);
+  if (az < 0.0) az = az + SSA_C(TWOPI);
+  aer[0] = az;
+  aer[1] = ssa_asin(ssa_div(uvw[2], r));
+  aer[2] = r;
+}
+
+// residual_z_aer.  The reference wraps the azimuth difference through atan2(sin d, cos d)
+// (dynamics.py:263).  For |d| < pi that expression IS d (to within an ulp of d, and d is the exact value), so
+// the wrap — one sincos and one atan2, 13 times per update — is only evaluated when it does something.
+SSA_HD void ssa_residual_aer(const double* a, const double* b, double* c) {
+  const double d = a[0] - b[0];
+  if (ssa_fabs(d) < SSA_C(PI)) {
+    c[0] = d;
+  } else {
+    double s, co;
+    ssa_sincos(d, &s, &co);
+    c[0] = ssa_atan2(s, co);
+  }
+  c[1] = a[1] - b[1];
+  c[2] = a[2] - b[2];
+}

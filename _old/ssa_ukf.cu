@@ -27,10 +27,7 @@
 #include <new>
 #include <numeric>
 
-#include <cuda.h>
-#include <cudaTypedefs.h>
-
-#include "../../include/ssa_ukf.h"
+#include "inc/ssa_ukf.h"
 #include "ssa_math.h"
 #include "ssa_meas.h"
 #include "ssa_orbit.h"
@@ -528,62 +525,26 @@ __device__ __forceinline__ void store_sentinel(const KParams& p, long obj) {
       p.P[ssa_pidx(i, j) * ld + obj] = (i == j) ? (i < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL) : 0.0;
 }
 
-// ---- bulk-async staging (TMA engine, 1-D cp.async.bulk) of the per-object columns ---------------------------------
-// A thread-per-object kernel on a C2-sized batch has ~1 warp per SM sub-partition: nothing hides a load, and the
-// ~100 L2 round trips that k_update makes one after the other (the compiler cannot hoist 135 loads into 128
-// registers) were 70 % of its run time (ncu: long_scoreboard 13.8 of 19 cycles per issue).  The staged variants
-// fetch every row tile the block will read with a few 2-D TMA tile loads (box = 32 objects x up to 81 rows of the
-// [rows][ld] SoA arrays; the scratch arrays and the state arrays are each ONE tensor, so k_update needs three
-// loads), all in flight together, completion counted by one mbarrier; every thread then reads only
-// its own column of the tile, so no further synchronisation is needed.  The arithmetic is the same template body.
-// MEASURED on B200 (k_update -> k_update_staged): 24.3 -> 16.4 us at C2, 75 -> 66 us at 125 k objects, 0.493 ->
-// 0.433 ms at 1 M.  The same treatment of k_ut (78 rows of F) did not pay (12.3 -> 12.3 us at C2, 0.221 -> 0.248 ms
-// at 1 M: that kernel already front-loads its loads with 246 registers and is bounded by the Cholesky chain), so
-// k_ut stays a plain global-load kernel.
-// (A first version issued one 1-D bulk copy per row from different lanes: UBLKCP is a uniform-datapath
-// instruction, so the compiler serialised the 135 copies through an ELECT loop, ~1000 extra instructions.)
-__device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// one TMA tile load: box (32 columns x the map's row count) at column c0, row c1 of a [rows][ld] fp64 array
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                   smem_u32(dst)),
-               "l"((uint64_t)tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-  } while (!ok);
-}
-
-// The unscented transform of the propagated points (UKF.predict, then the fork's re-draw).  F = the thread's column of
-// the propagated sigma set, fs = its row stride.
-__device__ __forceinline__ void ut_body(const KParams& p, long loc, long obj, const double* F, long fs) {
+__global__ void __launch_bounds__(kSplitThreads, SSA_LB_UT) k_ut(const KParams p) {
+  const long loc = (long)blockIdx.x * blockDim.x + threadIdx.x;  // index inside the chunk
+  if (loc >= p.Nc) return;
+  const long obj = p.obj0 + loc;
   const long lds = p.lds;
+  if (!(p.flags & SSA_STEP_PREDICT)) return;
   const long ld = p.ld;
   int st = p.status[obj];
   if (st & SSA_ST_FAILED) return;
   int code = p.code[obj];
   if (!code && p.exc[obj]) code = SSA_ST_FXEXC;
   if (!code) {
+    const double* F = p.F + loc;
     double xb[6];
     int nan = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      double acc = ssa_mul(p.Wm[0], F[i * fs]);
+      double acc = ssa_mul(p.Wm[0], F[i * lds]);
 #pragma unroll
-      for (int k = 1; k < SSA_NSIG; ++k) acc = ssa_fma(p.Wm[k], F[(k * 6 + i) * fs], acc);
+      for (int k = 1; k < SSA_NSIG; ++k) acc = ssa_fma(p.Wm[k], F[(k * 6 + i) * lds], acc);
       xb[i] = acc;
       nan |= ssa_isnan(acc);
     }
@@ -594,7 +555,7 @@ __device__ __forceinline__ void ut_body(const KParams& p, long loc, long obj, co
     for (int k = 0; k < SSA_NSIG; ++k) {
       double y[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) y[i] = F[(k * 6 + i) * fs] - xb[i];
+      for (int i = 0; i < 6; ++i) y[i] = F[(k * 6 + i) * lds] - xb[i];
 #pragma unroll
       for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -624,17 +585,6 @@ __device__ __forceinline__ void ut_body(const KParams& p, long loc, long obj, co
   }
   p.code[obj] = code;
 }
-
-__global__ void __launch_bounds__(kSplitThreads, SSA_LB_UT) k_ut(const KParams p) {
-  const long loc = (long)blockIdx.x * blockDim.x + threadIdx.x;  // index inside the chunk
-  if (loc >= p.Nc) return;
-  if (!(p.flags & SSA_STEP_PREDICT)) return;
-  ut_body(p, loc, p.obj0 + loc, p.F + loc, p.lds);
-}
-
-// Rows of the scratch tensor [U 21][F 78][ZS 39][UVW 39][ZT 3] and of the state tensor [xt 6][x 6][P 21]
-constexpr int SC_U = 0, SC_ZS = 99, SC_ROWS = 180;
-constexpr int ST_ROWS = 33;
 
 // object index of update slot `idx` (ALL: identity; ACT: the tasked object of env idx), -1 if none
 __device__ __forceinline__ long upd_object(const KParams& p, long lidx) {
@@ -707,37 +657,23 @@ __global__ void __launch_bounds__(kSplitThreads, SSA_LB_HX) k_hx(const KParams p
   for (int a = 0; a < 3; ++a) p.ZS[(k * 3 + a) * lds + loc] = z[a];
 }
 
-// Row offsets of the staged tile of k_update_staged
-constexpr int UR_ZS = 0, UR_UVW = 39, UR_ZT = 78, UR_U = 81, UR_XT = 102, UR_X = 108, UR_P = 114, UR_ROWS = 135;
-
-// UKF.update + epilogue of one object.  STAGED = false: every operand is read from global memory (k_update);
-// STAGED = true: from the block's shared tile `sm` (already offset by the thread's column, row stride ss).
-template <bool STAGED>
-__device__ __forceinline__ void update_body(const KParams& p, long loc, long obj, const double* sm, int ss) {
+__global__ void __launch_bounds__(kSplitThreads, SSA_LB_UPD) k_update(const KParams p) {
+  const long loc = (long)blockIdx.x * blockDim.x + threadIdx.x;  // index inside the chunk
+  if (loc >= p.Nc) return;
+  const long obj = p.obj0 + loc;
   const long lds = p.lds;
   const long ld = p.ld;
   const int flags = p.flags;
-#define V_ZS(e) (STAGED ? sm[(UR_ZS + (e)) * ss] : p.ZS[(e) * lds + loc])
-#define V_UVW(e) (STAGED ? sm[(UR_UVW + (e)) * ss] : p.UVW[(e) * lds + loc])
-#define V_U(e) (STAGED ? sm[(UR_U + (e)) * ss] : p.U[(e) * lds + loc])
-#define V_P(e) (STAGED ? sm[(UR_P + (e)) * ss] : p.P[(e) * ld + obj])
-#define V_X(e) (STAGED ? sm[(UR_X + (e)) * ss] : p.x[(e) * ld + obj])
-#define V_XT(e) (STAGED ? sm[(UR_XT + (e)) * ss] : p.xt[(e) * ld + obj])
-#define V_ZT(e) (STAGED ? sm[(UR_ZT + (e)) * ss] : p.ZT[(e) * lds + loc])
   int st = p.status[obj];
   bool want_upd = (flags & SSA_STEP_UPDATE_ALL) != 0;
   if (flags & SSA_STEP_UPDATE_ACT) want_upd = want_upd || (p.actions[obj / p.m] == (int)(obj % p.m));
   int updated = 0;
   int code = 0;
-  // the state as the epilogue will see it: the prior, overwritten below by the update (or by the failure sentinel)
-  double xe[6], dg[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) { xe[i] = V_X(i); dg[i] = V_P(ssa_pidx(i, i)); }
   if (want_upd && !(st & SSA_ST_FAILED)) {
     double zt[3];
     const int visible = p.visible[obj];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) zt[a] = (p.obs_type == SSA_OBS_AER) ? V_ZT(a) : V_XT(a);
+    for (int a = 0; a < 3; ++a) zt[a] = (p.obs_type == SSA_OBS_AER) ? p.ZT[a * lds + loc] : p.xt[a * ld + obj];
     if (p.z_true) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) p.z_true[obj * 3 + a] = zt[a];
@@ -747,25 +683,27 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
     } else if (visible) {
       double x[6], z[3], zp[3];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) x[i] = xe[i];
+      for (int i = 0; i < 6; ++i) x[i] = p.x[i * ld + obj];
 #pragma unroll
       for (int a = 0; a < 3; ++a) z[a] = zt[a] + (p.z_noise ? p.z_noise[obj * 3 + a] : 0.0);
+      const double* ZS = p.ZS + loc;
       if (p.obs_type == SSA_OBS_AER) {
+        const double* UV = p.UVW + loc;
         double zm[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          double acc = ssa_mul(p.Wm[0], V_UVW(a));
+          double acc = ssa_mul(p.Wm[0], UV[a * lds]);
 #pragma unroll
-          for (int k = 1; k < SSA_NSIG; ++k) acc = ssa_fma(p.Wm[k], V_UVW(k * 3 + a), acc);
+          for (int k = 1; k < SSA_NSIG; ++k) acc = ssa_fma(p.Wm[k], UV[(k * 3 + a) * lds], acc);
           zm[a] = acc;
         }
         ssa_uvw2aer(zm, zp);
       } else {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          double acc = ssa_mul(p.Wm[0], V_ZS(a));
+          double acc = ssa_mul(p.Wm[0], ZS[a * lds]);
 #pragma unroll
-          for (int k = 1; k < SSA_NSIG; ++k) acc = ssa_fma(p.Wm[k], V_ZS(k * 3 + a), acc);
+          for (int k = 1; k < SSA_NSIG; ++k) acc = ssa_fma(p.Wm[k], ZS[(k * 3 + a) * lds], acc);
           zp[a] = acc;
         }
       }
@@ -784,7 +722,7 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
       for (int k = 0; k < SSA_NSIG; ++k) {
         double zk[3], rz[3], sk[6];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) zk[a] = V_ZS(k * 3 + a);
+        for (int a = 0; a < 3; ++a) zk[a] = ZS[(k * 3 + a) * lds];
         if (p.obs_type == SSA_OBS_AER) ssa_residual_aer(zk, zp, rz);
         else {
 #pragma unroll
@@ -793,15 +731,8 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
         if (from_f) {
 #pragma unroll
           for (int i = 0; i < 6; ++i) sk[i] = p.F[(k * 6 + i) * lds + loc];
-        } else {  // sigma point k re-drawn around the prior: x +- U[r, :]
-          const int r = (k == 0) ? -1 : (k - 1) % 6;
-          const bool minus = k > 6;
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            double u = 0.0;
-            if (r >= 0 && r <= j) u = V_U(ssa_pidx(r, j));
-            sk[j] = minus ? (x[j] - u) : (x[j] + u);
-          }
+        } else {
+          load_sigma(p, loc, k, x, sk);
         }
         if (p.obs_type == SSA_OBS_AER) {
 #pragma unroll
@@ -853,7 +784,6 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
         const double xn = x[i] + ssa_fma(K[3 * i + 2], yr[2], ssa_fma(K[3 * i + 1], yr[1], ssa_mul(K[3 * i], yr[0])));
         nan |= ssa_isnan(xn);
         p.x[i * ld + obj] = xn;
-        xe[i] = xn;
       }
 #pragma unroll
       for (int i = 0; i < 6; ++i)
@@ -861,9 +791,7 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
         for (int j = i; j < 6; ++j) {
           const int e = ssa_pidx(i, j);
           const double kt = ssa_fma(K[3 * i + 2], T[12 + j], ssa_fma(K[3 * i + 1], T[6 + j], ssa_mul(K[3 * i], T[j])));
-          const double pn = V_P(e) - kt;
-          p.P[e * ld + obj] = pn;
-          if (i == j) dg[i] = pn;
+          p.P[e * ld + obj] = p.P[e * ld + obj] - kt;
         }
       if (p.y) {
 #pragma unroll
@@ -875,7 +803,7 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
       }
       if (p.sigmas_h) {
 #pragma unroll 1
-        for (int e = 0; e < 39; ++e) p.sigmas_h[obj * 39 + e] = V_ZS(e);
+        for (int e = 0; e < 39; ++e) p.sigmas_h[obj * 39 + e] = ZS[e * lds];
       }
       updated = 1;
       if (!ok) code = SSA_ST_LINALG | SSA_ST_IN_UPDATE;
@@ -883,8 +811,6 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
     }
     if (code) {
       store_sentinel(p, obj);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) xe[i] = dg[i] = (i < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL);
       st |= SSA_ST_FAILED | code;
       p.status[obj] = st;
     }
@@ -892,57 +818,20 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
   if (p.updated) p.updated[obj] = (uint8_t)updated;
   if (p.status_out) p.status_out[obj] = st;
   if (flags & SSA_STEP_EPILOGUE) {
-    double xt[6];
+    double x[6], xt[6], dg[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) xt[i] = V_XT(i);
+    for (int i = 0; i < 6; ++i) { x[i] = p.x[i * ld + obj]; xt[i] = p.xt[i * ld + obj]; dg[i] = p.P[ssa_pidx(i, i) * ld + obj]; }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { p.obs[obj * 12 + i] = xe[i]; p.obs[obj * 12 + 6 + i] = dg[i]; }
-    const double d0 = xe[0] - xt[0], d1 = xe[1] - xt[1], d2 = xe[2] - xt[2];
-    const double d3 = xe[3] - xt[3], d4 = xe[4] - xt[4], d5 = xe[5] - xt[5];
+    for (int i = 0; i < 6; ++i) { p.obs[obj * 12 + i] = x[i]; p.obs[obj * 12 + 6 + i] = dg[i]; }
+    const double d0 = x[0] - xt[0], d1 = x[1] - xt[1], d2 = x[2] - xt[2];
+    const double d3 = x[3] - xt[3], d4 = x[4] - xt[4], d5 = x[5] - xt[5];
     p.dpos[obj] = ssa_sqrt(ssa_fma(d2, d2, ssa_fma(d1, d1, ssa_mul(d0, d0))));
     p.dvel[obj] = ssa_sqrt(ssa_fma(d5, d5, ssa_fma(d4, d4, ssa_mul(d3, d3))));
     p.spos[obj] = ssa_sqrt((dg[0] + dg[1]) + dg[2]);
     p.svel[obj] = ssa_sqrt((dg[3] + dg[4]) + dg[5]);
     p.trace[obj] = ((((dg[0] + dg[1]) + dg[2]) + dg[3]) + dg[4]) + dg[5];
   }
-#undef V_ZS
-#undef V_UVW
-#undef V_U
-#undef V_P
-#undef V_X
-#undef V_XT
-#undef V_ZT
 }
-
-__global__ void __launch_bounds__(kSplitThreads, SSA_LB_UPD) k_update(const KParams p) {
-  const long loc = (long)blockIdx.x * blockDim.x + threadIdx.x;  // index inside the chunk
-  if (loc >= p.Nc) return;
-  update_body<false>(p, loc, p.obj0 + loc, nullptr, 0);
-}
-
-// Launched instead of k_update for an update of EVERY object (SSA_STEP_UPDATE_ALL, resampled sigma points).
-__global__ void __launch_bounds__(32) k_update_staged(const KParams p, const __grid_constant__ CUtensorMap tm_z,
-                                                       const __grid_constant__ CUtensorMap tm_u,
-                                                       const __grid_constant__ CUtensorMap tm_s) {
-  extern __shared__ __align__(128) double tile[];  // [UR_ROWS][32], then the mbarrier
-  uint64_t* bar = (uint64_t*)(tile + UR_ROWS * 32);
-  const int col0 = blockIdx.x * 32;
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    mbar_expect_tx(bar, UR_ROWS * 256);
-    tma_load_2d(tile + UR_ZS * 32, &tm_z, col0, SC_ZS, bar);               // ZS, UVW, ZT: 81 rows
-    tma_load_2d(tile + UR_U * 32, &tm_u, col0, SC_U, bar);                 // U: 21 rows
-    tma_load_2d(tile + UR_XT * 32, &tm_s, (int)p.obj0 + col0, 0, bar);     // xt, x, P: 33 rows
-  }
-  __syncwarp();
-  const long loc = col0 + threadIdx.x;
-  mbar_wait(bar, 0);
-  if (loc >= p.Nc) return;
-  update_body<true>(p, loc, p.obj0 + loc, tile + threadIdx.x, 32);
-}
-
-constexpr int kUpdStagedSmem = UR_ROWS * 32 * 8 + 16;
-constexpr long kStagedMaxDefault = 1L << 40;
 
 // ---- team-mapped variants of the two per-object kernels (experiment, off by default) ------------------------
 // With C2-sized batches (20 000 objects) a thread-per-object kernel has only ~4 warps per SM and is a latency
@@ -1462,26 +1351,6 @@ __global__ void ssa_unit_inv3_kernel(const double* S, double* SI, int32_t* ok, i
 }
 
 thread_local char g_err[512] = "";
-// 2-D tensor map over a row-major [rows][ld] fp64 array with a box of 32 columns x box_rows rows (no swizzle: a
-// thread reads only its own column of the tile).  cuTensorMapEncodeTiled is resolved through the runtime so that
-// the library does not link against libcuda.
-int make_tmap(CUtensorMap* tm, const double* base, long ld, int rows, int box_rows) {
-  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
-  if (!enc) {
-    cudaDriverEntryPointQueryResult q;
-    void* fn = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return 1;
-    enc = (PFN_cuTensorMapEncodeTiled_v12000)fn;
-  }
-  const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
-  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1u, 1u};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 1;
-}
-
 int set_err(const char* what, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
   return SSA_ECUDA;
@@ -1513,8 +1382,6 @@ struct ssa_ukf {
   int32_t* step_idx;  // [E]
   int32_t *code, *exc;
   long chunk;     // objects per chunk of the split pipeline (scratch capacity); N when everything fits in L2
-  long staged_max;  // chunks up to this many objects use the TMA-staged k_update (default: all)
-  CUtensorMap tm_z, tm_u, tm_s;
   int team_small; // SSA_UKF_TEAM_SMALL=1: team-mapped UT / update kernels for batches <= kTeamMaxN (slower; tests)
   int use_team;   // SSA_UKF_KERNEL=team selects the fused 16-lane team kernel instead of the split pipeline
   // double-buffered host pipeline (ssa_ukf_step_host)
@@ -1633,14 +1500,6 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
     h->use_team = (kv && strcmp(kv, "team") == 0) ? 1 : 0;
     const char* ts = getenv("SSA_UKF_TEAM_SMALL");
     h->team_small = (ts && strcmp(ts, "1") == 0) ? 1 : 0;
-    h->staged_max = kStagedMaxDefault;
-    const char* sv = getenv("SSA_UKF_STAGED_MAX");
-    if (sv) h->staged_max = atol(sv);
-    cudaFuncSetAttribute(k_update_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdStagedSmem);
-    // tensor maps of the two SoA tensors (scratch [180][lds], state [33][ld]); one map per box height
-    const int rc = make_tmap(&h->tm_z, h->scratch, lds, SC_ROWS, 81) |
-                   make_tmap(&h->tm_u, h->scratch, lds, SC_ROWS, 21) | make_tmap(&h->tm_s, h->xt, ld, ST_ROWS, ST_ROWS);
-    if (rc) { ssa_ukf_destroy(h); return set_err("cuTensorMapEncodeTiled", cudaErrorUnknown); }
   }
   if ((e = cudaMalloc(&h->visible, 2 * ld + E)) != cudaSuccess) { ssa_ukf_destroy(h); return set_err("cudaMalloc(u8)", e); }
   cudaMemset(h->visible, 0, 2 * ld + E);
@@ -1870,7 +1729,6 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
     if (predict || truth) { k_fx<<<dim3(gobj, 14), kSplitThreads, 0, st>>>(p); h->launches++; }
     if (evc) CK(cudaEventRecord(evc[2], st));
     const bool small = h->team_small && p.Nc <= kTeamMaxN;
-    const bool staged = p.Nc <= h->staged_max;
     const unsigned gteam = (unsigned)((p.Nc + kTeamsPerCta - 1) / kTeamsPerCta);
     if (predict) {
       if (small) k_ut_team<<<gteam, kCtaThreads, 0, st>>>(p);
@@ -1882,8 +1740,6 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
     if (evc) CK(cudaEventRecord(evc[4], st));
     if (update || epi) {
       if (small) k_update_team<<<gteam, kCtaThreads, 0, st>>>(p);
-      else if (staged && p.resample && (flags & SSA_STEP_UPDATE_ALL))
-        k_update_staged<<<(unsigned)((p.Nc + 31) / 32), 32, kUpdStagedSmem, st>>>(p, h->tm_z, h->tm_u, h->tm_s);
       else k_update<<<gobj, kSplitThreads, 0, st>>>(p);
       h->launches++;
     }
