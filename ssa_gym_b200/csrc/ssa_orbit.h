@@ -397,7 +397,10 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   const double rr = ssa_dot3(r, r), vv = ssa_dot3(v, v), rv = ssa_dot3(r, v), hh = ssa_dot3(h, h);
   const double rn = ssa_sqrt_i(rr), hn = ssa_sqrt_i(hh);
   const double hxy2 = ssa_fma(h[1], h[1], ssa_mul(h[0], h[0]));
-  bool fast = (rn > 0.0) && (hn > 0.0) && (hxy2 > 0.0);
+  // planar: the orbit plane is the reference plane (h along +z exactly: the GEO class of the reference's catalog,
+  // inclination drawn from uniform(0, 0)).  rv2coe then calls the orbit equatorial and puts the node on the x axis.
+  const bool planar = (hxy2 == 0.0);
+  bool fast = (rn > 0.0) && (hn > 0.0) && (hxy2 > 0.0 || h[2] > 0.0);
   double ecc = 0.0, e_ce = 0.0, ci = 0.0, inv_hn = 0.0, inv_rn = 0.0;
   if (fast) {
     inv_rn = ssa_div_i(1.0, rn);
@@ -409,7 +412,11 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
     inv_hn = ssa_div_i(1.0, hn);
     ci = ssa_mul(h[2], inv_hn);
     e_ce = ssa_fma(ssa_mul(rn, vv), kinv, -1.0);
-    fast = (ecc >= SSA_C(TOL8)) && (ecc < SSA_C(DELTA99)) && (ci < 1.0);
+    // Circular orbits: rv2coe drops the periapsis direction when ecc < 1e-8 (argp = 0, nu = argument of latitude)
+    // but keeps ecc in the anomaly conversions, an O(a ecc) inconsistency; keeping the direction, as this path
+    // does, agrees with it to a * ecc, so only ecc < 1e-12 (< 5e-5 m) may take this path; [1e-12, 1e-8) goes to
+    // the literal restatement.
+    fast = ((ecc >= SSA_C(TOL8)) || (ecc < SSA_C(TOL12))) && (ecc < SSA_C(DELTA99)) && (planar || ci < 1.0);
   }
   if (!fast) return ssa_fx_general(x, tof, out);
 
@@ -449,15 +456,16 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   const double d1 = ssa_div_i(1.0, ssa_fma(-ecc, sc1.c, 1.0));
   const double cnu = ssa_mul(sc1.c - ecc, d1), snu = ssa_mul(ssa_mul(sq, sc1.s), d1);
   // argument of latitude of the initial position: px = r.n, py = r.(h x n)/|h|, n = (-h_y, h_x, 0)
-  const double px = ssa_fma(r[1], h[0], -ssa_mul(r[0], h[1]));
-  const double py = ssa_mul(ssa_fma(r[2], hxy2, -ssa_mul(h[2], ssa_fma(r[1], h[1], ssa_mul(r[0], h[0])))), inv_hn);
+  const double px = planar ? r[0] : ssa_fma(r[1], h[0], -ssa_mul(r[0], h[1]));
+  const double py =
+      planar ? r[1] : ssa_mul(ssa_fma(r[2], hxy2, -ssa_mul(h[2], ssa_fma(r[1], h[1], ssa_mul(r[0], h[0])))), inv_hn);
   const double hxy = ssa_sqrt_i(hxy2);
-  const double inv_hxy = ssa_div_i(1.0, hxy);
+  const double inv_hxy = ssa_div_i(1.0, planar ? 1.0 : hxy);
   const double inv_rho = ssa_mul(inv_rn, inv_hxy);  // sqrt(px^2 + py^2) = |r| h_xy: r lies in the orbital plane
   const double cu0 = ssa_mul(px, inv_rho), su0 = ssa_mul(py, inv_rho);
   const double cw = ssa_fma(cu0, cnu0, ssa_mul(su0, snu0)), sw = ssa_fma(su0, cnu0, -ssa_mul(cu0, snu0));
   // rotation (farnocchia.py:90-97) from the vectors
-  const double cO = -ssa_mul(h[1], inv_hxy), sO = ssa_mul(h[0], inv_hxy);
+  const double cO = planar ? 1.0 : -ssa_mul(h[1], inv_hxy), sO = planar ? 0.0 : ssa_mul(h[0], inv_hxy);
   const double si = ssa_mul(hxy, inv_hn);
   // perifocal position / velocity (farnocchia.py:70-72)
   const double rp = ssa_mul(a, ssa_fma(-ecc, sc1.c, 1.0));  // p/(1 + e cos nu) = a (1 - e cos E)

@@ -28,6 +28,7 @@
 #include <numeric>
 
 #include <cuda.h>
+#include <utility>
 #include <cudaTypedefs.h>
 
 #include "../../include/ssa_ukf.h"
@@ -433,6 +434,14 @@ __global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) 
 // same sequence of rounded operations as in the team kernel and the host twin.
 // =====================================================================================================
 constexpr int kSplitThreads = 128;
+#ifndef SSA_FX_THREADS
+#define SSA_FX_THREADS 128
+#endif
+#ifndef SSA_OBJ_THREADS
+#define SSA_OBJ_THREADS 128
+#endif
+constexpr int kFxThreads = SSA_FX_THREADS;    // block size of the per-sigma-point kernels k_fx / k_hx
+constexpr int kObjThreads = SSA_OBJ_THREADS;  // block size of the per-object kernels k_factor / k_ut
 #ifndef SSA_LB_FX
 #define SSA_LB_FX 8
 #endif
@@ -449,7 +458,17 @@ constexpr int kSplitThreads = 128;
 #define SSA_LB_HX 8
 #endif
 
-__global__ void __launch_bounds__(kSplitThreads, SSA_LB_FAC) k_factor(const KParams p) {
+// Programmatic dependent launch: the five kernels of a step form a chain on one stream.  Each kernel lets its
+// successor be scheduled as soon as all of its own blocks are resident (launch_dependents) and waits for the
+// complete, flushed results of its predecessor before touching memory (wait) — so the successor's launch latency
+// and block ramp-up overlap the predecessor's tail.  Both instructions are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kObjThreads, SSA_LB_FAC * 128 / kObjThreads) k_factor(const KParams p) {
+  pdl_prologue();
   const long loc = (long)blockIdx.x * blockDim.x + threadIdx.x;  // index inside the chunk
   if (loc >= p.Nc) return;
   const long obj = p.obj0 + loc;
@@ -487,7 +506,8 @@ __device__ __forceinline__ void load_sigma(const KParams& p, long loc, int k, co
   }
 }
 
-__global__ void __launch_bounds__(kSplitThreads, SSA_LB_FX) k_fx(const KParams p) {
+__global__ void __launch_bounds__(kFxThreads, SSA_LB_FX * 128 / kFxThreads) k_fx(const KParams p) {
+  pdl_prologue();
   const long loc = (long)blockIdx.x * blockDim.x + threadIdx.x;  // index inside the chunk
   if (loc >= p.Nc) return;
   const long obj = p.obj0 + loc;
@@ -625,7 +645,8 @@ __device__ __forceinline__ void ut_body(const KParams& p, long loc, long obj, co
   p.code[obj] = code;
 }
 
-__global__ void __launch_bounds__(kSplitThreads, SSA_LB_UT) k_ut(const KParams p) {
+__global__ void __launch_bounds__(kObjThreads, SSA_LB_UT * 128 / kObjThreads) k_ut(const KParams p) {
+  pdl_prologue();
   const long loc = (long)blockIdx.x * blockDim.x + threadIdx.x;  // index inside the chunk
   if (loc >= p.Nc) return;
   if (!(p.flags & SSA_STEP_PREDICT)) return;
@@ -650,7 +671,8 @@ __device__ __forceinline__ long upd_object(const KParams& p, long lidx) {
   return -1;
 }
 
-__global__ void __launch_bounds__(kSplitThreads, SSA_LB_HX) k_hx(const KParams p) {
+__global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx(const KParams p) {
+  pdl_prologue();
   const long lidx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int k = blockIdx.y;
   const long ld = p.ld;
@@ -915,6 +937,7 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
 }
 
 __global__ void __launch_bounds__(kSplitThreads, SSA_LB_UPD) k_update(const KParams p) {
+  pdl_prologue();
   const long loc = (long)blockIdx.x * blockDim.x + threadIdx.x;  // index inside the chunk
   if (loc >= p.Nc) return;
   update_body<false>(p, loc, p.obj0 + loc, nullptr, 0);
@@ -925,6 +948,7 @@ __global__ void __launch_bounds__(32) k_update_staged(const KParams p, const __g
                                                        const __grid_constant__ CUtensorMap tm_u,
                                                        const __grid_constant__ CUtensorMap tm_s) {
   extern __shared__ __align__(128) double tile[];  // [UR_ROWS][32], then the mbarrier
+  pdl_prologue();
   uint64_t* bar = (uint64_t*)(tile + UR_ROWS * 32);
   const int col0 = blockIdx.x * 32;
   if (threadIdx.x == 0) {
@@ -1482,6 +1506,22 @@ int make_tmap(CUtensorMap* tm, const double* base, long ld, int rows, int box_ro
   return r == CUDA_SUCCESS ? 0 : 1;
 }
 
+// launch with the programmatic-stream-serialization attribute (see pdl_prologue)
+template <typename... KArgs, typename... Args>
+void launch_chain(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 int set_err(const char* what, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
   return SSA_ECUDA;
@@ -1515,6 +1555,7 @@ struct ssa_ukf {
   long chunk;     // objects per chunk of the split pipeline (scratch capacity); N when everything fits in L2
   long staged_max;  // chunks up to this many objects use the TMA-staged k_update (default: all)
   CUtensorMap tm_z, tm_u, tm_s;
+  int pdl;  // programmatic dependent launch of the step's kernel chain (SSA_UKF_PDL=0 turns it off)
   int team_small; // SSA_UKF_TEAM_SMALL=1: team-mapped UT / update kernels for batches <= kTeamMaxN (slower; tests)
   int use_team;   // SSA_UKF_KERNEL=team selects the fused 16-lane team kernel instead of the split pipeline
   // double-buffered host pipeline (ssa_ukf_step_host)
@@ -1633,6 +1674,8 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
     h->use_team = (kv && strcmp(kv, "team") == 0) ? 1 : 0;
     const char* ts = getenv("SSA_UKF_TEAM_SMALL");
     h->team_small = (ts && strcmp(ts, "1") == 0) ? 1 : 0;
+    const char* pv = getenv("SSA_UKF_PDL");
+    h->pdl = (pv && strcmp(pv, "0") == 0) ? 0 : 1;
     h->staged_max = kStagedMaxDefault;
     const char* sv = getenv("SSA_UKF_STAGED_MAX");
     if (sv) h->staged_max = atol(sv);
@@ -1864,27 +1907,30 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
     p.obj0 = o0;
     p.Nc = (int)((c.n_objects - o0) < h->chunk ? (c.n_objects - o0) : h->chunk);
     const unsigned gobj = (unsigned)((p.Nc + kSplitThreads - 1) / kSplitThreads);
+    const unsigned gobj2 = (unsigned)((p.Nc + kObjThreads - 1) / kObjThreads);
+    const unsigned gfx = (unsigned)((p.Nc + kFxThreads - 1) / kFxThreads);
     cudaEvent_t* evc = (ev && o0 == 0) ? ev : nullptr;
-    if (predict || update) { k_factor<<<gobj, kSplitThreads, 0, st>>>(p); h->launches++; }
+    const bool pdl = h->pdl && !ev;
+    if (predict || update) { launch_chain(pdl, k_factor, gobj2, kObjThreads, 0, st, p); h->launches++; }
     if (evc) CK(cudaEventRecord(evc[1], st));
-    if (predict || truth) { k_fx<<<dim3(gobj, 14), kSplitThreads, 0, st>>>(p); h->launches++; }
+    if (predict || truth) { launch_chain(pdl, k_fx, dim3(gfx, 14), kFxThreads, 0, st, p); h->launches++; }
     if (evc) CK(cudaEventRecord(evc[2], st));
     const bool small = h->team_small && p.Nc <= kTeamMaxN;
     const bool staged = p.Nc <= h->staged_max;
     const unsigned gteam = (unsigned)((p.Nc + kTeamsPerCta - 1) / kTeamsPerCta);
     if (predict) {
       if (small) k_ut_team<<<gteam, kCtaThreads, 0, st>>>(p);
-      else k_ut<<<gobj, kSplitThreads, 0, st>>>(p);
+      else launch_chain(pdl, k_ut, gobj2, kObjThreads, 0, st, p);
       h->launches++;
     }
     if (evc) CK(cudaEventRecord(evc[3], st));
-    if (update || epi) { k_hx<<<dim3(gobj, 14), kSplitThreads, 0, st>>>(p); h->launches++; }
+    if (update || epi) { launch_chain(pdl, k_hx, dim3(gfx, 14), kFxThreads, 0, st, p); h->launches++; }
     if (evc) CK(cudaEventRecord(evc[4], st));
     if (update || epi) {
       if (small) k_update_team<<<gteam, kCtaThreads, 0, st>>>(p);
       else if (staged && p.resample && (flags & SSA_STEP_UPDATE_ALL))
-        k_update_staged<<<(unsigned)((p.Nc + 31) / 32), 32, kUpdStagedSmem, st>>>(p, h->tm_z, h->tm_u, h->tm_s);
-      else k_update<<<gobj, kSplitThreads, 0, st>>>(p);
+        launch_chain(pdl, k_update_staged, (unsigned)((p.Nc + 31) / 32), 32, kUpdStagedSmem, st, p, h->tm_z, h->tm_u, h->tm_s);
+      else launch_chain(pdl, k_update, gobj, kSplitThreads, 0, st, p);
       h->launches++;
     }
     if (evc) CK(cudaEventRecord(evc[5], st));

@@ -31,6 +31,37 @@ def test_fx_full_catalog(c2):
             assert err.max() < 1e-11 and np.quantile(err, 0.999) < 1e-13 and np.median(err) < 1e-15
 
 
+def test_fx_planar_and_circular_regimes(c2):
+    """The GEO class of the reference's catalog is exactly equatorial (dynamics.py:388 draws the inclination from
+    uniform(0, 0)) and half of it exactly circular: rv2coe takes its equatorial / circular branches there
+    (farnocchia.py:281-309).  The product propagates these states on its streamlined path (node on the x axis,
+    periapsis direction kept when ecc < 1e-12); eccentricities in [1e-12, 1e-8) go through the literal branch."""
+    from ssa_gym_b200.catalog import coe2rv
+    cat = c2[0]
+    h = np.cross(cat[:, :3], cat[:, 3:])
+    planar = (h[:, 0] ** 2 + h[:, 1] ** 2) == 0
+    assert planar.sum() > 4000
+    rng = np.random.RandomState(5)
+    n = 2000
+    a = rng.uniform(6378137.0 + 400e3, 42164e3, n)
+    inc, raan, nu = rng.uniform(0.01, 3.1, n), rng.uniform(0, 6.28, n), rng.uniform(0, 6.28, n)
+    sets = [cat[planar]] + [coe2rv(a * (1 - e * e), np.full(n, e), inc, raan, np.zeros(n), nu)
+                            for e in (0.0, 1e-14, 5e-13, 2e-12, 1e-10, 5e-9, 2e-8)]
+    for states in sets:
+        for dt in (20.0, 6000.0, 86400.0):
+            o, eo = H.lib_fx("oracle", states, dt)
+            t, et = H.lib_fx("twin", states, dt)
+            assert not eo.any() and not et.any()
+            rn = np.linalg.norm(o[:, :3], axis=1)[:, None]
+            vn = np.linalg.norm(o[:, 3:], axis=1)[:, None]
+            err = np.concatenate([np.abs(t[:, :3] - o[:, :3]) / rn, np.abs(t[:, 3:] - o[:, 3:]) / vn], 1)
+            # (a day is ~15 LEO revolutions: the phase error n * tof grows with the number of revolutions)
+            assert err.max() < 1e-12 and np.median(err) < (1e-15 if dt < 1e4 else 5e-15)
+    # a planar orbit stays planar, bit for bit (z and vz exactly zero), like the reference's
+    t, _ = H.lib_fx("twin", cat[planar], 6000.0)
+    assert np.all(t[:, 2] == 0) and np.all(t[:, 5] == 0)
+
+
 def test_fx_invariants_at_full_size(c2):
     """Size-independent properties of two-body propagation: energy and angular momentum are conserved and
     fx(fx(x, dt), -dt) returns to x."""
