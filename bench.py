@@ -318,30 +318,35 @@ def main():
     barrier()
     b2b_ms = e0.elapsed_time(e1) / a.steps
 
-    # ---- e2e: the user-facing call with HOST buffers: H2D z_noise + M each step, D2H obs + errors ----
-    zn_pin = torch.from_numpy(zn).pin_memory()
-    obs_pin = torch.empty((n_obj, 12), dtype=torch.float64).pin_memory()
-    dpos_pin = torch.empty(n_obj, dtype=torch.float64).pin_memory()
-    st_pin = torch.empty(n_obj, dtype=torch.int32).pin_memory()
-    zn_np, obs_np, dpos_np, st_np = zn_pin.numpy(), obs_pin.numpy(), dpos_pin.numpy(), st_pin.numpy()
-    # every step: H2D of that step's z_noise (pinned) + M, the kernels, D2H of obs / delta_pos / status into pinned
-    # host buffers (ssa_ukf_step_host: double-buffered, copies overlap the neighbouring steps' kernels)
-    for w in range(3):
-        ukf.step_host(M, flags, z_noise=zn_np[w % 8], obs_out=obs_np, dpos_out=dpos_np, status_out=st_np, stream=sp)
+    # ---- e2e: the user-facing call with HOST buffers: every step ONE H2D copy of that step's inputs (z_noise +
+    # trans_matrix) from the handle's pinned input block, the kernel chain (one captured graph launch), ONE D2H copy
+    # of obs / delta_pos / status into the pinned output block (ssa_ukf_step_pinned: double-buffered, the copies
+    # overlap the neighbouring steps' kernels).  The two pinned input blocks hold two of the pre-drawn noise slices.
+    io = ukf.host_io()
+    for b_ in range(2):
+        io[b_]["z_noise"][:] = zn[b_]
+        io[b_]["M"][:] = M.reshape(9)
+    for w in range(4):
+        ukf.step_pinned(flags, stream=sp)
     ukf.host_join(stream=sp)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_e0 = ukf.launch_count
     e0.record(stream)
     for s in range(a.steps):
-        ukf.step_host(M, flags, z_noise=zn_np[s % 8], obs_out=obs_np, dpos_out=dpos_np, status_out=st_np, stream=sp)
+        b_ = ukf.next_parity
+        io[b_]["M"][:] = M.reshape(9)  # this step's trans_matrix[i] (72 B) travels with the noise
+        ukf.step_pinned(flags, stream=sp)
     ukf.host_join(stream=sp)
     e1.record(stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1) / a.steps
+    e2e_launches = ukf.launch_count - launches_e0
+    obs_np = io[0]["obs"]
     clocks = sampler.stop()  # sampled over both timed regions (value and e2e)
     assert np.isfinite(obs_np).all()
-    h2d = zn_np[0].nbytes + 72
-    d2h = obs_np.nbytes + dpos_np.nbytes + st_np.nbytes
+    h2d = io[0]["z_noise"].nbytes + 80 + 8  # z_noise, trans_matrix (+1 pad double), the env's action word
+    d2h = io[0]["obs"].nbytes + (ukf.ld + ukf.ld // 2) * 8
 
     # ---- reduce over ranks (max time) --------------------------------------------------------------
     t = torch.tensor([total_ms, b2b_ms, e2e_ms], dtype=torch.float64, device="cuda")
@@ -397,7 +402,8 @@ def main():
                          "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"}},
             "e2e": {"value": e2e_val, "unit": "object-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms},
+                    "ms_per_step": e2e_ms, "gpu_launches": int(e2e_launches),
+                    "api": "BatchedUKF.step_pinned (ssa_ukf_step_pinned): pinned host I/O blocks, 1 H2D + 1 graph launch + 1 D2H per step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "extra": {"ms_per_step_back_to_back_no_flush": b2b_ms, "wall_s_timed_region": t_wall, "failed_filters": n_failed,

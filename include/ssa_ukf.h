@@ -151,7 +151,20 @@ int ssa_ukf_step_profile(ssa_ukf* h, const double M[9], int flags, void* stream,
 int ssa_ukf_step_host(ssa_ukf* h, const double M[9], int flags, const int32_t* actions_host,
                       const double* z_noise_host, double* obs_host, double* delta_pos_host,
                       int32_t* status_host, void* stream);
-/* make `stream` wait for every outstanding internal copy of ssa_ukf_step_host */
+/* Pinned-I/O variant of ssa_ukf_step_host for launch-bound batch sizes.  The handle owns two pinned host input
+ * blocks and two pinned host output blocks (one per pipeline parity); ssa_ukf_host_io returns their addresses:
+ *   inputs   z_noise [N][3], M [9] (the step's trans_matrix[i]), actions [E]
+ *   outputs  obs [N][12], delta_pos [N], status [N]
+ * The caller fills the inputs of the parity the next call will use (parities alternate 0,1,0,... from the first
+ * call; *parity_used reports it), calls ssa_ukf_step_pinned, and reads the outputs of that parity after
+ * ssa_ukf_host_join + a synchronize of `stream`.  Per call: ONE host-to-device copy, the step's kernel chain as ONE
+ * captured CUDA graph launch (SSA_UKF_GRAPH=0: plain launches), ONE device-to-host copy - the same arithmetic as
+ * ssa_ukf_step (the trans_matrix is read from the uploaded block instead of the launch parameters).  Replaces the
+ * same reference lines as ssa_ukf_step_host (SS2:259-322, histories SS2:278-322).                               */
+int ssa_ukf_host_io(ssa_ukf* h, int parity, double** z_noise, double** M, int32_t** actions, double** obs,
+                    double** delta_pos, int32_t** status);
+int ssa_ukf_step_pinned(ssa_ukf* h, int flags, void* stream, int* parity_used);
+/* make `stream` wait for every outstanding internal copy of ssa_ukf_step_host / ssa_ukf_step_pinned */
 int ssa_ukf_host_join(ssa_ukf* h, void* stream);
 /* Convenience wrappers with the reference's call structure */
 int ssa_ukf_predict(ssa_ukf* h, void* stream);                      /* truth + predict              */

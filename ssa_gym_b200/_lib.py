@@ -57,6 +57,8 @@ PROTOTYPES = {
     "ssa_ukf_step_profile": (_I, [c_void_p, c_void_p, _I, c_void_p, c_double_p]),
     "ssa_ukf_step_host": (_I, [c_void_p, c_void_p, _I, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ssa_ukf_host_join": (_I, [c_void_p, c_void_p]),
+    "ssa_ukf_host_io": (_I, [c_void_p, _I] + [c_void_p] * 6),
+    "ssa_ukf_step_pinned": (_I, [c_void_p, _I, c_void_p, c_void_p]),
     "ssa_ukf_predict": (_I, [c_void_p, c_void_p]),
     "ssa_ukf_update": (_I, [c_void_p, c_void_p, _I, c_void_p]),
     "ssa_ukf_env_reduce": (_I, [c_void_p, c_void_p, _I, c_void_p]),

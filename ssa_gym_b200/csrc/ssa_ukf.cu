@@ -70,7 +70,8 @@ struct KParams {
   // inputs
   const int32_t* actions;  // [E]
   const double* z_noise;   // [N][3] AoS
-  const double* Menv;      // [E][9] per-env trans_matrix (SSA_STEP_M_PER_ENV) or null
+  const double* Menv;      // device-resident trans_matrix: [E][9] per env (Mstride 9) or one for all (Mstride 0); null = p.ob.M
+  int Mstride;
   // outputs
   double* obs;             // [N][12] AoS
   double* dpos; double* dvel; double* spos; double* svel; double* trace;  // [ld]
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) 
     ssa_obs ob = p.ob;
     if (p.Menv) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(obj / p.m) * 9 + i];
+      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(obj / p.m) * p.Mstride + i];
     }
     ssa_hx_aer(hin, &ob, zk);
     // broadcast the truth measurement of lane 13
@@ -687,7 +688,7 @@ __global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx
     ssa_obs ob = p.ob;
     if (p.Menv) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(idx / p.m) * 9 + i];
+      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(idx / p.m) * p.Mstride + i];
     }
     ssa_hx_aer(xt, &ob, zt);
 #pragma unroll
@@ -715,7 +716,7 @@ __global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx
     ssa_obs ob = p.ob;
     if (p.Menv) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(obj / p.m) * 9 + i];
+      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(obj / p.m) * p.Mstride + i];
     }
     ssa_hx_aer(s, &ob, z);
     ssa_aer2uvw(z, uvw);
@@ -1564,8 +1565,17 @@ struct ssa_ukf {
     long calls;
     cudaStream_t up, dn;
     cudaEvent_t e_up[2], e_c[2], e_dn[2];
-    double* block[2];   // [obs 12N][dpos dvel spos svel trace: 5 ld][z_noise 3N]
-    int32_t* iblock[2];  // [status_out ld][actions E]
+    // device block per parity, in doubles:
+    //   OUT  [obs 12N][dpos ld][status ld int32]        <- one D2H copy in the pinned mode
+    //        [dvel ld][spos ld][svel ld][trace ld]
+    //   IN   [z_noise 3N][M 9][pad 1][actions E int32]  <- one H2D copy in the pinned mode
+    double* block[2];
+    double* hin[2];     // pinned host mirror of IN  (ssa_ukf_host_io)
+    double* hout[2];    // pinned host mirror of OUT
+    size_t out_doubles, in_off, in_doubles;
+    cudaGraphExec_t gexec[2];  // the step's kernel chain captured per parity (ssa_ukf_step_pinned)
+    int gflags[2], gkernels[2];
+    int use_graph;
   } hp;
   int32_t *status, *infl, *actions, *greedy;
   uint8_t *visible, *updated, *done;
@@ -1700,7 +1710,8 @@ int ssa_ukf_destroy(ssa_ukf* h) {
   if (h->hp.init) {
     cudaStreamSynchronize(h->hp.up); cudaStreamSynchronize(h->hp.dn);
     for (int b = 0; b < 2; ++b) {
-      cudaFree(h->hp.block[b]); cudaFree(h->hp.iblock[b]);
+      cudaFree(h->hp.block[b]); cudaFreeHost(h->hp.hin[b]); cudaFreeHost(h->hp.hout[b]);
+      if (h->hp.gexec[b]) cudaGraphExecDestroy(h->hp.gexec[b]);
       cudaEventDestroy(h->hp.e_up[b]); cudaEventDestroy(h->hp.e_c[b]); cudaEventDestroy(h->hp.e_dn[b]);
     }
     cudaStreamDestroy(h->hp.up); cudaStreamDestroy(h->hp.dn);
@@ -1856,7 +1867,8 @@ int ssa_ukf_download(ssa_ukf* h, int field, void* host, size_t bytes, void* stre
 
 static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cudaEvent_t* ev, int hostbuf = -1) {
   if (!h) return SSA_EINVAL;
-  if ((flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE)) && !M && !(flags & SSA_STEP_M_PER_ENV)) {
+  if ((flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE)) && !M && !(flags & SSA_STEP_M_PER_ENV) &&
+      hostbuf < 0) {
     snprintf(g_err, sizeof(g_err), "trans_matrix required for update/epilogue");
     return SSA_EINVAL;
   }
@@ -1868,6 +1880,7 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
   p.xt = h->xt; p.x = h->x; p.P = h->P; p.status = h->status; p.infl = h->infl;
   p.actions = h->actions; p.z_noise = h->z_noise;
   p.Menv = (flags & SSA_STEP_M_PER_ENV) ? h->Menv : nullptr;
+  p.Mstride = 9;
   p.obs = h->obs; p.dpos = h->dpos; p.dvel = h->dvel; p.spos = h->spos; p.svel = h->svel; p.trace = h->trace;
   if (flags & SSA_STEP_RECORD) { p.z_true = h->z_true; p.y = h->y; p.S = h->S; p.sigmas_h = h->sigmas_h; }
   p.visible = h->visible; p.updated = h->updated;
@@ -1882,10 +1895,14 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
   if (hostbuf >= 0) {  // outputs / inputs of the double-buffered host pipeline
     const long N_ = c.n_objects, ld_ = h->ld;
     double* b = h->hp.block[hostbuf];
-    p.obs = b; p.dpos = b + 12 * N_; p.dvel = p.dpos + ld_; p.spos = p.dvel + ld_; p.svel = p.spos + ld_; p.trace = p.svel + ld_;
-    p.z_noise = p.trace + ld_;
-    p.status_out = h->hp.iblock[hostbuf];
-    p.actions = h->hp.iblock[hostbuf] + ld_;
+    p.obs = b; p.dpos = b + 12 * N_; p.status_out = (int32_t*)(p.dpos + ld_);
+    p.dvel = p.dpos + ld_ + ld_ / 2; p.spos = p.dvel + ld_; p.svel = p.spos + ld_; p.trace = p.svel + ld_;
+    p.z_noise = b + h->hp.in_off;
+    p.actions = (const int32_t*)(p.z_noise + 3 * N_ + 10);
+    if (!M && !(flags & SSA_STEP_M_PER_ENV)) {  // pinned mode: the trans_matrix arrives with the input block
+      p.Menv = p.z_noise + 3 * N_;
+      p.Mstride = 0;
+    }
   }
   if (M) memcpy(p.ob.M, M, sizeof(p.ob.M));
   memcpy(p.ob.obs_itrs, c.obs_itrs, sizeof(p.ob.obs_itrs));
@@ -1946,11 +1963,23 @@ static int hostpipe_init(ssa_ukf* h) {
   const size_t N = h->cfg.n_objects, E = h->cfg.n_envs, ld = h->ld;
   CK(cudaStreamCreateWithFlags(&h->hp.up, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->hp.dn, cudaStreamNonBlocking));
+  h->hp.out_doubles = 12 * N + ld + ld / 2;
+  h->hp.in_off = h->hp.out_doubles + 4 * ld;
+  h->hp.in_doubles = 3 * N + 10 + (E + 1) / 2;
+  {
+    const char* gv = getenv("SSA_UKF_GRAPH");
+    h->hp.use_graph = (gv && strcmp(gv, "0") == 0) ? 0 : 1;
+  }
   for (int b = 0; b < 2; ++b) {
-    CK(cudaMalloc(&h->hp.block[b], sizeof(double) * (12 * N + 5 * ld + 3 * N)));
-    CK(cudaMemset(h->hp.block[b], 0, sizeof(double) * (12 * N + 5 * ld + 3 * N)));
-    CK(cudaMalloc(&h->hp.iblock[b], sizeof(int32_t) * (ld + E)));
-    CK(cudaMemset(h->hp.iblock[b], 0, sizeof(int32_t) * (ld + E)));
+    const size_t tot = h->hp.in_off + h->hp.in_doubles;
+    CK(cudaMalloc(&h->hp.block[b], sizeof(double) * tot));
+    CK(cudaMemset(h->hp.block[b], 0, sizeof(double) * tot));
+    CK(cudaHostAlloc(&h->hp.hin[b], sizeof(double) * h->hp.in_doubles, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&h->hp.hout[b], sizeof(double) * h->hp.out_doubles, cudaHostAllocDefault));
+    memset(h->hp.hin[b], 0, sizeof(double) * h->hp.in_doubles);
+    memset(h->hp.hout[b], 0, sizeof(double) * h->hp.out_doubles);
+    h->hp.gexec[b] = nullptr;
+    h->hp.gflags[b] = -1;
     CK(cudaEventCreateWithFlags(&h->hp.e_up[b], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->hp.e_c[b], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->hp.e_dn[b], cudaEventDisableTiming));
@@ -1971,12 +2000,13 @@ int ssa_ukf_step_host(ssa_ukf* h, const double M[9], int flags, const int32_t* a
   const size_t N = h->cfg.n_objects, E = h->cfg.n_envs, ld = h->ld;
   const int b = h->hp.parity;
   double* blk = h->hp.block[b];
-  int32_t* iblk = h->hp.iblock[b];
-  double* zn_dev = blk + 12 * N + 5 * ld;
+  int32_t* iblk = (int32_t*)(blk + 12 * N + ld);
+  double* zn_dev = blk + h->hp.in_off;
+  if (!M) { snprintf(g_err, sizeof(g_err), "ssa_ukf_step_host: trans_matrix required"); return SSA_EINVAL; }
   // upload stream: buffer b is free once the compute of two calls ago has consumed it
   if (h->hp.calls >= 2) CK(cudaStreamWaitEvent(h->hp.up, h->hp.e_c[b], 0));
   if (z_noise_host) CK(cudaMemcpyAsync(zn_dev, z_noise_host, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, h->hp.up));
-  if (actions_host) CK(cudaMemcpyAsync(iblk + ld, actions_host, sizeof(int32_t) * E, cudaMemcpyHostToDevice, h->hp.up));
+  if (actions_host) CK(cudaMemcpyAsync(zn_dev + 3 * N + 10, actions_host, sizeof(int32_t) * E, cudaMemcpyHostToDevice, h->hp.up));
   CK(cudaEventRecord(h->hp.e_up[b], h->hp.up));
   // compute on the caller's stream: needs this step's inputs and a drained output buffer
   CK(cudaStreamWaitEvent(st, h->hp.e_up[b], 0));
@@ -2001,6 +2031,77 @@ int ssa_ukf_host_join(ssa_ukf* h, void* stream) {
   CK(cudaSetDevice(h->device));
   const long nb = h->hp.calls >= 2 ? 2 : h->hp.calls;
   for (int b = 0; b < nb; ++b) CK(cudaStreamWaitEvent((cudaStream_t)stream, h->hp.e_dn[b], 0));
+  return SSA_OK;
+}
+
+int ssa_ukf_host_io(ssa_ukf* h, int parity, double** z_noise, double** M, int32_t** actions, double** obs,
+                    double** delta_pos, int32_t** status) {
+  if (!h || parity < 0 || parity > 1) return SSA_EINVAL;
+  CK(cudaSetDevice(h->device));
+  int rc = hostpipe_init(h);
+  if (rc) return rc;
+  const size_t N = h->cfg.n_objects, ld = h->ld;
+  double* in = h->hp.hin[parity];
+  double* out = h->hp.hout[parity];
+  if (z_noise) *z_noise = in;
+  if (M) *M = in + 3 * N;
+  if (actions) *actions = (int32_t*)(in + 3 * N + 10);
+  if (obs) *obs = out;
+  if (delta_pos) *delta_pos = out + 12 * N;
+  if (status) *status = (int32_t*)(out + 12 * N + ld);
+  return SSA_OK;
+}
+
+int ssa_ukf_step_pinned(ssa_ukf* h, int flags, void* stream, int* parity_used) {
+  if (!h) return SSA_EINVAL;
+  if (flags & SSA_STEP_M_PER_ENV) { snprintf(g_err, sizeof(g_err), "ssa_ukf_step_pinned: one trans_matrix per call"); return SSA_EINVAL; }
+  CK(cudaSetDevice(h->device));
+  int rc = hostpipe_init(h);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int b = h->hp.parity;
+  double* blk = h->hp.block[b];
+  // upload stream: the device buffer is free once the compute of two calls ago has consumed it
+  if (h->hp.calls >= 2) CK(cudaStreamWaitEvent(h->hp.up, h->hp.e_c[b], 0));
+  CK(cudaMemcpyAsync(blk + h->hp.in_off, h->hp.hin[b], sizeof(double) * h->hp.in_doubles, cudaMemcpyHostToDevice, h->hp.up));
+  CK(cudaEventRecord(h->hp.e_up[b], h->hp.up));
+  // compute on the caller's stream: needs this step's inputs and a drained output buffer
+  CK(cudaStreamWaitEvent(st, h->hp.e_up[b], 0));
+  if (h->hp.calls >= 2) CK(cudaStreamWaitEvent(st, h->hp.e_dn[b], 0));
+  if (h->hp.use_graph && !h->use_team) {
+    if (!h->hp.gexec[b] || h->hp.gflags[b] != flags) {  // (re)capture the kernel chain of this parity
+      if (h->hp.gexec[b]) { cudaGraphExecDestroy(h->hp.gexec[b]); h->hp.gexec[b] = nullptr; }
+      cudaStream_t cs;
+      CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      const long l0 = h->launches;
+      CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      rc = step_impl(h, nullptr, flags, cs, nullptr, b);
+      cudaGraph_t g = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(cs, &g);
+      h->hp.gkernels[b] = (int)(h->launches - l0);
+      h->launches = l0;
+      cudaStreamDestroy(cs);
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (ce != cudaSuccess) return set_err("cudaStreamEndCapture", ce);
+      const cudaError_t ie = cudaGraphInstantiate(&h->hp.gexec[b], g, 0);
+      cudaGraphDestroy(g);
+      if (ie != cudaSuccess) return set_err("cudaGraphInstantiate", ie);
+      h->hp.gflags[b] = flags;
+    }
+    CK(cudaGraphLaunch(h->hp.gexec[b], st));
+    h->launches += h->hp.gkernels[b];
+  } else {
+    rc = step_impl(h, nullptr, flags, stream, nullptr, b);
+    if (rc) return rc;
+  }
+  CK(cudaEventRecord(h->hp.e_c[b], st));
+  // download stream
+  CK(cudaStreamWaitEvent(h->hp.dn, h->hp.e_c[b], 0));
+  CK(cudaMemcpyAsync(h->hp.hout[b], blk, sizeof(double) * h->hp.out_doubles, cudaMemcpyDeviceToHost, h->hp.dn));
+  CK(cudaEventRecord(h->hp.e_dn[b], h->hp.dn));
+  if (parity_used) *parity_used = b;
+  h->hp.parity ^= 1;
+  h->hp.calls++;
   return SSA_OK;
 }
 

@@ -189,6 +189,40 @@ class BatchedUKF:
     def host_join(self, stream=None):
         _lib.check(self.lib.ssa_ukf_host_join(self.h, stream), "ssa_ukf_host_join")
 
+    def host_io(self):
+        """The handle's pinned host I/O blocks as numpy views, one dict per pipeline parity:
+        inputs 'z_noise' [N,3], 'M' [9], 'actions' [E]; outputs 'obs' [N,12], 'delta_pos' [N], 'status' [N]."""
+        if getattr(self, "_io", None) is None:
+            N, E = self.N, self.n_envs
+            io = []
+            for b in range(2):
+                ptrs = [ctypes.c_void_p() for _ in range(6)]
+                _lib.check(self.lib.ssa_ukf_host_io(self.h, b, *[ctypes.byref(q) for q in ptrs]), "ssa_ukf_host_io")
+
+                def view(q, ctype, shape):
+                    n = int(np.prod(shape))
+                    return np.ctypeslib.as_array(ctypes.cast(q, ctypes.POINTER(ctype)), shape=(n,)).reshape(shape)
+
+                io.append({"z_noise": view(ptrs[0], ctypes.c_double, (N, 3)), "M": view(ptrs[1], ctypes.c_double, (9,)),
+                           "actions": view(ptrs[2], ctypes.c_int32, (E,)), "obs": view(ptrs[3], ctypes.c_double, (N, 12)),
+                           "delta_pos": view(ptrs[4], ctypes.c_double, (N,)), "status": view(ptrs[5], ctypes.c_int32, (N,))})
+            self._io = io
+            self._parity_out = ctypes.c_int(0)
+        return self._io
+
+    def step_pinned(self, flags, stream=None):
+        """Pipelined step on the pinned blocks of host_io(): fill host_io()[b] of the parity this call will use
+        (0, 1, 0, ... from the first call; `next_parity`), call, read host_io()[b] outputs after host_join()+sync.
+        One H2D copy, one graph launch, one D2H copy per call.  Returns the parity used."""
+        self.host_io()
+        _lib.check(self.lib.ssa_ukf_step_pinned(self.h, int(flags), stream, ctypes.byref(self._parity_out)), "ssa_ukf_step_pinned")
+        self._next_parity = self._parity_out.value ^ 1
+        return self._parity_out.value
+
+    @property
+    def next_parity(self):
+        return getattr(self, "_next_parity", 0)
+
     def predict(self, stream=None):
         _lib.check(self.lib.ssa_ukf_predict(self.h, stream), "ssa_ukf_predict")
 

@@ -204,6 +204,71 @@ def test_pipelined_host_step_equals_twin(kernel):
     ukf.close()
 
 
+@pytest.mark.parametrize("graph", ["1", "0"])
+def test_pinned_pipelined_step_equals_twin(graph, monkeypatch):
+    """ssa_ukf_step_pinned: the handle's pinned I/O blocks, ONE copy each way, the kernel chain as a captured CUDA
+    graph (graph=1) or plain launches (graph=0), trans_matrix read from the uploaded block.  Catalog mode (update
+    all, a different trans_matrix every step) and RL mode (actions through the pinned block) against the twin."""
+    monkeypatch.setenv("SSA_UKF_GRAPH", graph)
+    N, steps = 3000, 7
+    cat, x, P0, zn = H.c2_inputs(N, steps)
+    cfg = H.make_cfg(N)
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE
+    rng = np.random.RandomState(3)
+    Ms = [H.CEL2TER06AXY @ _rotz(1e-3 * s) for s in range(steps)]
+    ukf = BatchedUKF(n_envs=1, m=N, dt=20.0, Q=np.array(cfg.Q).reshape(6, 6), R=np.array(cfg.R).reshape(3, 3),
+                     obs_lla=[np.radians(H.OBSERVER_DEG[0]), np.radians(H.OBSERVER_DEG[1]), H.OBSERVER_DEG[2]],
+                     obs_limit_rad=np.radians(-90.0))
+    ukf.reset(cat, x, P0)
+    io = ukf.host_io()
+    st = H.HostState(cat, x, P0)
+    pending = None
+    for s in range(steps + 1):
+        if s < steps:
+            b = ukf.next_parity
+            if s >= 2:  # this parity's previous results are about to be overwritten: consume them first
+                ukf.host_join(); ukf.sync()
+            io[b]["z_noise"][:] = zn[s]
+            io[b]["M"][:] = Ms[s].reshape(9)
+            assert ukf.step_pinned(flags) == b
+        if s >= 1:  # check step s-1
+            ukf.host_join(); ukf.sync()
+            bp = (s - 1) & 1
+            H.cpu_step("twin", cfg, st, Ms[s - 1], flags, z_noise=zn[s - 1])
+            assert H.bits_equal(io[bp]["obs"], st.obs) and H.bits_equal(io[bp]["delta_pos"], st.dpos), s
+            assert np.array_equal(io[bp]["status"], st.status), s
+    assert H.bits_equal(ukf.download(F.F_X_FILTER), st.x)
+    ukf.close()
+    # RL mode: E envs x m objects, update only the tasked object of every env
+    E, m = 300, 7
+    N = E * m
+    cat, x, P0, zn = H.c2_inputs(N, 4)
+    cfg = H.make_cfg(N, E=E, m=m)
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ACT | F.STEP_EPILOGUE
+    ukf = BatchedUKF(n_envs=E, m=m, dt=20.0, Q=np.array(cfg.Q).reshape(6, 6), R=np.array(cfg.R).reshape(3, 3),
+                     obs_lla=[np.radians(H.OBSERVER_DEG[0]), np.radians(H.OBSERVER_DEG[1]), H.OBSERVER_DEG[2]],
+                     obs_limit_rad=np.radians(-90.0))
+    ukf.reset(cat, x, P0)
+    io = ukf.host_io()
+    st = H.HostState(cat, x, P0)
+    for s in range(4):
+        act = rng.randint(0, m, size=E).astype(np.int32)
+        b = ukf.next_parity
+        io[b]["z_noise"][:] = zn[s]
+        io[b]["M"][:] = H.CEL2TER06AXY.reshape(9)
+        io[b]["actions"][:] = act
+        ukf.step_pinned(flags)
+        ukf.host_join(); ukf.sync()
+        H.cpu_step("twin", cfg, st, H.CEL2TER06AXY, flags, actions=act, z_noise=zn[s])
+        assert H.bits_equal(io[b]["obs"], st.obs) and np.array_equal(io[b]["status"], st.status), s
+    ukf.close()
+
+
+def _rotz(a):
+    c, s_ = np.cos(a), np.sin(a)
+    return np.array([[c, s_, 0.0], [-s_, c, 0.0], [0.0, 0.0, 1.0]])
+
+
 @pytest.mark.parametrize("chunk", ["640", "4000"])
 def test_chunked_execution_bitexact(chunk, monkeypatch):
     """Large batches run in L2-sized chunks (SSA_UKF_CHUNK objects per chunk, env-aligned in RL mode).  Forcing
