@@ -49,7 +49,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c3"])
+    ap.add_argument("--envs", type=int, default=4096, help="c3: parallel environments per GPU")
+    ap.add_argument("--rng", default="device", choices=["device", "host"], help="c3: episodic RNG mode of VecSSATaskerEnv")
     ap.add_argument("--objects", type=int, default=0, help="override objects per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -205,8 +207,95 @@ def make_cfg(N):
     return c
 
 
+def run_c3(a):
+    """BASELINE.json config 3: E parallel environments x default RSO count, one vectorised env step per call, actions
+    from the device-side greedy tasker, obs [E, m*12] fp64 handed to the host every step (the RLlib rollout shape).
+    Metric: env-steps per second through the public API (VecSSATaskerEnv.vector_step), i.e. end to end by
+    construction: every step copies the actions host->device and obs / reward / done device->host."""
+    import torch
+    import torch.distributed as dist
+    from ssa_gym_b200 import env_config, _lib as F
+    from ssa_gym_b200.catalog import synthetic_catalog
+    from ssa_gym_b200.transformations import gcrs2irts_matrix_approx, time_table
+    from ssa_gym_b200.ukf import fp64_peak_tflops
+    from ssa_gym_b200.vec_env import VecSSATaskerEnv
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the UKF hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    E = a.envs
+    cfg = dict(env_config)
+    cfg["orbits"] = synthetic_catalog(20000, 0)
+    cfg["trans_matrix"] = gcrs2irts_matrix_approx(time_table(cfg["t_0"], cfg["time_step"], cfg["steps"]))
+    m = cfg["rso_count"]
+    t0 = time.perf_counter()
+    env = VecSSATaskerEnv(cfg, E, seeds=[rank * E + e for e in range(E)], device=local_rank, rng=a.rng)
+    t_construct = time.perf_counter() - t0
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_done = 0
+    for w in range(max(a.warmup, 3)):
+        _, _, d, _ = env.vector_step(env.greedy_actions())
+    peak_tf = fp64_peak_tflops(local_rank, sp)
+    sampler = ClockSampler(local_rank)
+    launches0 = env.ukf.launch_count
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    tw0 = time.perf_counter()
+    for s in range(a.steps):
+        obs, r, d, _ = env.vector_step(env.greedy_actions())
+        n_done += int(d.sum())
+    e1.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - tw0
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = env.ukf.launch_count - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    val = E * world * a.steps / (ms * 1e-3)
+    flop_env_step = m * (14 * FLOP_FX + 2.0e3) + 6.9e3   # m predicts (14 fx + factorisations/UT) + one update
+    if rank == 0:
+        line = {"metric": "env-steps per second (vectorised ssa_tasker_simple_2, RL mode)", "value": val, "unit": "env-steps/s",
+                "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C3: {E} parallel envs x {m} RSOs per GPU, vector_step + device greedy tasker, obs to host",
+                           "envs_per_gpu": E, "rso_count": m, "episode_steps": cfg["steps"], "rng": a.rng, "reward_type": cfg["reward_type"],
+                           "l2": f"inputs/outputs larger than nothing to flush: every step moves {E * m * 12 * 8} B of fresh obs over PCIe"},
+                "object_predicts_per_s": val * m,
+                "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * E,
+                        "d2h_bytes_per_step": E * m * 12 * 8 + E * 8 + E * 16 + E, "ms_per_step": ms / a.steps,
+                        "api": "VecSSATaskerEnv.vector_step (ssa_ukf_rollout_step)" if a.rng == "device" else "VecSSATaskerEnv.vector_step"},
+                "roofline": {"bound": "fp64", "kernel": "whole env step", "achieved": val / world * flop_env_step / 1e12, "peak": peak_tf,
+                             "unit": "TFLOP/s", "frac": val / world * flop_env_step / 1e12 / peak_tf, "traffic": None,
+                             "note": "RL-mode step = m predicts + 1 update per env; at E*m = 40960 objects the step is launch/latency and "
+                                     "PCIe bound, not FP64 bound"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "extra": {"episodes_finished_in_timed_region": n_done, "construct_and_first_reset_s": t_construct,
+                          "wall_s_timed_region": t_wall}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     a = parse()
+    if a.workload == "c3" and a.impl != "reference":
+        return run_c3(a)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -164,6 +164,29 @@ int ssa_ukf_step_host(ssa_ukf* h, const double M[9], int flags, const int32_t* a
 int ssa_ukf_host_io(ssa_ukf* h, int parity, double** z_noise, double** M, int32_t** actions, double** obs,
                     double** delta_pos, int32_t** status);
 int ssa_ukf_step_pinned(ssa_ukf* h, int flags, void* stream, int* parity_used);
+/* ---- device-resident episodic mode (vectorised reset) ---------------------------------------------
+ * Replaces, for E parallel environments, the whole host side of an RL step: reset() with its catalog sampling and
+ * noise draws (SS2:193-241), the per-step bookkeeping of step() (SS2:243-367: step counter, trans_matrix[i],
+ * z_noise[i], update_interval gate SS2:292, reward / done SS2:324-354) and the auto-reset of finished episodes.
+ * Random numbers are counter-based (Philox4x32-10 keyed by the environment's seed, addressed by episode / object /
+ * step - csrc/ssa_rng.h): same distributions as the reference, NOT the same streams as its np_random (the host-RNG
+ * path ssa_ukf_reset + ssa_ukf_step keeps stream parity).  'shaped' rewards are not available here.
+ *   rollout_config  catalog [n_orbits][6], trans_matrix table [n_table][9] (row i = step i), one 64-bit seed per env,
+ *                   x_sigma[6], z_sigma[3] (radians / metres), P0[36], update_interval
+ *   rollout_io      pinned host blocks owned by the handle: actions [E] (in); obs [N][12], reward [E],
+ *                   greedy [E][SSA_N_TASKERS], done [E] (out)
+ *   rollout_reset   draw every environment, step index 0; outputs: obs, greedy
+ *   rollout_step    one step of every environment with the actions in the pinned block: ONE H2D copy, ONE CUDA-graph
+ *                   launch (noise, the five UKF kernels, reward / done, reset of the finished environments and their
+ *                   fresh obs when auto_reset, greedy taskers of the new state), ONE D2H copy.  Asynchronous on
+ *                   `stream`; outputs are valid after a synchronize.  With auto_reset the obs rows of a finished
+ *                   environment are those of its NEW episode; reward / done refer to the step just taken.        */
+int ssa_ukf_rollout_config(ssa_ukf* h, const double* orbits, int n_orbits, const double* trans_table, int n_table,
+                           const uint64_t* seeds, const double x_sigma[6], const double z_sigma[3], const double P0[36],
+                           int update_interval);
+int ssa_ukf_rollout_io(ssa_ukf* h, int32_t** actions, double** obs, double** reward, int32_t** greedy, uint8_t** done);
+int ssa_ukf_rollout_reset(ssa_ukf* h, void* stream);
+int ssa_ukf_rollout_step(ssa_ukf* h, int auto_reset, void* stream);
 /* make `stream` wait for every outstanding internal copy of ssa_ukf_step_host / ssa_ukf_step_pinned */
 int ssa_ukf_host_join(ssa_ukf* h, void* stream);
 /* Convenience wrappers with the reference's call structure */

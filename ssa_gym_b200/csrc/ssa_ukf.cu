@@ -35,6 +35,7 @@
 #include "ssa_math.h"
 #include "ssa_meas.h"
 #include "ssa_orbit.h"
+#include "ssa_rng.h"
 #include "ssa_ukf_core.h"
 
 namespace {
@@ -72,6 +73,8 @@ struct KParams {
   const double* z_noise;   // [N][3] AoS
   const double* Menv;      // device-resident trans_matrix: [E][9] per env (Mstride 9) or one for all (Mstride 0); null = p.ob.M
   int Mstride;
+  const int32_t* Mstep;    // episodic mode: Menv is the whole trans_matrix table [n][9], env e uses row Mstep[e] + Mbias
+  int Mbias, Mrows;
   // outputs
   double* obs;             // [N][12] AoS
   double* dpos; double* dvel; double* spos; double* svel; double* trace;  // [ld]
@@ -101,6 +104,16 @@ struct KParams {
 };
 
 __device__ __forceinline__ void team_sync(unsigned mask) { __syncwarp(mask); }
+
+// trans_matrix of environment e when it is device-resident (p.Menv != null)
+__device__ __forceinline__ const double* env_M(const KParams& p, long e) {
+  if (p.Mstep) {
+    int row = p.Mstep[e] + p.Mbias;
+    row = row < p.Mrows ? row : p.Mrows - 1;
+    return p.Menv + 9L * row;
+  }
+  return p.Menv + e * p.Mstride;
+}
 
 // The fused step.  Stage selection by p.flags (uniform across the grid).
 __global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) {
@@ -246,7 +259,7 @@ __global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) 
     ssa_obs ob = p.ob;
     if (p.Menv) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(obj / p.m) * p.Mstride + i];
+      for (int i = 0; i < 9; ++i) ob.M[i] = env_M(p, obj / p.m)[i];
     }
     ssa_hx_aer(hin, &ob, zk);
     // broadcast the truth measurement of lane 13
@@ -688,7 +701,7 @@ __global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx
     ssa_obs ob = p.ob;
     if (p.Menv) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(idx / p.m) * p.Mstride + i];
+      for (int i = 0; i < 9; ++i) ob.M[i] = env_M(p, idx / p.m)[i];
     }
     ssa_hx_aer(xt, &ob, zt);
 #pragma unroll
@@ -716,7 +729,7 @@ __global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx
     ssa_obs ob = p.ob;
     if (p.Menv) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) ob.M[i] = p.Menv[(obj / p.m) * p.Mstride + i];
+      for (int i = 0; i < 9; ++i) ob.M[i] = env_M(p, obj / p.m)[i];
     }
     ssa_hx_aer(s, &ob, z);
     ssa_aer2uvw(z, uvw);
@@ -1246,8 +1259,10 @@ struct EnvParams {
   const double* dpos; const double* dvel; const double* spos; const double* trace;
   const uint8_t* visible;
   double* reward; uint8_t* done; int32_t* greedy; double* env_stats;  // env_stats[E][4]: max dpos, trinary, argmax spos, n_visible
-  const int32_t* step_idx;  // per-env step counters (used when step_index < 0)
+  int32_t* step_idx;  // per-env step counters (used when step_index < 0)
   int E, m, reward_type, n_steps, step_index;
+  int increment;    // episodic mode: step_idx[e] += 1 before it is used (the device owns the counters)
+  int greedy_only;  // refresh greedy / env_stats only (after an auto-reset); reward and done stay
 };
 
 struct ArgMax { double v; int i; };
@@ -1310,7 +1325,8 @@ __global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) 
     for (int q = 0; q < 6; ++q) for (int k = 1; k < nw; ++k) sm[q][0] = am_better(sm[q][0], sm[q][k]);
     for (int k = 1; k < nw; ++k) { si[0][0] += si[0][k]; si[1][0] += si[1][k]; si[2][0] |= si[2][k]; }
     const double max_dpos = sm[5][0].v;
-    const int step_i = p.step_index >= 0 ? p.step_index : p.step_idx[e];
+    int step_i = p.step_index >= 0 ? p.step_index : p.step_idx[e];
+    if (p.increment) { step_i += 1; p.step_idx[e] = step_i; }
     // `if not np.any(visible)` tests the INDEX array: it is also false-y when the only visible
     // object is index 0 (agents.py:37) -> the reference samples a random action; we return -1.
     const int any_vis = si[2][0];
@@ -1323,6 +1339,7 @@ __global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) 
     p.env_stats[e * 4 + 1] = trinary;
     p.env_stats[e * 4 + 2] = (double)sm[4][0].i;
     p.env_stats[e * 4 + 3] = (double)si[1][0];
+    if (p.greedy_only) return;
     double reward = 0.0;
     int done = 0;
     if (p.reward_type == SSA_REWARD_JONES) {  // SS2:324-336
@@ -1338,6 +1355,62 @@ __global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) 
     if (step_i + 1 >= p.n_steps) done = 1;  // SS2:353-354
     p.reward[e] = reward;
     p.done[e] = (uint8_t)done;
+  }
+}
+
+// ---- device-resident episodic mode: vectorised reset and on-the-fly noise, see ssa_rng.h -----------
+struct RolloutParams {
+  double* xt; double* x; double* P; long ld;   // state (SoA)
+  int32_t* status; int32_t* infl;
+  double* z_noise;                            // [N][3]
+  const double* orbits; int n_orbits;         // catalog [n_orbits][6]
+  const uint32_t* key;                        // [E][2] Philox key of each environment (from its seed)
+  uint32_t* episode;                          // [E] resets performed so far
+  int32_t* step_idx;                          // [E]
+  const int32_t* actions; int32_t* act_eff;   // [E] requested / effective (update_interval) actions
+  const uint8_t* done;                        // [E] reset mask (null: every environment)
+  const double* sig;                          // x_sigma[6], z_sigma[3], packed P0[21]
+  int E, m, update_interval;
+};
+
+// start of a step: measurement noise of step i+1 for every object, effective action of every environment
+__global__ void __launch_bounds__(128) k_env_begin(const RolloutParams p) {
+  const long obj = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (obj >= (long)p.E * p.m) return;
+  const int e = (int)(obj / p.m), j = (int)(obj % p.m);
+  const int step = p.step_idx[e] + 1;
+  double n3[3];
+  ssa_draw_z(p.key[2 * e], p.key[2 * e + 1], p.episode[e] - 1u, (uint32_t)j, (uint32_t)step, n3);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) p.z_noise[obj * 3 + a] = ssa_mul(n3[a], p.sig[6 + a]);
+  if (j == 0) p.act_eff[e] = (step % p.update_interval == 0) ? p.actions[e] : -1;  // SS2:292
+}
+
+// (re)draw the environments whose done flag is set (all of them when p.done is null): SS2:193-221
+__global__ void __launch_bounds__(128) k_env_reset(const RolloutParams p) {
+  const int e = blockIdx.x;
+  if (p.done && !p.done[e]) return;
+  const uint32_t k0 = p.key[2 * e], k1 = p.key[2 * e + 1], ep = p.episode[e];
+  for (int j = threadIdx.x; j < p.m; j += blockDim.x) {
+    const long obj = (long)e * p.m + j;
+    const uint32_t row = ssa_draw_orbit(k0, k1, ep, (uint32_t)j, (uint32_t)p.n_orbits);
+    double n6[6];
+    ssa_draw_x(k0, k1, ep, (uint32_t)j, n6);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double xt = p.orbits[(long)row * 6 + i];
+      p.xt[i * p.ld + obj] = xt;
+      p.x[i * p.ld + obj] = xt + ssa_mul(n6[i], p.sig[i]);
+    }
+#pragma unroll
+    for (int q = 0; q < SSA_NP; ++q) p.P[q * p.ld + obj] = p.sig[9 + q];
+    p.status[obj] = 0;
+    p.infl[obj] = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    p.episode[e] = ep + 1u;
+    p.step_idx[e] = 0;
   }
 }
 
@@ -1577,6 +1650,21 @@ struct ssa_ukf {
     int gflags[2], gkernels[2];
     int use_graph;
   } hp;
+  // device-resident episodic mode (ssa_ukf_rollout_*)
+  struct {
+    int init, n_orbits, n_table, update_interval;
+    double* dbuf;        // device: orbits [n_orbits][6], table [n_table][9], sig [30]
+    double *orbits, *table, *sig;
+    uint32_t* ibuf;      // device: key [E][2], episode [E], act_in [E], act_eff [E]
+    uint32_t *key, *episode;
+    int32_t *act_in, *act_eff;
+    double* dout;        // device out block: [obs 12N][reward E][greedy 4E int32][done E uint8]
+    double* hout;        // pinned host mirror
+    int32_t* hin;        // pinned host actions [E]
+    size_t out_bytes;
+    cudaGraphExec_t gexec[2];  // [auto_reset]
+    int gkernels[2];
+  } ro;
   int32_t *status, *infl, *actions, *greedy;
   uint8_t *visible, *updated, *done;
   size_t stage_bytes;
@@ -1715,6 +1803,11 @@ int ssa_ukf_destroy(ssa_ukf* h) {
       cudaEventDestroy(h->hp.e_up[b]); cudaEventDestroy(h->hp.e_c[b]); cudaEventDestroy(h->hp.e_dn[b]);
     }
     cudaStreamDestroy(h->hp.up); cudaStreamDestroy(h->hp.dn);
+  }
+  if (h->ro.init) {
+    cudaFree(h->ro.dbuf); cudaFree(h->ro.ibuf); cudaFree(h->ro.dout);
+    cudaFreeHost(h->ro.hout); cudaFreeHost(h->ro.hin);
+    for (int i = 0; i < 2; ++i) if (h->ro.gexec[i]) cudaGraphExecDestroy(h->ro.gexec[i]);
   }
   cudaFree(h->stage);
   cudaFree(h->scratch);
@@ -1865,10 +1958,15 @@ int ssa_ukf_download(ssa_ukf* h, int field, void* host, size_t bytes, void* stre
   return SSA_OK;
 }
 
-static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cudaEvent_t* ev, int hostbuf = -1) {
+struct StepOverride {  // episodic mode: redirect the step's inputs / outputs
+  double* obs; const int32_t* actions; const double* table; const int32_t* step_idx; int bias, rows;
+};
+
+static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cudaEvent_t* ev, int hostbuf = -1,
+                     const StepOverride* ov = nullptr) {
   if (!h) return SSA_EINVAL;
   if ((flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE)) && !M && !(flags & SSA_STEP_M_PER_ENV) &&
-      hostbuf < 0) {
+      hostbuf < 0 && !ov) {
     snprintf(g_err, sizeof(g_err), "trans_matrix required for update/epilogue");
     return SSA_EINVAL;
   }
@@ -1903,6 +2001,10 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
       p.Menv = p.z_noise + 3 * N_;
       p.Mstride = 0;
     }
+  }
+  if (ov) {
+    p.obs = ov->obs; p.actions = ov->actions;
+    p.Menv = ov->table; p.Mstep = ov->step_idx; p.Mbias = ov->bias; p.Mrows = ov->rows;
   }
   if (M) memcpy(p.ob.M, M, sizeof(p.ob.M));
   memcpy(p.ob.obs_itrs, c.obs_itrs, sizeof(p.ob.obs_itrs));
@@ -2105,6 +2207,170 @@ int ssa_ukf_step_pinned(ssa_ukf* h, int flags, void* stream, int* parity_used) {
   return SSA_OK;
 }
 
+// ---- device-resident episodic mode ------------------------------------------------------------------------------
+static void rollout_params(ssa_ukf* h, RolloutParams* p, int only_done) {
+  p->xt = h->xt; p->x = h->x; p->P = h->P; p->ld = h->ld;
+  p->status = h->status; p->infl = h->infl; p->z_noise = h->z_noise;
+  p->orbits = h->ro.orbits; p->n_orbits = h->ro.n_orbits;
+  p->key = h->ro.key; p->episode = h->ro.episode; p->step_idx = h->step_idx;
+  p->actions = h->ro.act_in; p->act_eff = h->ro.act_eff;
+  const size_t N = h->cfg.n_objects, E = h->cfg.n_envs;
+  p->done = only_done ? (const uint8_t*)((int32_t*)(h->ro.dout + 12 * N + E) + SSA_N_TASKERS * E) : nullptr;
+  p->sig = h->ro.sig;
+  p->E = h->cfg.n_envs; p->m = h->cfg.m; p->update_interval = h->ro.update_interval;
+}
+
+static void rollout_env_params(ssa_ukf* h, EnvParams* p, int increment, int greedy_only) {
+  const size_t N = h->cfg.n_objects, E = h->cfg.n_envs;
+  p->dpos = h->dpos; p->dvel = h->dvel; p->spos = h->spos; p->trace = h->trace; p->visible = h->visible;
+  p->reward = h->ro.dout + 12 * N;
+  p->greedy = (int32_t*)(p->reward + E);
+  p->done = (uint8_t*)(p->greedy + SSA_N_TASKERS * E);
+  p->env_stats = h->env_stats;
+  p->E = h->cfg.n_envs; p->m = h->cfg.m; p->reward_type = h->cfg.reward_type; p->n_steps = h->cfg.n_steps;
+  p->step_index = -1; p->step_idx = h->step_idx; p->increment = increment; p->greedy_only = greedy_only;
+}
+
+// obs / errors / visibility of the current states + greedy taskers (after a reset)
+static int rollout_refresh(ssa_ukf* h, cudaStream_t st) {
+  StepOverride ov{h->ro.dout, h->ro.act_eff, h->ro.table, h->step_idx, 0, h->ro.n_table};
+  int rc = step_impl(h, nullptr, SSA_STEP_EPILOGUE, st, nullptr, -1, &ov);
+  if (rc) return rc;
+  EnvParams ep;
+  rollout_env_params(h, &ep, 0, 1);
+  ssa_env_reduce_kernel<<<(unsigned)ep.E, 128, 0, st>>>(ep);
+  h->launches++;
+  return SSA_OK;
+}
+
+int ssa_ukf_rollout_config(ssa_ukf* h, const double* orbits, int n_orbits, const double* trans_table, int n_table,
+                           const uint64_t* seeds, const double x_sigma[6], const double z_sigma[3], const double P0[36],
+                           int update_interval) {
+  if (!h || !orbits || n_orbits < 1 || !trans_table || n_table < 1 || !seeds || !x_sigma || !z_sigma || !P0 || update_interval < 1)
+    return SSA_EINVAL;
+  if (h->cfg.reward_type == SSA_REWARD_SHAPED) {
+    snprintf(g_err, sizeof(g_err), "episodic device mode: the 'shaped' reward needs the host-side reward history");
+    return SSA_EINVAL;
+  }
+  CK(cudaSetDevice(h->device));
+  const size_t N = h->cfg.n_objects, E = h->cfg.n_envs;
+  if (h->ro.init) {
+    cudaFree(h->ro.dbuf); cudaFree(h->ro.ibuf); cudaFree(h->ro.dout); cudaFreeHost(h->ro.hout); cudaFreeHost(h->ro.hin);
+    for (int i = 0; i < 2; ++i) if (h->ro.gexec[i]) { cudaGraphExecDestroy(h->ro.gexec[i]); h->ro.gexec[i] = nullptr; }
+    h->ro.init = 0;
+  }
+  h->ro.n_orbits = n_orbits; h->ro.n_table = n_table; h->ro.update_interval = update_interval;
+  CK(cudaMalloc(&h->ro.dbuf, sizeof(double) * ((size_t)n_orbits * 6 + (size_t)n_table * 9 + 32)));
+  h->ro.orbits = h->ro.dbuf; h->ro.table = h->ro.orbits + (size_t)n_orbits * 6; h->ro.sig = h->ro.table + (size_t)n_table * 9;
+  CK(cudaMemcpy(h->ro.orbits, orbits, sizeof(double) * (size_t)n_orbits * 6, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->ro.table, trans_table, sizeof(double) * (size_t)n_table * 9, cudaMemcpyHostToDevice));
+  double sig[30];
+  for (int i = 0; i < 6; ++i) sig[i] = x_sigma[i];
+  for (int i = 0; i < 3; ++i) sig[6 + i] = z_sigma[i];
+  { int q = 0; for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) sig[9 + q++] = P0[6 * i + j]; }
+  CK(cudaMemcpy(h->ro.sig, sig, sizeof(sig), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->ro.ibuf, sizeof(uint32_t) * 5 * E));
+  CK(cudaMemset(h->ro.ibuf, 0, sizeof(uint32_t) * 5 * E));
+  h->ro.key = h->ro.ibuf; h->ro.episode = h->ro.key + 2 * E;
+  h->ro.act_in = (int32_t*)(h->ro.episode + E); h->ro.act_eff = h->ro.act_in + E;
+  CK(cudaMemcpy(h->ro.key, seeds, sizeof(uint64_t) * E, cudaMemcpyHostToDevice));  // little-endian: key[2e] = low word
+  h->ro.out_bytes = sizeof(double) * (12 * N + E) + sizeof(int32_t) * SSA_N_TASKERS * E + ((E + 7) / 8) * 8;
+  CK(cudaMalloc(&h->ro.dout, h->ro.out_bytes));
+  CK(cudaMemset(h->ro.dout, 0, h->ro.out_bytes));
+  CK(cudaHostAlloc(&h->ro.hout, h->ro.out_bytes, cudaHostAllocDefault));
+  CK(cudaHostAlloc(&h->ro.hin, sizeof(int32_t) * E, cudaHostAllocDefault));
+  memset(h->ro.hout, 0, h->ro.out_bytes);
+  memset(h->ro.hin, 0, sizeof(int32_t) * E);
+  h->ro.gexec[0] = h->ro.gexec[1] = nullptr;
+  h->ro.init = 1;
+  return SSA_OK;
+}
+
+int ssa_ukf_rollout_io(ssa_ukf* h, int32_t** actions, double** obs, double** reward, int32_t** greedy, uint8_t** done) {
+  if (!h || !h->ro.init) return SSA_EINVAL;
+  const size_t N = h->cfg.n_objects, E = h->cfg.n_envs;
+  if (actions) *actions = h->ro.hin;
+  if (obs) *obs = h->ro.hout;
+  if (reward) *reward = h->ro.hout + 12 * N;
+  if (greedy) *greedy = (int32_t*)(h->ro.hout + 12 * N + E);
+  if (done) *done = (uint8_t*)((int32_t*)(h->ro.hout + 12 * N + E) + SSA_N_TASKERS * E);
+  return SSA_OK;
+}
+
+int ssa_ukf_rollout_reset(ssa_ukf* h, void* stream) {
+  if (!h || !h->ro.init) return SSA_EINVAL;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  RolloutParams rp;
+  rollout_params(h, &rp, 0);
+  k_env_reset<<<(unsigned)rp.E, 128, 0, st>>>(rp);
+  h->launches++;
+  int rc = rollout_refresh(h, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->ro.hout, h->ro.dout, h->ro.out_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaGetLastError());
+  return SSA_OK;
+}
+
+// the kernels of one episodic step (captured into a graph by ssa_ukf_rollout_step)
+static int rollout_chain(ssa_ukf* h, cudaStream_t st, int auto_reset) {
+  RolloutParams rp;
+  rollout_params(h, &rp, 1);
+  const long N = h->cfg.n_objects;
+  k_env_begin<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(rp);
+  h->launches++;
+  StepOverride ov{h->ro.dout, h->ro.act_eff, h->ro.table, h->step_idx, 1, h->ro.n_table};
+  int rc = step_impl(h, nullptr, SSA_STEP_TRUTH | SSA_STEP_PREDICT | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE, st, nullptr, -1, &ov);
+  if (rc) return rc;
+  EnvParams ep;
+  rollout_env_params(h, &ep, 1, 0);
+  ssa_env_reduce_kernel<<<(unsigned)ep.E, 128, 0, st>>>(ep);
+  h->launches++;
+  if (auto_reset) {
+    k_env_reset<<<(unsigned)rp.E, 128, 0, st>>>(rp);
+    h->launches++;
+    rc = rollout_refresh(h, st);
+    if (rc) return rc;
+  }
+  return SSA_OK;
+}
+
+int ssa_ukf_rollout_step(ssa_ukf* h, int auto_reset, void* stream) {
+  if (!h || !h->ro.init) return SSA_EINVAL;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t E = h->cfg.n_envs;
+  const int a = auto_reset ? 1 : 0;
+  CK(cudaMemcpyAsync(h->ro.act_in, h->ro.hin, sizeof(int32_t) * E, cudaMemcpyHostToDevice, st));
+  const char* gv = getenv("SSA_UKF_GRAPH");
+  if (!(gv && strcmp(gv, "0") == 0) && !h->use_team) {
+    if (!h->ro.gexec[a]) {
+      cudaStream_t cs;
+      CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      const long l0 = h->launches;
+      CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      const int rc = rollout_chain(h, cs, a);
+      cudaGraph_t g = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(cs, &g);
+      h->ro.gkernels[a] = (int)(h->launches - l0);
+      h->launches = l0;
+      cudaStreamDestroy(cs);
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (ce != cudaSuccess) return set_err("cudaStreamEndCapture", ce);
+      const cudaError_t ie = cudaGraphInstantiate(&h->ro.gexec[a], g, 0);
+      cudaGraphDestroy(g);
+      if (ie != cudaSuccess) return set_err("cudaGraphInstantiate", ie);
+    }
+    CK(cudaGraphLaunch(h->ro.gexec[a], st));
+    h->launches += h->ro.gkernels[a];
+  } else {
+    const int rc = rollout_chain(h, st, a);
+    if (rc) return rc;
+  }
+  CK(cudaMemcpyAsync(h->ro.hout, h->ro.dout, h->ro.out_bytes, cudaMemcpyDeviceToHost, st));
+  return SSA_OK;
+}
+
 int ssa_ukf_step_profile(ssa_ukf* h, const double M[9], int flags, void* stream, double ms[5]) {
   if (!h || !ms) return SSA_EINVAL;
   CK(cudaSetDevice(h->device));
@@ -2141,6 +2407,7 @@ int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stre
   p.E = h->cfg.n_envs; p.m = h->cfg.m; p.reward_type = h->cfg.reward_type; p.n_steps = h->cfg.n_steps;
   p.step_index = step_index;
   p.step_idx = h->step_idx;
+  p.increment = 0; p.greedy_only = 0;
   ssa_env_reduce_kernel<<<(unsigned)p.E, 128, 0, st>>>(p);
   h->launches++;
   CK(cudaGetLastError());

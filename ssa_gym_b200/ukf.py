@@ -219,6 +219,36 @@ class BatchedUKF:
         self._next_parity = self._parity_out.value ^ 1
         return self._parity_out.value
 
+    # -- device-resident episodic mode (vectorised reset, counter-based RNG) --------------------------------
+    def rollout_config(self, orbits, trans_table, seeds, x_sigma, z_sigma, P0, update_interval=1):
+        orbits = np.ascontiguousarray(orbits, dtype=np.float64).reshape(-1, 6)
+        table = np.ascontiguousarray(trans_table, dtype=np.float64).reshape(-1, 9)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64).reshape(self.n_envs)
+        xs = np.ascontiguousarray(x_sigma, dtype=np.float64).reshape(6)
+        zs = np.ascontiguousarray(z_sigma, dtype=np.float64).reshape(3)
+        P0 = np.ascontiguousarray(P0, dtype=np.float64).reshape(36)
+        _lib.check(self.lib.ssa_ukf_rollout_config(self.h, _ptr(orbits), len(orbits), _ptr(table), len(table), _ptr(seeds),
+                                                   _ptr(xs), _ptr(zs), _ptr(P0), int(update_interval)), "ssa_ukf_rollout_config")
+        ptrs = [ctypes.c_void_p() for _ in range(5)]
+        _lib.check(self.lib.ssa_ukf_rollout_io(self.h, *[ctypes.byref(q) for q in ptrs]), "ssa_ukf_rollout_io")
+
+        def view(q, ctype, shape):
+            n = int(np.prod(shape))
+            return np.ctypeslib.as_array(ctypes.cast(q, ctypes.POINTER(ctype)), shape=(n,)).reshape(shape)
+
+        N, E = self.N, self.n_envs
+        self.rollout_io = {"actions": view(ptrs[0], ctypes.c_int32, (E,)), "obs": view(ptrs[1], ctypes.c_double, (N, 12)),
+                           "reward": view(ptrs[2], ctypes.c_double, (E,)),
+                           "greedy": view(ptrs[3], ctypes.c_int32, (E, _lib.N_TASKERS)),
+                           "done": view(ptrs[4], ctypes.c_uint8, (E,))}
+        return self.rollout_io
+
+    def rollout_reset(self, stream=None):
+        _lib.check(self.lib.ssa_ukf_rollout_reset(self.h, stream), "ssa_ukf_rollout_reset")
+
+    def rollout_step(self, auto_reset=True, stream=None):
+        _lib.check(self.lib.ssa_ukf_rollout_step(self.h, 1 if auto_reset else 0, stream), "ssa_ukf_rollout_step")
+
     @property
     def next_parity(self):
         return getattr(self, "_next_parity", 0)

@@ -52,3 +52,102 @@ def test_vec_env_equals_independent_envs(over, tasker, agent):
             assert H.bits_equal(obs_v[e], np.asarray(o)), (t, e)
     assert n_resets >= E  # every env went through at least one auto-reset
     vec.close()
+
+
+# ---- device-resident episodic mode (rng='device'): vectorised reset + counter-based noise --------------------------
+def _emu_env_reduce(st, E, m, step_idx, reward_type, n_steps):
+    """numpy restatement of ssa_env_reduce_kernel (SS2:324-354, agents.py:7-81) on the twin's outputs."""
+    dpos = st.dpos.reshape(E, m); dvel = st.dvel.reshape(E, m); tr = st.trace.reshape(E, m)
+    vis = st.visible.reshape(E, m).astype(bool)
+    max_dpos = dpos.max(1)
+    tri = ((dpos < 1e4).astype(int) + (dpos < 1e7).astype(int)).sum(1)
+    trinary = (tri.astype(float) / float(m)) / 2.0
+    reward = np.zeros(E); done = np.zeros(E, bool)
+    if reward_type == "jones":
+        hi, lo = max_dpos > 5e6, max_dpos < 3e4
+        done |= hi | lo
+        reward[lo & ~hi] = 1.0
+    else:
+        reward = trinary
+    done |= (step_idx + 1 >= n_steps)
+    greedy = np.full((E, F.N_TASKERS), -1, np.int32)
+    greedy[:, F.TASKER_NAIVE_GREEDY] = tr.argmax(1)
+    for e in range(E):
+        idx = np.where(vis[e])[0]
+        if np.any(idx):  # agents.py:37 tests the INDEX array: false-y when only object 0 is visible
+            greedy[e, F.TASKER_VISIBLE_GREEDY] = idx[tr[e, idx].argmax()]
+            greedy[e, F.TASKER_POS_ERROR_GREEDY] = idx[dpos[e, idx].argmax()]
+            greedy[e, F.TASKER_VEL_ERROR_GREEDY] = idx[dvel[e, idx].argmax()]
+    return reward, done, greedy
+
+
+@pytest.mark.parametrize("over", [{"steps": 14, "reward_type": "jones", "update_interval": 1},
+                                  {"steps": 9, "reward_type": "trinary", "update_interval": 2, "obs_limit": 10}])
+def test_device_episodic_mode_equals_twin_emulation(over):
+    """ssa_ukf_rollout_reset / ssa_ukf_rollout_step (one graph launch per step: noise, UKF kernels, reward / done,
+    auto-reset, fresh obs, greedy taskers) against a step-by-step emulation built from the host twin: the same
+    counter-based draws (twin_env_reset / twin_env_noise), twin_step with the per-env trans_matrix, numpy
+    reward / done / taskers.  Observations, rewards, dones and tasker decisions must be EXACT over many auto-resets."""
+    E, total_steps = 48, 40
+    cfg = dict(ssa_gym_b200.env_config)
+    cfg.update(over)
+    n, m = cfg["steps"], cfg["rso_count"]
+    cfg["trans_matrix"] = gcrs2irts_matrix_approx(time_table(cfg["t_0"], cfg["time_step"], n))
+    seeds = list(range(500, 500 + E))
+    vec = VecSSATaskerEnv(cfg, E, seeds=seeds, rng="device")
+    tw = H.twin()
+    keys = np.array(seeds, dtype=np.uint64)
+    table = np.ascontiguousarray(vec.trans_matrix).reshape(n, 9)
+    sig = np.concatenate([vec.x_sigma, vec.z_sigma, vec.P_0[np.triu_indices(6)]])
+    orbits = np.ascontiguousarray(vec.orbits, dtype=np.float64)
+    N = E * m
+    episode = np.zeros(E, np.uint32); step_idx = np.zeros(E, np.int32)
+    xt = np.zeros((N, 6)); xf = np.zeros((N, 6)); Pp = np.zeros((N, 21)); status = np.zeros(N, np.int32); infl = np.zeros(N, np.int32)
+
+    def emu_reset(st, done):
+        tw.twin_env_reset(E, m, H.p(keys), H.p(episode), H.p(step_idx), H.p(done) if done is not None else None, H.p(orbits),
+                          len(orbits), H.p(sig), H.p(xt), H.p(xf), H.p(Pp), H.p(status), H.p(infl))
+        sel = np.repeat(done.astype(bool), m) if done is not None else np.ones(N, bool)
+        if st is None:
+            st = H.HostState(xt, xf, H.unpack_P(Pp))
+        else:
+            st.x_true[sel] = xt[sel]; st.x[sel] = xf[sel]; st.P[sel] = H.unpack_P(Pp)[sel]
+            st.status[sel] = 0; st.infl[sel] = 0
+        return st
+
+    tcfg = H.make_cfg(N, E=E, m=m, dt=cfg["time_step"], alpha=cfg["alpha"], beta=cfg["beta"], kappa=cfg["kappa"],
+                      q_sigma=cfg["q_sigma"], R=vec.R, observer_deg=cfg["observer"], obs_limit_deg=cfg["obs_limit"], n_steps=n)
+    st = emu_reset(None, None)
+    H.cpu_step("twin", tcfg, st, table[step_idx].reshape(E, 9), F.STEP_EPILOGUE | F.STEP_M_PER_ENV)
+    _, _, g_e = _emu_env_reduce(st, E, m, step_idx, cfg["reward_type"], n)
+    assert H.bits_equal(vec.obs.reshape(N, 12), st.obs)
+    assert np.array_equal(vec._io["greedy"], g_e)
+    rng = np.random.RandomState(11)
+    n_resets = 0
+    for t in range(total_steps):
+        a = vec.greedy_actions(F.TASKER_VISIBLE_GREEDY) if t % 2 else rng.randint(0, m, size=E)
+        a = np.asarray(a, dtype=np.int32)
+        obs_v, r_v, d_v, _ = vec.vector_step(a)
+        # emulation
+        zn = np.zeros((N, 3))
+        tw.twin_env_noise(E, m, H.p(keys), H.p(episode), H.p(step_idx), H.p(sig), H.p(zn))
+        nxt = step_idx + 1
+        a_eff = np.where(nxt % cfg["update_interval"] == 0, a, -1).astype(np.int32)
+        Ms = table[np.minimum(nxt, n - 1)].reshape(E, 9)
+        H.cpu_step("twin", tcfg, st, Ms, F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ACT | F.STEP_EPILOGUE | F.STEP_M_PER_ENV,
+                   actions=a_eff, z_noise=zn)
+        step_idx[:] = nxt
+        r_e, d_e, _ = _emu_env_reduce(st, E, m, step_idx, cfg["reward_type"], n)
+        assert np.array_equal(d_v, d_e), (t, d_v, d_e)
+        assert H.bits_equal(r_v, r_e), (t, r_v, r_e)
+        if d_e.any():
+            n_resets += int(d_e.sum())
+            st = emu_reset(st, d_e.astype(np.uint8))
+            H.cpu_step("twin", tcfg, st, table[step_idx].reshape(E, 9), F.STEP_EPILOGUE | F.STEP_M_PER_ENV)
+        _, _, g_e = _emu_env_reduce(st, E, m, step_idx, cfg["reward_type"], n)
+        assert H.bits_equal(obs_v.reshape(N, 12), st.obs), t
+        assert np.array_equal(vec._io["greedy"], g_e), t
+        assert np.array_equal(vec.i, step_idx), t
+    assert n_resets >= E
+    assert H.bits_equal(vec.ukf.download(F.F_X_FILTER), st.x) and H.bits_equal(vec.ukf.download(F.F_X_TRUE), st.x_true)
+    vec.close()

@@ -17,6 +17,7 @@
 #include "../../ssa_gym_b200/csrc/ssa_math.h"
 #include "../../ssa_gym_b200/csrc/ssa_meas.h"
 #include "../../ssa_gym_b200/csrc/ssa_orbit.h"
+#include "../../ssa_gym_b200/csrc/ssa_rng.h"
 #include "../../ssa_gym_b200/csrc/ssa_ukf_core.h"
 
 namespace {
@@ -263,5 +264,56 @@ TW1(twin_sinh, ssa_sinh) TW1(twin_cosh, ssa_cosh) TW1(twin_tanh, ssa_tanh) TW1(t
 TW1(twin_asinh, ssa_asinh) TW1(twin_acosh, ssa_acosh) TW1(twin_pow23, ssa_pow23)
 void twin_atan2(const double* y, const double* x, double* z, int n) { for (int i = 0; i < n; ++i) z[i] = ssa_atan2(y[i], x[i]); }
 void twin_pymod(const double* y, const double* x, double* z, int n) { for (int i = 0; i < n; ++i) z[i] = ssa_pymod(y[i], x[i]); }
+
+// ---- episodic device mode: the draws of k_env_reset / k_env_begin (ssa_rng.h) -------------------------------------
+// (re)draw the environments with done[e] != 0 (all when done is null); host layout: x_true / x_filter [N][6],
+// P packed [N][21]; sig = x_sigma[6], z_sigma[3], packed P0[21]
+void twin_env_reset(int E, int m, const uint64_t* seeds, uint32_t* episode, int32_t* step_idx, const uint8_t* done,
+                    const double* orbits, int n_orbits, const double* sig, double* x_true, double* x_filter, double* P,
+                    int32_t* status, int32_t* infl) {
+  for (int e = 0; e < E; ++e) {
+    if (done && !done[e]) continue;
+    const uint32_t k0 = (uint32_t)(seeds[e] & 0xffffffffu), k1 = (uint32_t)(seeds[e] >> 32), ep = episode[e];
+    for (int j = 0; j < m; ++j) {
+      const size_t obj = (size_t)e * m + j;
+      const uint32_t row = ssa_draw_orbit(k0, k1, ep, (uint32_t)j, (uint32_t)n_orbits);
+      double n6[6];
+      ssa_draw_x(k0, k1, ep, (uint32_t)j, n6);
+      for (int i = 0; i < 6; ++i) {
+        const double xt = orbits[(size_t)row * 6 + i];
+        x_true[obj * 6 + i] = xt;
+        x_filter[obj * 6 + i] = xt + ssa_mul(n6[i], sig[i]);
+      }
+      for (int q = 0; q < SSA_NP; ++q) P[obj * SSA_NP + q] = sig[9 + q];
+      status[obj] = 0;
+      infl[obj] = 0;
+    }
+    episode[e] = ep + 1u;
+    step_idx[e] = 0;
+  }
+}
+// measurement noise of step step_idx[e] + 1, [N][3]
+void twin_env_noise(int E, int m, const uint64_t* seeds, const uint32_t* episode, const int32_t* step_idx, const double* sig,
+                    double* z_noise) {
+  for (int e = 0; e < E; ++e)
+    for (int j = 0; j < m; ++j) {
+      double n3[3];
+      ssa_draw_z((uint32_t)(seeds[e] & 0xffffffffu), (uint32_t)(seeds[e] >> 32), episode[e] - 1u, (uint32_t)j,
+                 (uint32_t)(step_idx[e] + 1), n3);
+      for (int a = 0; a < 3; ++a) z_noise[((size_t)e * m + j) * 3 + a] = ssa_mul(n3[a], sig[6 + a]);
+    }
+}
+// n standard normals of stream (key, ep = 0, STREAM_Z, j = i, step = 0): for the statistical tests
+void twin_normals(uint64_t seed, double* out, int n) {
+  for (int i = 0; i + 2 < n + 3; i += 3) {
+    double n3[3];
+    ssa_draw_z((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), 0u, (uint32_t)(i / 3), 0u, n3);
+    for (int a = 0; a < 3 && i + a < n; ++a) out[i + a] = n3[a];
+  }
+}
+void twin_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  const ssa_u4 r = ssa_philox4x32(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+  for (int i = 0; i < 4; ++i) out[i] = r.v[i];
+}
 
 }  // extern "C"
