@@ -95,7 +95,10 @@ enum ssa_field {
   SSA_F_Z_TRUE = 9, SSA_F_Y = 10, SSA_F_S = 11, SSA_F_SIGMAS_H = 12, SSA_F_Z_NOISE = 13,
   SSA_F_VISIBLE = 14, SSA_F_STATUS = 15, SSA_F_INFLATIONS = 16,
   SSA_F_ACTIONS = 17, SSA_F_REWARD = 18, SSA_F_DONE = 19, SSA_F_GREEDY = 20, SSA_F_SCORES = 21,
-  SSA_F_UPDATED = 22, SSA_F_TRANS_ENV = 23, SSA_F_STEP_INDEX = 24, SSA_F_ENV_STATS = 25, SSA_F_COUNT_
+  SSA_F_UPDATED = 22, SSA_F_TRANS_ENV = 23, SSA_F_STEP_INDEX = 24, SSA_F_ENV_STATS = 25,
+  SSA_F_DIAG = 26,        /* double [N][2]: NEES, NIS (NaN where the object was not updated) - ssa_ukf_diagnostics */
+  SSA_F_INNOV_FLAGS = 27, /* uint8 [N]: 0x80 valid | bit a: |y_a| < sqrt(S_aa) | bit 3+a: |y_a| < 2 sqrt(S_aa) */
+  SSA_F_COUNT_
 };
 
 /* heuristic taskers evaluated on the device by ssa_ukf_env_reduce (agents.py) */
@@ -201,6 +204,10 @@ int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stre
 /* reward.py score terms from the current covariances: out double[N][6] =
  * [score_scaled_trace_P, score_trace_P, score_scaled_det_P(dt), score_det_P, score_det_pos_P, |dpos|] */
 int ssa_ukf_scores(ssa_ukf* h, void* stream);
+/* Consistency diagnostics of the current state: per object NEES = (x_true - x)^T P^-1 (x_true - x)
+ * (SS2:436-446 anees), and for the objects updated by the last step run with SSA_STEP_RECORD the NIS
+ * y^T S^-1 y (SS2:564-569) and the innovation-bound flags (SS2:598-604) -> SSA_F_DIAG, SSA_F_INNOV_FLAGS.      */
+int ssa_ukf_diagnostics(ssa_ukf* h, void* stream);
 
 int ssa_ukf_sync(ssa_ukf* h, void* stream);
 /* number of kernel launches issued through this handle so far (bench.py `gpu_launches`) */

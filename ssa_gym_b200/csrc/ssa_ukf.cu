@@ -1414,6 +1414,31 @@ __global__ void __launch_bounds__(128) k_env_reset(const RolloutParams p) {
   }
 }
 
+// consistency diagnostics of the current step, one thread per object (ssa_ukf_core.h: ssa_nees6 / ssa_nis3)
+__global__ void ssa_diag_kernel(const double* __restrict__ xt, const double* __restrict__ x, const double* __restrict__ P,
+                                const double* __restrict__ y, const double* __restrict__ S, const uint8_t* __restrict__ updated,
+                                double* diag, uint8_t* flags, long ld, int N) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double d[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) d[i] = xt[i * ld + n] - x[i * ld + n];
+  diag[2 * n] = ssa_nees6(P + n, ld, d);
+  double nis = ssa_nan();
+  int f = 0;
+  if (updated[n]) {  // y / S of this step were recorded (SSA_STEP_RECORD) for the objects that were updated
+    double Sm[9], yy[3];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) Sm[e] = S[n * 9 + e];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) yy[a] = y[n * 3 + a];
+    nis = ssa_nis3(Sm, yy, &f);
+    f |= 0x80;
+  }
+  diag[2 * n + 1] = nis;
+  flags[n] = (uint8_t)f;
+}
+
 // reward.py:6-50 score terms, one thread per object
 __global__ void ssa_scores_kernel(const double* __restrict__ P, const double* __restrict__ dpos, double* out, long ld,
                                   int N, double dt) {
@@ -1666,7 +1691,8 @@ struct ssa_ukf {
     int gkernels[2];
   } ro;
   int32_t *status, *infl, *actions, *greedy;
-  uint8_t *visible, *updated, *done;
+  uint8_t *visible, *updated, *innov_flags, *done;
+  double* diag;     // [N][2] NEES, NIS of the last ssa_ukf_diagnostics call
   size_t stage_bytes;
 };
 
@@ -1706,7 +1732,7 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
   const long ld = h->ld;
   // fp64 slab: xt 6, x 6, P 21, dpos dvel spos svel trace 5 (SoA rows of ld) + AoS outputs
   const size_t n_soa = (size_t)(6 + 6 + 21 + 5) * ld;
-  const size_t n_aos = (size_t)N * (12 + 3 + 3 + 3 + 9 + 39 + 6) + (size_t)E * (1 + 4 + 9) + 32;
+  const size_t n_aos = (size_t)N * (12 + 3 + 3 + 3 + 9 + 39 + 6 + 2) + (size_t)E * (1 + 4 + 9) + 32;
   cudaError_t e = cudaMalloc(&h->slab, (n_soa + n_aos) * sizeof(double));
   if (e != cudaSuccess) { delete h; return set_err("cudaMalloc(slab)", e); }
   cudaMemset(h->slab, 0, (n_soa + n_aos) * sizeof(double));
@@ -1722,6 +1748,7 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
   h->S = q; q += N * 9;
   h->sigmas_h = q; q += N * 39;
   h->scores = q; q += N * 6;
+  h->diag = q; q += N * 2;
   h->reward = q; q += E;
   h->env_stats = q; q += E * 4;
   h->qr = q; q += 32;
@@ -1783,10 +1810,11 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
                    make_tmap(&h->tm_u, h->scratch, lds, SC_ROWS, 21) | make_tmap(&h->tm_s, h->xt, ld, ST_ROWS, ST_ROWS);
     if (rc) { ssa_ukf_destroy(h); return set_err("cuTensorMapEncodeTiled", cudaErrorUnknown); }
   }
-  if ((e = cudaMalloc(&h->visible, 2 * ld + E)) != cudaSuccess) { ssa_ukf_destroy(h); return set_err("cudaMalloc(u8)", e); }
-  cudaMemset(h->visible, 0, 2 * ld + E);
+  if ((e = cudaMalloc(&h->visible, 3 * ld + E)) != cudaSuccess) { ssa_ukf_destroy(h); return set_err("cudaMalloc(u8)", e); }
+  cudaMemset(h->visible, 0, 3 * ld + E);
   h->updated = h->visible + ld;
-  h->done = h->updated + ld;
+  h->innov_flags = h->updated + ld;
+  h->done = h->innov_flags + ld;
   *out = h;
   return SSA_OK;
 }
@@ -1883,6 +1911,8 @@ static int field_info(ssa_ukf* h, int field, void** p, size_t* bytes, int* soa_c
     case SSA_F_TRANS_ENV: *p = h->Menv; *bytes = E * 9 * 8; break;
     case SSA_F_STEP_INDEX: *p = h->step_idx; *bytes = E * 4; break;
     case SSA_F_ENV_STATS: *p = h->env_stats; *bytes = E * 4 * 8; break;
+    case SSA_F_DIAG: *p = h->diag; *bytes = N * 2 * 8; break;
+    case SSA_F_INNOV_FLAGS: *p = h->innov_flags; *bytes = N; break;
     default: snprintf(g_err, sizeof(g_err), "unknown field %d", field); return SSA_EINVAL;
   }
   return SSA_OK;
@@ -2409,6 +2439,18 @@ int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stre
   p.step_idx = h->step_idx;
   p.increment = 0; p.greedy_only = 0;
   ssa_env_reduce_kernel<<<(unsigned)p.E, 128, 0, st>>>(p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SSA_OK;
+}
+
+int ssa_ukf_diagnostics(ssa_ukf* h, void* stream) {
+  if (!h) return SSA_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  const int N = h->cfg.n_objects;
+  ssa_diag_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(h->xt, h->x, h->P, h->y, h->S, h->updated, h->diag, h->innov_flags,
+                                                             h->ld, N);
   h->launches++;
   CK(cudaGetLastError());
   return SSA_OK;

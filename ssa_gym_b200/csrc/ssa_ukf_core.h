@@ -185,6 +185,49 @@ SSA_HD int ssa_inv3(const double* S /* row-major 3x3 */, double* SI) {
   return ok;
 }
 
+// Consistency diagnostics.
+// NEES d^T P^-1 d of one object (SS2:436-446 `anees`: delta @ inv(P_filter) @ delta), evaluated through the Cholesky
+// factor P = U^T U (w = U^-T d, NEES = w.w) instead of an explicit inverse: same value for a positive definite P,
+// better conditioned; NaN when P is not positive definite (numpy's inv would return some number there).
+SSA_HD double ssa_nees6(const double* P, long stride, const double* d) {
+  double U[SSA_NP];
+#pragma unroll
+  for (int e = 0; e < SSA_NP; ++e) U[e] = P[e * stride];
+  if (!ssa_chol6(U)) return ssa_nan();
+  double w[6], acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {  // forward substitution with U^T (lower triangular)
+    double t = d[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) t = ssa_fma(-U[ssa_pidx(k, i)], w[k], t);
+    w[i] = ssa_div(t, U[ssa_pidx(i, i)]);
+    acc = ssa_fma(w[i], w[i], acc);
+  }
+  return acc;
+}
+// NIS y^T S^-1 y (SS2:564-569 plot_NIS: y @ inv(S) @ y, numpy's order: the row vector y @ inv(S) first) and the
+// innovation-bound flags of SS2:598-604: bit a = |y_a| < sqrt(S_aa), bit 3+a = |y_a| < 2 sqrt(S_aa).
+SSA_HD double ssa_nis3(const double* S, const double* y, int* flags) {
+  double SI[9];
+  const int ok = ssa_inv3(S, SI);
+  int f = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double sd = ssa_sqrt(S[4 * a]);
+    f |= ((y[a] < sd) && (y[a] > -sd)) ? (1 << a) : 0;
+    f |= ((y[a] < ssa_mul(2.0, sd)) && (y[a] > -ssa_mul(2.0, sd))) ? (8 << a) : 0;
+  }
+  *flags = f;
+  if (!ok) return ssa_nan();
+  double acc = 0.0;
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    const double t = ssa_fma(y[2], SI[6 + b], ssa_fma(y[1], SI[3 + b], ssa_mul(y[0], SI[b])));
+    acc = (b == 0) ? ssa_mul(t, y[0]) : ssa_fma(t, y[b], acc);
+  }
+  return acc;
+}
+
 // np.trace(P) over the packed diagonal, numpy's left-to-right order (agents.py:8,40)
 SSA_HD double ssa_trace6(const double* P, long stride) {
   double t = P[0];

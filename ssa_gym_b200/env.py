@@ -129,6 +129,7 @@ class SSA_Tasker_Env(Env):
                               obs_type=self.obs_type, reward_type=self.reward_type, n_steps=n,
                               resample_after_predict=config.get('resample_after_predict', True),
                               device=config.get('device', 0))
+        self._device = config.get('device', 0)
         self.np_random = None
         self.init_seed = self.seed()
         self.reset()
@@ -297,12 +298,55 @@ class SSA_Tasker_Env(Env):
             obs[4 * j + 3] = np.trace(self.P_filter[i, j])
         return np.nan_to_num(obs, copy=False, nan=0.001, posinf=0.001, neginf=0.001)
 
+    # -- consistency diagnostics (SS2:436-446, 564-624), evaluated on the device over the episode's histories --------
+    def _history_diagnostics(self):
+        """NEES of every (step, object) up to the current step and NIS / innovation-bound flags of every tasked
+        observation, in one launch of ssa_ukf_diagnostics over the host histories (n*m pseudo-objects)."""
+        steps = min(self.i + 1, self.n)
+        N = steps * self.m
+        tmp = BatchedUKF(n_envs=1, m=N, dt=self.dt, Q=self.Q, R=self.R, obs_lla=self.obs_lla, obs_limit_rad=self.obs_limit,
+                         alpha=self.alpha, beta=self.beta, kappa=self.kappa, obs_type=self.obs_type,
+                         device=self._device)
+        try:
+            tmp.reset(self.x_true[:steps].reshape(N, 6), self.x_filter[:steps].reshape(N, 6),
+                      self.P_filter[:steps].reshape(N, 36))
+            upd = np.zeros((steps, self.m), dtype=np.uint8)
+            for i in range(1, steps):
+                a = int(self.actions[i])
+                if not np.isnan(self.y[i, a]).any():
+                    upd[i, a] = 1
+            tmp.upload(F.F_Y, np.nan_to_num(self.y[:steps].reshape(N, -1)))
+            tmp.upload(F.F_S, np.nan_to_num(self.S[:steps].reshape(N, 3, 3)))
+            tmp.upload(F.F_UPDATED, upd.reshape(N))
+            nees, nis, flags = tmp.diagnostics()
+        finally:
+            tmp.close()
+        return nees.reshape(steps, self.m), nis.reshape(steps, self.m), flags.reshape(steps, self.m)
+
     def anees(self):
-        delta = self.x_true - self.x_filter
-        for i in range(self.n):
-            for j in range(self.m):
-                self.nees[i, j] = delta[i, j] @ np.linalg.inv(self.P_filter[i, j]) @ delta[i, j]
-        return np.mean(self.nees)
+        """SS2:436-446: average normalised estimation error squared over the episode (steps taken so far)."""
+        nees, _, _ = self._history_diagnostics()
+        self.nees[:] = np.nan
+        self.nees[:len(nees)] = nees
+        # NaN marks a covariance that is not positive definite at that step (the reference's explicit inverse
+        # returns an arbitrary number there); such entries are left out of the average
+        return np.nanmean(nees)
+
+    def nis(self):
+        """The series plotted by SS2:564-569: NIS of the tasked object's innovation at every step that had an update."""
+        _, nis, flags = self._history_diagnostics()
+        return np.array([nis[i, int(self.actions[i])] for i in range(1, len(nis)) if flags[i, int(self.actions[i])] & 0x80])
+
+    def innovation_bounds(self):
+        """SS2:598-604: percentage of the tasked innovations inside one / two innovation standard deviations,
+        rows = (sigma, two sigmas), columns = measurement components (the reference renders this as a table)."""
+        _, _, flags = self._history_diagnostics()
+        f = np.array([flags[i, int(self.actions[i])] for i in range(1, len(flags)) if flags[i, int(self.actions[i])] & 0x80])
+        if len(f) == 0:
+            return np.full((2, 3), np.nan)
+        one = np.stack([(f >> a) & 1 for a in range(3)], axis=1)
+        two = np.stack([(f >> (3 + a)) & 1 for a in range(3)], axis=1)
+        return np.round(np.stack((np.mean(one, axis=0), np.mean(two, axis=0))) * 100, 2)
 
     def close(self):
         if getattr(self, "ukf", None) is not None:

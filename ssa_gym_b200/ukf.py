@@ -101,6 +101,7 @@ class BatchedUKF:
             _lib.F_DONE: ((self.n_envs,), np.uint8), _lib.F_GREEDY: ((self.n_envs, _lib.N_TASKERS), np.int32),
             _lib.F_SCORES: ((self.N, 6), np.float64), _lib.F_TRANS_ENV: ((self.n_envs, 3, 3), np.float64),
             _lib.F_STEP_INDEX: ((self.n_envs,), np.int32), _lib.F_ENV_STATS: ((self.n_envs, 4), np.float64),
+            _lib.F_DIAG: ((self.N, 2), np.float64), _lib.F_INNOV_FLAGS: ((self.N,), np.uint8),
         }
 
     # -- lifetime ---------------------------------------------------------------------------------
@@ -266,6 +267,13 @@ class BatchedUKF:
     def scores(self, stream=None):
         _lib.check(self.lib.ssa_ukf_scores(self.h, stream), "ssa_ukf_scores")
         return self.download(_lib.F_SCORES, stream=stream)
+
+    def diagnostics(self, stream=None):
+        """Consistency diagnostics of the current state: (nees [N], nis [N] (NaN where not updated), flags uint8 [N]:
+        0x80 valid | bit a: |y_a| < sqrt(S_aa) | bit 3+a: |y_a| < 2 sqrt(S_aa)).  NIS / flags need SSA_STEP_RECORD."""
+        _lib.check(self.lib.ssa_ukf_diagnostics(self.h, stream), "ssa_ukf_diagnostics")
+        d = self.download(_lib.F_DIAG, stream=stream)
+        return d[:, 0].copy(), d[:, 1].copy(), self.download(_lib.F_INNOV_FLAGS, stream=stream)
 
     def sync(self, stream=None):
         _lib.check(self.lib.ssa_ukf_sync(self.h, stream), "ssa_ukf_sync")

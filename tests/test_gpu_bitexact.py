@@ -296,3 +296,22 @@ def test_chunked_execution_bitexact(chunk, monkeypatch):
     ukf = _gpu_run({}, cat, x, P0, zn, [flags] * steps, actions=actions, E=E, m=m)
     _compare_all(ukf, st, check_update_outputs=False)
     ukf.close()
+
+
+def test_diagnostics_kernel_equals_twin():
+    """ssa_ukf_diagnostics (NEES, NIS, innovation-bound flags) on the device == the twin, bit for bit."""
+    N, steps = 5000, 3
+    cat, x, P0, zn = H.c2_inputs(N, steps)
+    cfg = H.make_cfg(N, obs_limit_deg=5.0)
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE | F.STEP_RECORD
+    st = H.HostState(cat, x, P0)
+    for s in range(steps):
+        H.cpu_step("twin", cfg, st, H.CEL2TER06AXY, flags, z_noise=zn[s])
+    ukf = _gpu_run(dict(obs_limit_deg=5.0), cat, x, P0, zn, [flags] * steps)
+    nees_g, nis_g, fl_g = ukf.diagnostics()
+    nees = np.zeros(N); nis = np.zeros(N); fl = np.zeros(N, np.uint8)
+    H.twin().twin_diagnostics(N, H.p(st.x_true), H.p(st.x), H.p(H.pack_P(st.P)), H.p(np.nan_to_num(st.y)),
+                              H.p(np.nan_to_num(st.S)), H.p(st.updated), H.p(nees), H.p(nis), H.p(fl))
+    assert st.updated.sum() > 0 and (st.updated == 0).sum() > 0
+    assert H.bits_equal(nees_g, nees) and H.bits_equal(nis_g, nis) and np.array_equal(fl_g, fl)
+    ukf.close()

@@ -112,3 +112,42 @@ def test_env_api_surface():
         e2.close()
     with pytest.raises(NotImplementedError):
         envmod.SSA_Tasker_Env(dict(cfg, fx=lambda x, dt: x))
+
+
+def test_env_consistency_diagnostics_match_reference_formulas():
+    """env.anees() / env.nis() / env.innovation_bounds() (SS2:436-446, 564-569, 598-604) are evaluated on the device
+    over the episode histories; against the numpy restatement of the reference's formulas on the SAME histories."""
+    from oracle import diagnostics as D
+    env = make_env("gpu", steps=60, reward_type="trinary",
+                   trans_matrix=gcrs2irts_matrix_approx(time_table(ssa_gym_b200.env_config["t_0"], 20.0, 60)))
+    env.seed(3); env.action_space.seed(3)
+    obs = env.reset()
+    done = False
+    while not done:
+        obs, r, done, _ = env.step(agents.agent_visible_greedy(obs, env))
+    n, m = env.n, env.m
+    steps = min(env.i + 1, n)
+    assert steps == n
+    got = env.anees()
+    ref = D.nees(env.x_true[:steps].reshape(-1, 6), env.x_filter[:steps].reshape(-1, 6), env.P_filter[:steps].reshape(-1, 6, 6))
+    cond = np.array([np.linalg.cond(p_) for p_ in env.P_filter[:steps].reshape(-1, 6, 6)])
+    mine = env.nees[:steps].ravel()
+    # P - K S K^T can lose positive definiteness in the last bits (the next robust_cholesky inflates it): the Cholesky
+    # route then reports NaN where np.linalg.inv returns an arbitrary (often negative) number
+    bad = np.isnan(mine)
+    for p_ in env.P_filter[:steps].reshape(-1, 6, 6)[bad]:
+        assert np.linalg.eigvalsh(p_).min() <= 1e-9 * np.abs(np.diag(p_)).max()
+    assert bad.mean() < 0.05
+    ok = ~bad
+    assert np.all(np.abs(mine[ok] - ref[ok]) <= 1e-15 * cond[ok] * np.abs(ref[ok]) + 1e-12)
+    assert abs(got - ref[ok].mean()) <= 1e-9 * abs(ref[ok].mean())
+    idx = [(i, int(env.actions[i])) for i in range(1, steps) if not np.isnan(env.y[i, int(env.actions[i])]).any()]
+    assert len(idx) > 10
+    y = np.array([env.y[i, a] for i, a in idx]); S = np.array([env.S[i, a] for i, a in idx])
+    ref_nis = D.nis(y, S)
+    nis = env.nis()
+    assert nis.shape == ref_nis.shape
+    condS = np.array([np.linalg.cond(s_) for s_ in S])
+    assert np.all(np.abs(nis - ref_nis) <= 1e-14 * condS * np.abs(ref_nis) + 1e-12)
+    assert np.array_equal(env.innovation_bounds(), D.innovation_bounds(y, S))
+    env.close()

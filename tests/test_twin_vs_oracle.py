@@ -182,3 +182,45 @@ def test_long_run_filter_health_matches():
     assert np.median(st.dpos) < 1.1 * np.median(so.dpos) and np.median(st.dpos) > 0.5 * np.median(so.dpos)
     assert np.median(st.dpos) < 400 and np.median(so.dpos) < 400      # both converge from ~1.7e5 m
     assert st.infl.sum() < 5 * (so.infl.sum() + 5) and so.infl.sum() < 5 * (st.infl.sum() + 5)
+
+
+def test_consistency_diagnostics_match_reference_formulas(c2):
+    """NEES / NIS / innovation-bound flags of the product (through the host twin) against the numpy
+    restatement of SS2:436-446, 564-569, 598-604 (explicit np.linalg.inv).  The product goes through the Cholesky
+    factor, so the bound is conditioning-aware: cond(P) * 1e-15."""
+    from oracle import diagnostics as D
+    cat, x, P0, zn = c2
+    N = 3000
+    cfg = H.make_cfg(N)
+    st = H.HostState(cat[:N], x[:N], P0)
+    flags = 0x1 | 0x2 | 0x4 | 0x10 | 0x20   # truth, predict, update all, epilogue, record
+    for s in range(3):
+        H.cpu_step("twin", cfg, st, H.CEL2TER06AXY, flags, z_noise=zn[s % len(zn)][:N])
+    nees = np.zeros(N); nis = np.zeros(N); fl = np.zeros(N, np.uint8)
+    Pp = H.pack_P(st.P)
+    upd = st.updated.copy(); upd[::7] = 0
+    H.twin().twin_diagnostics(N, H.p(st.x_true), H.p(st.x), H.p(Pp), H.p(st.y), H.p(st.S), H.p(upd), H.p(nees), H.p(nis), H.p(fl))
+    ref_nees = D.nees(st.x_true, st.x, st.P)
+    cond = np.array([np.linalg.cond(p_) for p_ in st.P])
+    assert np.all(np.abs(nees - ref_nees) <= 1e-15 * cond * np.abs(ref_nees) + 1e-12)
+    sel = upd.astype(bool)
+    ref_nis = D.nis(st.y[sel], st.S[sel])
+    condS = np.array([np.linalg.cond(s_) for s_ in st.S[sel]])
+    assert np.all(np.abs(nis[sel] - ref_nis) <= 1e-14 * condS * np.abs(ref_nis) + 1e-12)
+    assert np.isnan(nis[~sel]).all() and (fl[~sel] == 0).all() and np.all(fl[sel] & 0x80)
+    one, two = D.innovation_flags(st.y[sel], st.S[sel])
+    assert np.array_equal(np.stack([(fl[sel] >> a) & 1 for a in range(3)], 1).astype(bool), one)
+    assert np.array_equal(np.stack([(fl[sel] >> (3 + a)) & 1 for a in range(3)], 1).astype(bool), two)
+    # a filter that is consistent by construction: NEES of x ~ N(x_true, P) averages to the state dimension
+    rng = np.random.RandomState(4)
+    L = np.linalg.cholesky(P0)
+    xs = cat[:N] + rng.normal(size=(N, 6)) @ L.T
+    H.twin().twin_diagnostics(N, H.p(np.ascontiguousarray(cat[:N])), H.p(np.ascontiguousarray(xs)),
+                              H.p(H.pack_P(np.broadcast_to(P0, (N, 6, 6)))), H.p(st.y), H.p(st.S), H.p(np.zeros(N, np.uint8)),
+                              H.p(nees), H.p(nis), H.p(fl))
+    assert abs(nees.mean() - 6.0) < 5 * np.sqrt(12.0 / N)
+    # not positive definite -> NaN
+    bad = np.diag([1.0, 1, 1, 1, 1, -1.0])
+    H.twin().twin_diagnostics(1, H.p(np.zeros((1, 6))), H.p(np.ones((1, 6))), H.p(H.pack_P(bad[None])), H.p(st.y), H.p(st.S),
+                              H.p(np.zeros(1, np.uint8)), H.p(nees), H.p(nis), H.p(fl))
+    assert np.isnan(nees[0])

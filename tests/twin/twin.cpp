@@ -265,6 +265,24 @@ TW1(twin_asinh, ssa_asinh) TW1(twin_acosh, ssa_acosh) TW1(twin_pow23, ssa_pow23)
 void twin_atan2(const double* y, const double* x, double* z, int n) { for (int i = 0; i < n; ++i) z[i] = ssa_atan2(y[i], x[i]); }
 void twin_pymod(const double* y, const double* x, double* z, int n) { for (int i = 0; i < n; ++i) z[i] = ssa_pymod(y[i], x[i]); }
 
+// diagnostics of ssa_diag_kernel on host-layout arrays (P packed [N][21])
+void twin_diagnostics(int N, const double* x_true, const double* x, const double* P, const double* y, const double* S,
+                      const uint8_t* updated, double* nees, double* nis, uint8_t* flags) {
+  for (int n = 0; n < N; ++n) {
+    double d[6];
+    for (int i = 0; i < 6; ++i) d[i] = x_true[n * 6 + i] - x[n * 6 + i];
+    nees[n] = ssa_nees6(P + (size_t)n * SSA_NP, 1, d);
+    double v = ssa_nan();
+    int f = 0;
+    if (updated[n]) {
+      v = ssa_nis3(S + (size_t)n * 9, y + (size_t)n * 3, &f);
+      f |= 0x80;
+    }
+    nis[n] = v;
+    flags[n] = (uint8_t)f;
+  }
+}
+
 // ---- episodic device mode: the draws of k_env_reset / k_env_begin (ssa_rng.h) -------------------------------------
 // (re)draw the environments with done[e] != 0 (all when done is null); host layout: x_true / x_filter [N][6],
 // P packed [N][21]; sig = x_sigma[6], z_sigma[3], packed P0[21]
