@@ -62,7 +62,11 @@ def workload_inputs(n_objects, rank, steps):
     from ssa_gym_b200.catalog import synthetic_catalog, tiled_catalog
     from ssa_gym_b200.transformations import arcsec2rad
     if n_objects <= 20000:
-        cat = synthetic_catalog(n_objects, seed=rank)
+        # C2 is ONE catalog (the reference ships one 20 000-orbit file): every rank steps the same orbits with its own
+        # initial filter errors and measurement noise.  (Catalogs drawn with other seeds run up to 25 % slower or
+        # faster - more or fewer high-eccentricity perigee passes in the timed window - which would turn the
+        # max-over-ranks time of a weak-scaling run into a statement about the seeds.)
+        cat = synthetic_catalog(n_objects, seed=0)
     else:
         cat = tiled_catalog(n_objects, synthetic_catalog(20000, 0), seed=2 + rank)
     x = cat + np.random.RandomState(1000 + rank).normal(size=(n_objects, 6)) * np.array([1e5] * 3 + [1e2] * 3)
@@ -439,7 +443,11 @@ def main():
 
     # ---- reduce over ranks (max time) --------------------------------------------------------------
     t = torch.tensor([total_ms, b2b_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    per_rank = [total_ms / a.steps]
     if world > 1:
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        per_rank = [float(r_[0]) / a.steps for r_ in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, b2b_ms, e2e_ms = [float(v) for v in t.tolist()]
     ms_per_step = total_ms / a.steps
@@ -496,6 +504,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "extra": {"ms_per_step_back_to_back_no_flush": b2b_ms, "wall_s_timed_region": t_wall, "failed_filters": n_failed,
+                      "ms_per_step_of_each_rank": per_rank,
                       "step_ms_min": float(np.min(step_ms)), "step_ms_max": float(np.max(step_ms))},
         }
         if not a.no_cpu_baseline:

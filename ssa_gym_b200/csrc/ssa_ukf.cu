@@ -1675,6 +1675,19 @@ struct ssa_ukf {
     int gflags[2], gkernels[2];
     int use_graph;
   } hp;
+  // ssa_ukf_step as one graph launch (SSA_UKF_STEP_GRAPH=0: five plain launches).  The only launch parameter that
+  // changes from step to step is the trans_matrix, which only k_hx reads: its kernel node is re-parameterised
+  // before every launch (cudaGraphExecKernelNodeSetParams), the other four nodes stay as captured.
+  struct {
+    int on, n;
+    int flags[4];
+    cudaGraph_t graph[4];  // kept alive: the node handles used for the parameter update belong to it
+    cudaGraphExec_t gexec[4];
+    int gkernels[4];
+    cudaGraphNode_t hx_node[4];
+    cudaKernelNodeParams hx_params[4];
+    KParams p[4];
+  } sg;
   // device-resident episodic mode (ssa_ukf_rollout_*)
   struct {
     int init, n_orbits, n_table, update_interval;
@@ -1799,6 +1812,8 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
     h->use_team = (kv && strcmp(kv, "team") == 0) ? 1 : 0;
     const char* ts = getenv("SSA_UKF_TEAM_SMALL");
     h->team_small = (ts && strcmp(ts, "1") == 0) ? 1 : 0;
+    const char* gv = getenv("SSA_UKF_STEP_GRAPH");
+    h->sg.on = (gv && strcmp(gv, "0") == 0) ? 0 : 1;
     const char* pv = getenv("SSA_UKF_PDL");
     h->pdl = (pv && strcmp(pv, "0") == 0) ? 0 : 1;
     h->staged_max = kStagedMaxDefault;
@@ -1832,6 +1847,7 @@ int ssa_ukf_destroy(ssa_ukf* h) {
     }
     cudaStreamDestroy(h->hp.up); cudaStreamDestroy(h->hp.dn);
   }
+  for (int i = 0; i < h->sg.n; ++i) { cudaGraphExecDestroy(h->sg.gexec[i]); cudaGraphDestroy(h->sg.graph[i]); }
   if (h->ro.init) {
     cudaFree(h->ro.dbuf); cudaFree(h->ro.ibuf); cudaFree(h->ro.dout);
     cudaFreeHost(h->ro.hout); cudaFreeHost(h->ro.hin);
@@ -1993,7 +2009,7 @@ struct StepOverride {  // episodic mode: redirect the step's inputs / outputs
 };
 
 static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cudaEvent_t* ev, int hostbuf = -1,
-                     const StepOverride* ov = nullptr) {
+                     const StepOverride* ov = nullptr, KParams* p_out = nullptr) {
   if (!h) return SSA_EINVAL;
   if ((flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE)) && !M && !(flags & SSA_STEP_M_PER_ENV) &&
       hostbuf < 0 && !ov) {
@@ -2039,6 +2055,7 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
   if (M) memcpy(p.ob.M, M, sizeof(p.ob.M));
   memcpy(p.ob.obs_itrs, c.obs_itrs, sizeof(p.ob.obs_itrs));
   memcpy(p.ob.T, c.T, sizeof(p.ob.T));
+  if (p_out) *p_out = p;  // single-chunk launches all use these parameters (obj0 = 0, Nc = N)
   if (ev) CK(cudaEventRecord(ev[0], st));
   if (h->use_team) {
     const unsigned grid = (unsigned)((c.n_objects + kTeamsPerCta - 1) / kTeamsPerCta);
@@ -2088,7 +2105,62 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
   return SSA_OK;
 }
 
-int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) { return step_impl(h, M, flags, stream, nullptr); }
+int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
+  if (!h) return SSA_EINVAL;
+  if (!h->sg.on || h->use_team || (flags & SSA_STEP_M_PER_ENV) || !M || h->chunk < h->cfg.n_objects)
+    return step_impl(h, M, flags, stream, nullptr);
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int gi = -1;
+  for (int i = 0; i < h->sg.n; ++i) if (h->sg.flags[i] == flags) gi = i;
+  if (gi < 0) {  // capture the chain for this flag combination (at most 4 are cached)
+    if (h->sg.n == 4) { cudaGraphExecDestroy(h->sg.gexec[3]); cudaGraphDestroy(h->sg.graph[3]); h->sg.n = 3; }
+    gi = h->sg.n;
+    cudaStream_t cs;
+    CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    const long l0 = h->launches;
+    CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const int rc = step_impl(h, M, flags, cs, nullptr, -1, nullptr, &h->sg.p[gi]);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cs, &g);
+    h->sg.gkernels[gi] = (int)(h->launches - l0);
+    h->launches = l0;
+    cudaStreamDestroy(cs);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess) return set_err("cudaStreamEndCapture", ce);
+    h->sg.hx_node[gi] = nullptr;
+    size_t nn = 0;
+    cudaGraphGetNodes(g, nullptr, &nn);
+    cudaGraphNode_t nodes[16];
+    if (nn > 16) nn = 16;
+    cudaGraphGetNodes(g, nodes, &nn);
+    for (size_t i = 0; i < nn; ++i) {
+      cudaGraphNodeType ty;
+      cudaKernelNodeParams kp;
+      if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel &&
+          cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func == (void*)k_hx) {
+        h->sg.hx_node[gi] = nodes[i];
+        h->sg.hx_params[gi] = kp;
+      }
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&h->sg.gexec[gi], g, 0);
+    if (ie != cudaSuccess) { cudaGraphDestroy(g); return set_err("cudaGraphInstantiate", ie); }
+    h->sg.graph[gi] = g;
+    h->sg.flags[gi] = flags;
+    h->sg.n = gi + 1;
+  }
+  if (h->sg.hx_node[gi]) {  // this step's trans_matrix
+    memcpy(h->sg.p[gi].ob.M, M, 9 * sizeof(double));
+    void* args[1] = {&h->sg.p[gi]};
+    cudaKernelNodeParams kp = h->sg.hx_params[gi];
+    kp.kernelParams = args;
+    kp.extra = nullptr;
+    CK(cudaGraphExecKernelNodeSetParams(h->sg.gexec[gi], h->sg.hx_node[gi], &kp));
+  }
+  CK(cudaGraphLaunch(h->sg.gexec[gi], st));
+  h->launches += h->sg.gkernels[gi];
+  return SSA_OK;
+}
 
 static int hostpipe_init(ssa_ukf* h) {
   if (h->hp.init) return SSA_OK;
@@ -2284,6 +2356,7 @@ int ssa_ukf_rollout_config(ssa_ukf* h, const double* orbits, int n_orbits, const
   }
   CK(cudaSetDevice(h->device));
   const size_t N = h->cfg.n_objects, E = h->cfg.n_envs;
+  for (int i = 0; i < h->sg.n; ++i) { cudaGraphExecDestroy(h->sg.gexec[i]); cudaGraphDestroy(h->sg.graph[i]); }
   if (h->ro.init) {
     cudaFree(h->ro.dbuf); cudaFree(h->ro.ibuf); cudaFree(h->ro.dout); cudaFreeHost(h->ro.hout); cudaFreeHost(h->ro.hin);
     for (int i = 0; i < 2; ++i) if (h->ro.gexec[i]) { cudaGraphExecDestroy(h->ro.gexec[i]); h->ro.gexec[i] = nullptr; }
