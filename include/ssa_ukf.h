@@ -204,6 +204,16 @@ int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stre
 /* reward.py score terms from the current covariances: out double[N][6] =
  * [score_scaled_trace_P, score_trace_P, score_scaled_det_P(dt), score_det_P, score_det_pos_P, |dpos|] */
 int ssa_ukf_scores(ssa_ukf* h, void* stream);
+/* Catalog generator: the acceptance rule of envs/orbit_gen.py:47-75 for a batch of K candidate orbits
+ * (GCRS states at the epoch).  For each candidate and each of the n sample times i*step_s: two-body propagation from
+ * the epoch (the reference uses fx_xyz_markley there; this is the same two-body flow through ssa_fx), geodetic
+ * altitude of x @ trans_table[i] (ecef2lla, transformations.py:239-279) and elevation of hx_aer_erfa; accepted iff
+ * every altitude > min_alt and either the object is always visible, or it is seen within the first
+ * `first_window` samples and no visibility gap reaches `max_gap` samples.  Stand-alone (no handle): host arrays in,
+ * accept[K] out (and, optionally, elev / alt [K][n] for inspection).                                              */
+int ssa_orbit_gen_eval(const double* cand, int K, const double* trans_table, int n, double step_s, const double obs_itrs[3],
+                       const double T[9], double obs_limit, double min_alt, int first_window, int max_gap, uint8_t* accept,
+                       double* elev, double* alt, int device);
 /* Consistency diagnostics of the current state: per object NEES = (x_true - x)^T P^-1 (x_true - x)
  * (SS2:436-446 anees), and for the objects updated by the last step run with SSA_STEP_RECORD the NIS
  * y^T S^-1 y (SS2:564-569) and the innovation-bound flags (SS2:598-604) -> SSA_F_DIAG, SSA_F_INNOV_FLAGS.      */

@@ -42,6 +42,35 @@ SSA_HD void ssa_hx_aer(const double* x, const ssa_obs* o, double* out) {
   out[2] = r;
 }
 
+// Geodetic altitude of an ECEF position (transformations.py:239-279 `ecef2lla`, the closed form of You (2000);
+// only the altitude is needed by the catalog generator's 300 km rule, envs/orbit_gen.py:62).  WGS-84.
+SSA_HD double ssa_ecef_altitude(const double* ecef) {
+  const double a = 6378137.0, f = 1.0 / 298.257223563;
+  const double b = ssa_mul(1.0 - f, a);
+  const double x = ecef[0], y = ecef[1], z = ecef[2];
+  const double r2 = ssa_fma(z, z, ssa_fma(y, y, ssa_mul(x, x)));
+  const double E2 = ssa_fma(a, a, -ssa_mul(b, b));
+  const double E = ssa_sqrt(E2);
+  const double w = r2 - E2;
+  const double u = ssa_sqrt(ssa_fma(0.5, w, ssa_mul(0.5, ssa_sqrt(ssa_fma(ssa_mul(4.0, E2), ssa_mul(z, z), ssa_mul(w, w))))));
+  const double Q = ssa_sqrt(ssa_fma(y, y, ssa_mul(x, x)));
+  const double huE = ssa_sqrt(ssa_fma(u, u, E2));
+  double beta;
+  if (!(Q == 0.0 || u == 0.0)) beta = ssa_atan(ssa_mul(ssa_div(huE, u), ssa_div(z, Q)));
+  else beta = (z >= 0.0) ? SSA_C(PIO2_A) : -SSA_C(PIO2_A);
+  double sb, cb;
+  ssa_sincos(beta, &sb, &cb);
+  const double eps = ssa_div(ssa_mul(ssa_fma(b, u, -ssa_mul(a, huE)) + E2, sb),
+                             ssa_fma(ssa_mul(a, huE), ssa_div(1.0, cb), -ssa_mul(E2, cb)));
+  beta = beta + eps;
+  ssa_sincos(beta, &sb, &cb);
+  const double dz = ssa_fma(-b, sb, z), dq = ssa_fma(-a, cb, Q);
+  double alt = ssa_sqrt(ssa_fma(dq, dq, ssa_mul(dz, dz)));
+  const double inside = ssa_div(ssa_fma(y, y, ssa_mul(x, x)), ssa_mul(a, a)) + ssa_div(ssa_mul(z, z), ssa_mul(b, b));
+  if (inside < 1.0) alt = -alt;
+  return alt;
+}
+
 SSA_HD void ssa_aer2uvw(const double* aer, double* uvw) {
   double sa, ca, se, ce;
   ssa_sincos(aer[0], &sa, &ca);

@@ -1439,6 +1439,52 @@ __global__ void ssa_diag_kernel(const double* __restrict__ xt, const double* __r
   flags[n] = (uint8_t)f;
 }
 
+// ---- catalog generator (envs/orbit_gen.py:47-75): acceptance rule of a batch of candidate orbits ------
+// one thread per (candidate, sample time): propagate from the epoch, altitude and elevation at that time
+__global__ void __launch_bounds__(128) ssa_orbit_eval_kernel(const double* __restrict__ cand, int K, const double* __restrict__ table,
+                                                             int n, double step_s, ssa_obs ob, double obs_limit, double min_alt,
+                                                             uint8_t* flags, double* elev, double* alt) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)K * n) return;
+  const int i = (int)(t / K), c = (int)(t % K);  // candidates fastest: a warp shares the sample time (and its matrix)
+  double x0[6], x[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) x0[q] = cand[(long)c * 6 + q];
+  const int exc = ssa_fx(x0, ssa_mul(step_s, (double)i), x);
+#pragma unroll
+  for (int q = 0; q < 9; ++q) ob.M[q] = table[(long)i * 9 + q];
+  // orbit_gen.py:57 forms x_gcrs[:3] @ trans_matrix[i] (a row vector times the matrix, i.e. M^T x) for the altitude test
+  double xi[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) xi[j] = ssa_fma(x[2], ob.M[6 + j], ssa_fma(x[1], ob.M[3 + j], ssa_mul(x[0], ob.M[j])));
+  const double h = ssa_ecef_altitude(xi);
+  double z[3];
+  ssa_hx_aer(x, &ob, z);
+  const long o = (long)c * n + i;
+  flags[o] = (uint8_t)((h > min_alt ? 1 : 0) | (z[1] >= obs_limit ? 2 : 0) | (exc ? 4 : 0));
+  if (elev) elev[o] = z[1];
+  if (alt) alt[o] = h;
+}
+// one thread per candidate: the visibility-gap rule (orbit_gen.py:60-73)
+__global__ void ssa_orbit_accept_kernel(const uint8_t* __restrict__ flags, int K, int n, int first_window, int max_gap, uint8_t* accept) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= K) return;
+  int all_alt = 1, all_vis = 1, any_gap = 0, first = 0, run = 0, longest = 0, bad = 0;
+  for (int i = 0; i < n; ++i) {
+    const int f = flags[(long)c * n + i];
+    all_alt &= f & 1;
+    const int vis = (f >> 1) & 1;
+    bad |= f & 4;
+    all_vis &= vis;
+    if (i < first_window) first += vis;
+    if (!vis) { any_gap = 1; run += 1; longest = run > longest ? run : longest; }
+    else run = 0;
+  }
+  int ok = 0;
+  if (all_alt && !bad) ok = any_gap ? (first > 0 && longest < max_gap) : all_vis;
+  accept[c] = (uint8_t)ok;
+}
+
 // reward.py:6-50 score terms, one thread per object
 __global__ void ssa_scores_kernel(const double* __restrict__ P, const double* __restrict__ dpos, double* out, long ld,
                                   int N, double dt) {
@@ -2527,6 +2573,45 @@ int ssa_ukf_diagnostics(ssa_ukf* h, void* stream) {
   h->launches++;
   CK(cudaGetLastError());
   return SSA_OK;
+}
+
+int ssa_orbit_gen_eval(const double* cand, int K, const double* trans_table, int n, double step_s, const double obs_itrs[3],
+                       const double T[9], double obs_limit, double min_alt, int first_window, int max_gap, uint8_t* accept,
+                       double* elev, double* alt, int device) {
+  if (!cand || K < 1 || !trans_table || n < 1 || !obs_itrs || !T || !accept) return SSA_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { snprintf(g_err, sizeof(g_err), "no CUDA device"); return SSA_ENODEV; }
+  CK(cudaSetDevice(device));
+  const size_t KN = (size_t)K * n;
+  double *d_c = nullptr, *d_t = nullptr, *d_e = nullptr, *d_a = nullptr;
+  uint8_t *d_f = nullptr, *d_acc = nullptr;
+  int rc = SSA_OK;
+  cudaError_t e;
+#define OG(call) do { if ((e = (call)) != cudaSuccess) { rc = set_err(#call, e); goto done; } } while (0)
+  OG(cudaMalloc(&d_c, sizeof(double) * 6 * K));
+  OG(cudaMalloc(&d_t, sizeof(double) * 9 * n));
+  OG(cudaMalloc(&d_f, KN));
+  OG(cudaMalloc(&d_acc, K));
+  if (elev) OG(cudaMalloc(&d_e, sizeof(double) * KN));
+  if (alt) OG(cudaMalloc(&d_a, sizeof(double) * KN));
+  OG(cudaMemcpy(d_c, cand, sizeof(double) * 6 * K, cudaMemcpyHostToDevice));
+  OG(cudaMemcpy(d_t, trans_table, sizeof(double) * 9 * n, cudaMemcpyHostToDevice));
+  {
+    ssa_obs ob;
+    memset(&ob, 0, sizeof(ob));
+    memcpy(ob.obs_itrs, obs_itrs, sizeof(ob.obs_itrs));
+    memcpy(ob.T, T, sizeof(ob.T));
+    ssa_orbit_eval_kernel<<<(unsigned)((KN + 127) / 128), 128>>>(d_c, K, d_t, n, step_s, ob, obs_limit, min_alt, d_f, d_e, d_a);
+    ssa_orbit_accept_kernel<<<(unsigned)((K + 127) / 128), 128>>>(d_f, K, n, first_window, max_gap, d_acc);
+  }
+  OG(cudaGetLastError());
+  OG(cudaMemcpy(accept, d_acc, K, cudaMemcpyDeviceToHost));
+  if (elev) OG(cudaMemcpy(elev, d_e, sizeof(double) * KN, cudaMemcpyDeviceToHost));
+  if (alt) OG(cudaMemcpy(alt, d_a, sizeof(double) * KN, cudaMemcpyDeviceToHost));
+#undef OG
+done:
+  cudaFree(d_c); cudaFree(d_t); cudaFree(d_f); cudaFree(d_acc); cudaFree(d_e); cudaFree(d_a);
+  return rc;
 }
 
 int ssa_ukf_scores(ssa_ukf* h, void* stream) {

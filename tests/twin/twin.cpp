@@ -265,6 +265,34 @@ TW1(twin_asinh, ssa_asinh) TW1(twin_acosh, ssa_acosh) TW1(twin_pow23, ssa_pow23)
 void twin_atan2(const double* y, const double* x, double* z, int n) { for (int i = 0; i < n; ++i) z[i] = ssa_atan2(y[i], x[i]); }
 void twin_pymod(const double* y, const double* x, double* z, int n) { for (int i = 0; i < n; ++i) z[i] = ssa_pymod(y[i], x[i]); }
 
+// acceptance rule of the catalog generator (ssa_orbit_eval_kernel + ssa_orbit_accept_kernel)
+void twin_orbit_gen_eval(const double* cand, int K, const double* table, int n, double step_s, const double* obs_itrs,
+                         const double* T, double obs_limit, double min_alt, int first_window, int max_gap, uint8_t* accept,
+                         double* elev, double* alt) {
+#pragma omp parallel for
+  for (int c = 0; c < K; ++c) {
+    int all_alt = 1, all_vis = 1, any_gap = 0, first = 0, run = 0, longest = 0, bad = 0;
+    for (int i = 0; i < n; ++i) {
+      ssa_obs ob;
+      memcpy(ob.obs_itrs, obs_itrs, 24); memcpy(ob.T, T, 72); memcpy(ob.M, table + (size_t)i * 9, 72);
+      double x[6], xi[3], z[3];
+      const int exc = ssa_fx(cand + (size_t)c * 6, ssa_mul(step_s, (double)i), x);
+      for (int j = 0; j < 3; ++j) xi[j] = ssa_fma(x[2], ob.M[6 + j], ssa_fma(x[1], ob.M[3 + j], ssa_mul(x[0], ob.M[j])));
+      const double h = ssa_ecef_altitude(xi);
+      ssa_hx_aer(x, &ob, z);
+      const int vis = z[1] >= obs_limit;
+      if (elev) elev[(size_t)c * n + i] = z[1];
+      if (alt) alt[(size_t)c * n + i] = h;
+      all_alt &= (h > min_alt); bad |= exc; all_vis &= vis;
+      if (i < first_window) first += vis;
+      if (!vis) { any_gap = 1; run += 1; longest = run > longest ? run : longest; } else run = 0;
+    }
+    int ok = 0;
+    if (all_alt && !bad) ok = any_gap ? (first > 0 && longest < max_gap) : all_vis;
+    accept[c] = (uint8_t)ok;
+  }
+}
+
 // diagnostics of ssa_diag_kernel on host-layout arrays (P packed [N][21])
 void twin_diagnostics(int N, const double* x_true, const double* x, const double* P, const double* y, const double* S,
                       const uint8_t* updated, double* nees, double* nis, uint8_t* flags) {
