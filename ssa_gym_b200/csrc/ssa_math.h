@@ -341,6 +341,45 @@ SSA_HD double ssa_atan(double x) { return ssa_atan2(x, 1.0); }
 // ---------------------------------------------------------------------------------------------
 // asin / acos — fdlibm rational kernel R(t) = t*P(t)/Q(t)
 // ---------------------------------------------------------------------------------------------
+// INL selects the inlined division / square root (ssa_div_i / ssa_sqrt_i) for the kernels that are bound by issue
+// slots rather than code size (k_hx); both variants are IEEE operations and return the same bits.
+template <bool INL> SSA_HD double ssa_div_t(double a, double b) { return INL ? ssa_div_i(a, b) : ssa_div(a, b); }
+template <bool INL> SSA_HD double ssa_sqrt_t(double a) { return INL ? ssa_sqrt_i(a) : ssa_sqrt(a); }
+template <bool INL>
+SSA_HD double ssa_asin_R_t(double t) {
+  double p = ssa_fma(t, SSA_C(PS5), SSA_C(PS4));
+  p = ssa_fma(t, p, SSA_C(PS3));
+  p = ssa_fma(t, p, SSA_C(PS2));
+  p = ssa_fma(t, p, SSA_C(PS1));
+  p = ssa_fma(t, p, SSA_C(PS0));
+  p = ssa_mul(t, p);
+  double q = ssa_fma(t, SSA_C(QS4), SSA_C(QS3));
+  q = ssa_fma(t, q, SSA_C(QS2));
+  q = ssa_fma(t, q, SSA_C(QS1));
+  q = ssa_fma(t, q, SSA_C(ONE));
+  return ssa_div_t<INL>(p, q);
+}
+template <bool INL>
+SSA_HD double ssa_asin_t(double x) {
+  const double ax = ssa_fabs(x);
+  double res;
+  if (ax < SSA_C(HALF)) {
+    res = ssa_fma(ax, ssa_asin_R_t<INL>(ssa_mul(ax, ax)), ax);
+  } else if (ax <= SSA_C(ONE)) {
+    // asin(x) = pi/2 - 2 asin(sqrt((1-x)/2)); c = (t - s*s)/(2s) is the FMA residual of the square root,
+    // folded in so that pi/2 - 2(s + c)(1 + r) does not lose the low part of s.
+    const double t = ssa_mul(SSA_C(HALF), SSA_C(ONE) - ax);
+    const double s = ssa_sqrt_t<INL>(t);
+    const double r = ssa_asin_R_t<INL>(t);
+    const double c = (s == 0.0) ? 0.0 : ssa_div_t<INL>(ssa_fma(-s, s, t), ssa_add(s, s));
+    const double p = ssa_fma(2.0, ssa_mul(s, r), -(SSA_C(PIO2_B) - ssa_mul(2.0, c)));
+    const double q = SSA_C(PIO4_HI) - ssa_mul(2.0, s);
+    res = SSA_C(PIO4_HI) - (p - q);
+  } else {
+    res = ssa_nan();
+  }
+  return ssa_signbit(x) ? -res : res;
+}
 SSA_HD double ssa_asin_R(double t) {
   double p = ssa_fma(t, SSA_C(PS5), SSA_C(PS4));
   p = ssa_fma(t, p, SSA_C(PS3));
@@ -354,26 +393,7 @@ SSA_HD double ssa_asin_R(double t) {
   q = ssa_fma(t, q, SSA_C(ONE));
   return ssa_div(p, q);
 }
-SSA_HD_NOINLINE double ssa_asin(double x) {
-  const double ax = ssa_fabs(x);
-  double res;
-  if (ax < SSA_C(HALF)) {
-    res = ssa_fma(ax, ssa_asin_R(ssa_mul(ax, ax)), ax);
-  } else if (ax <= SSA_C(ONE)) {
-    // asin(x) = pi/2 - 2 asin(sqrt((1-x)/2)); c = (t - s*s)/(2s) is the FMA residual of the square root,
-    // folded in so that pi/2 - 2(s + c)(1 + r) does not lose the low part of s.
-    const double t = ssa_mul(SSA_C(HALF), SSA_C(ONE) - ax);
-    const double s = ssa_sqrt(t);
-    const double r = ssa_asin_R(t);
-    const double c = (s == 0.0) ? 0.0 : ssa_div(ssa_fma(-s, s, t), ssa_add(s, s));
-    const double p = ssa_fma(2.0, ssa_mul(s, r), -(SSA_C(PIO2_B) - ssa_mul(2.0, c)));
-    const double q = SSA_C(PIO4_HI) - ssa_mul(2.0, s);
-    res = SSA_C(PIO4_HI) - (p - q);
-  } else {
-    res = ssa_nan();
-  }
-  return ssa_signbit(x) ? -res : res;
-}
+SSA_HD_NOINLINE double ssa_asin(double x) { return ssa_asin_t<false>(x); }
 SSA_HD_NOINLINE double ssa_acos(double x) {
   const double ax = ssa_fabs(x);
   if (ax < SSA_C(HALF)) {

@@ -24,8 +24,9 @@ typedef struct {
   double T[9];         // trans_uvw_ecef, row-major, as in transformations.py:341-343
 } ssa_obs;
 
-// hx for the 'aer' observation type.  out = [az, el, range]
-SSA_HD void ssa_hx_aer(const double* x, const ssa_obs* o, double* out) {
+// hx for the 'aer' observation type.  out = [az, el, range].  INL: inlined math (k_hx), same arithmetic.
+template <bool INL>
+SSA_HD void ssa_hx_aer_t(const double* x, const ssa_obs* o, double* out) {
   // x_itrs = M @ x[:3]
   double xi[3], d[3], e[3];
   for (int i = 0; i < 3; ++i)
@@ -34,13 +35,14 @@ SSA_HD void ssa_hx_aer(const double* x, const ssa_obs* o, double* out) {
   // R_enz = T^T @ delta
   for (int i = 0; i < 3; ++i)
     e[i] = ssa_fma(o->T[6 + i], d[2], ssa_fma(o->T[3 + i], d[1], ssa_mul(o->T[i], d[0])));
-  const double r = ssa_sqrt(ssa_fma(d[2], d[2], ssa_fma(d[1], d[1], ssa_mul(d[0], d[0]))));
-  double az = ssa_atan2(e[1], e[0]);
+  const double r = ssa_sqrt_t<INL>(ssa_fma(d[2], d[2], ssa_fma(d[1], d[1], ssa_mul(d[0], d[0]))));
+  double az = INL ? ssa_atan2_i(e[1], e[0]) : ssa_atan2(e[1], e[0]);
   if (az < 0.0) az = az + SSA_C(TWOPI);
   out[0] = az;
-  out[1] = ssa_asin(ssa_div(e[2], r));
+  out[1] = INL ? ssa_asin_t<true>(ssa_div_i(e[2], r)) : ssa_asin(ssa_div(e[2], r));
   out[2] = r;
 }
+SSA_HD void ssa_hx_aer(const double* x, const ssa_obs* o, double* out) { ssa_hx_aer_t<false>(x, o, out); }
 
 // Geodetic altitude of an ECEF position (transformations.py:239-279 `ecef2lla`, the closed form of You (2000);
 // only the altitude is needed by the catalog generator's 300 km rule, envs/orbit_gen.py:62).  WGS-84.
@@ -71,15 +73,16 @@ SSA_HD double ssa_ecef_altitude(const double* ecef) {
   return alt;
 }
 
-SSA_HD void ssa_aer2uvw(const double* aer, double* uvw) {
-  double sa, ca, se, ce;
-  ssa_sincos(aer[0], &sa, &ca);
-  ssa_sincos(aer[1], &se, &ce);
-  const double rc = ssa_mul(aer[2], ce);
-  uvw[0] = ssa_mul(rc, ca);
-  uvw[1] = ssa_mul(rc, sa);
-  uvw[2] = ssa_mul(aer[2], se);
+template <bool INL>
+SSA_HD void ssa_aer2uvw_t(const double* aer, double* uvw) {
+  const ssa_sc a = INL ? ssa_sincos_i(aer[0]) : ssa_sincos_v(aer[0]);
+  const ssa_sc e = INL ? ssa_sincos_i(aer[1]) : ssa_sincos_v(aer[1]);
+  const double rc = ssa_mul(aer[2], e.c);
+  uvw[0] = ssa_mul(rc, a.c);
+  uvw[1] = ssa_mul(rc, a.s);
+  uvw[2] = ssa_mul(aer[2], e.s);
 }
+SSA_HD void ssa_aer2uvw(const double* aer, double* uvw) { ssa_aer2uvw_t<false>(aer, uvw); }
 
 SSA_HD void ssa_uvw2aer(const double* uvw, double* aer) {
   const double r = ssa_sqrt(ssa_fma(uvw[2], uvw[2], ssa_fma(uvw[1], uvw[1], ssa_mul(uvw[0], uvw[0]))));

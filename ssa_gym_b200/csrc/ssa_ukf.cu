@@ -685,6 +685,9 @@ __device__ __forceinline__ long upd_object(const KParams& p, long lidx) {
   return -1;
 }
 
+#ifndef SSA_HX_INLINE
+#define SSA_HX_INLINE true
+#endif
 __global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx(const KParams p) {
   pdl_prologue();
   const long lidx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -703,7 +706,7 @@ __global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx
 #pragma unroll
       for (int i = 0; i < 9; ++i) ob.M[i] = env_M(p, idx / p.m)[i];
     }
-    ssa_hx_aer(xt, &ob, zt);
+    ssa_hx_aer_t<SSA_HX_INLINE>(xt, &ob, zt);
 #pragma unroll
     for (int a = 0; a < 3; ++a) p.ZT[a * lds + loc] = zt[a];
     p.visible[idx] = (uint8_t)(zt[1] >= p.obs_limit);
@@ -731,8 +734,8 @@ __global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx
 #pragma unroll
       for (int i = 0; i < 9; ++i) ob.M[i] = env_M(p, obj / p.m)[i];
     }
-    ssa_hx_aer(s, &ob, z);
-    ssa_aer2uvw(z, uvw);
+    ssa_hx_aer_t<SSA_HX_INLINE>(s, &ob, z);
+    ssa_aer2uvw_t<SSA_HX_INLINE>(z, uvw);
 #pragma unroll
     for (int a = 0; a < 3; ++a) p.UVW[(k * 3 + a) * lds + loc] = uvw[a];
   } else {
