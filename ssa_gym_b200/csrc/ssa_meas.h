@@ -84,14 +84,16 @@ SSA_HD void ssa_aer2uvw_t(const double* aer, double* uvw) {
 }
 SSA_HD void ssa_aer2uvw(const double* aer, double* uvw) { ssa_aer2uvw_t<false>(aer, uvw); }
 
-SSA_HD void ssa_uvw2aer(const double* uvw, double* aer) {
-  const double r = ssa_sqrt(ssa_fma(uvw[2], uvw[2], ssa_fma(uvw[1], uvw[1], ssa_mul(uvw[0], uvw[0]))));
-  double az = ssa_atan2(uvw[1], uvw[0]);
+template <bool INL>
+SSA_HD void ssa_uvw2aer_t(const double* uvw, double* aer) {
+  const double r = ssa_sqrt_t<INL>(ssa_fma(uvw[2], uvw[2], ssa_fma(uvw[1], uvw[1], ssa_mul(uvw[0], uvw[0]))));
+  double az = INL ? ssa_atan2_i(uvw[1], uvw[0]) : ssa_atan2(uvw[1], uvw[0]);
   if (az < 0.0) az = az + SSA_C(TWOPI);
   aer[0] = az;
-  aer[1] = ssa_asin(ssa_div(uvw[2], r));
+  aer[1] = INL ? ssa_asin_t<true>(ssa_div_i(uvw[2], r)) : ssa_asin(ssa_div(uvw[2], r));
   aer[2] = r;
 }
+SSA_HD void ssa_uvw2aer(const double* uvw, double* aer) { ssa_uvw2aer_t<false>(uvw, aer); }
 
 // residual_z_aer.  The reference wraps the azimuth difference through atan2(sin d, cos d)
 // (dynamics.py:263).  For |d| < pi that expression IS d (to within an ulp of d, and d is the exact value), so

@@ -751,6 +751,9 @@ constexpr int UR_ZS = 0, UR_UVW = 39, UR_ZT = 78, UR_U = 81, UR_XT = 102, UR_X =
 
 // UKF.update + epilogue of one object.  STAGED = false: every operand is read from global memory (k_update);
 // STAGED = true: from the block's shared tile `sm` (already offset by the thread's column, row stride ss).
+#ifndef SSA_UPD_INLINE
+#define SSA_UPD_INLINE true
+#endif
 template <bool STAGED>
 __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj, const double* sm, int ss) {
   const long lds = p.lds;
@@ -798,7 +801,7 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
           for (int k = 1; k < SSA_NSIG; ++k) acc = ssa_fma(p.Wm[k], V_UVW(k * 3 + a), acc);
           zm[a] = acc;
         }
-        ssa_uvw2aer(zm, zp);
+        ssa_uvw2aer_t<SSA_UPD_INLINE>(zm, zp);
       } else {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -873,7 +876,7 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
 #pragma unroll
         for (int e = 0; e < 9; ++e) Sm[e] = Ss[e] + __ldg(p.qr + 21 + e);
       }
-      const int ok = ssa_inv3(Sm, SI);
+      const int ok = ssa_inv3_t<SSA_UPD_INLINE>(Sm, SI);
       if (p.obs_type == SSA_OBS_AER) ssa_residual_aer(z, zp, yr);
       else {
 #pragma unroll
@@ -938,10 +941,10 @@ __device__ __forceinline__ void update_body(const KParams& p, long loc, long obj
     for (int i = 0; i < 6; ++i) { p.obs[obj * 12 + i] = xe[i]; p.obs[obj * 12 + 6 + i] = dg[i]; }
     const double d0 = xe[0] - xt[0], d1 = xe[1] - xt[1], d2 = xe[2] - xt[2];
     const double d3 = xe[3] - xt[3], d4 = xe[4] - xt[4], d5 = xe[5] - xt[5];
-    p.dpos[obj] = ssa_sqrt(ssa_fma(d2, d2, ssa_fma(d1, d1, ssa_mul(d0, d0))));
-    p.dvel[obj] = ssa_sqrt(ssa_fma(d5, d5, ssa_fma(d4, d4, ssa_mul(d3, d3))));
-    p.spos[obj] = ssa_sqrt((dg[0] + dg[1]) + dg[2]);
-    p.svel[obj] = ssa_sqrt((dg[3] + dg[4]) + dg[5]);
+    p.dpos[obj] = ssa_sqrt_t<SSA_UPD_INLINE>(ssa_fma(d2, d2, ssa_fma(d1, d1, ssa_mul(d0, d0))));
+    p.dvel[obj] = ssa_sqrt_t<SSA_UPD_INLINE>(ssa_fma(d5, d5, ssa_fma(d4, d4, ssa_mul(d3, d3))));
+    p.spos[obj] = ssa_sqrt_t<SSA_UPD_INLINE>((dg[0] + dg[1]) + dg[2]);
+    p.svel[obj] = ssa_sqrt_t<SSA_UPD_INLINE>((dg[3] + dg[4]) + dg[5]);
     p.trace[obj] = ((((dg[0] + dg[1]) + dg[2]) + dg[3]) + dg[4]) + dg[5];
   }
 #undef V_ZS

@@ -140,7 +140,8 @@ SSA_HD double ssa_wouter13(const double* ya, int lda, int i, const double* yb, i
 // inverse of a general 3x3 by LU with partial pivoting, the way numpy.linalg.inv does it
 // (LAPACK dgesv on the identity: dgetrf column scaling by the reciprocal pivot, dgetrs solves).
 // Returns 0 if a pivot is exactly zero (numpy raises LinAlgError "Singular matrix").
-SSA_HD int ssa_inv3(const double* S /* row-major 3x3 */, double* SI) {
+template <bool INL>
+SSA_HD int ssa_inv3_t(const double* S /* row-major 3x3 */, double* SI) {
   double a[3][3], b[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -163,7 +164,7 @@ SSA_HD int ssa_inv3(const double* S /* row-major 3x3 */, double* SI) {
       }
     }
     ok &= (a[c][c] != 0.0);
-    const double rp = ssa_div(1.0, a[c][c]);
+    const double rp = ssa_div_t<INL>(1.0, a[c][c]);
 #pragma unroll
     for (int i = c + 1; i < 3; ++i) {
       a[i][c] = ssa_mul(a[i][c], rp);
@@ -177,13 +178,15 @@ SSA_HD int ssa_inv3(const double* S /* row-major 3x3 */, double* SI) {
     double y0 = b[0][col];
     double y1 = ssa_fma(-a[1][0], y0, b[1][col]);
     double y2 = ssa_fma(-a[2][1], y1, ssa_fma(-a[2][0], y0, b[2][col]));
-    const double x2 = ssa_div(y2, a[2][2]);
-    const double x1 = ssa_div(ssa_fma(-a[1][2], x2, y1), a[1][1]);
-    const double x0 = ssa_div(ssa_fma(-a[0][1], x1, ssa_fma(-a[0][2], x2, y0)), a[0][0]);
+    const double x2 = ssa_div_t<INL>(y2, a[2][2]);
+    const double x1 = ssa_div_t<INL>(ssa_fma(-a[1][2], x2, y1), a[1][1]);
+    const double x0 = ssa_div_t<INL>(ssa_fma(-a[0][1], x1, ssa_fma(-a[0][2], x2, y0)), a[0][0]);
     SI[col] = x0; SI[3 + col] = x1; SI[6 + col] = x2;
   }
   return ok;
 }
+
+SSA_HD int ssa_inv3(const double* S, double* SI) { return ssa_inv3_t<false>(S, SI); }
 
 // Consistency diagnostics.
 // NEES d^T P^-1 d of one object (SS2:436-446 `anees`: delta @ inv(P_filter) @ delta), evaluated through the Cholesky
