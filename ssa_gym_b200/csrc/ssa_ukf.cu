@@ -447,6 +447,9 @@ __global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) 
 // lanes), intermediates stay in L2 for C2-sized batches.  The arithmetic of every output element is the
 // same sequence of rounded operations as in the team kernel and the host twin.
 // =====================================================================================================
+#ifndef SSA_CHOL_INLINE
+#define SSA_CHOL_INLINE true
+#endif
 constexpr int kSplitThreads = 128;
 #ifndef SSA_FX_THREADS
 #define SSA_FX_THREADS 128
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(kObjThreads, SSA_LB_FAC * 128 / kObjThreads) k
   const bool update = (p.flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT)) != 0;
   if ((predict || update) && !(st & SSA_ST_FAILED)) {
     double U[SSA_NP];
-    const int r = ssa_robust_chol6(p.P + obj, ld, p.lam, U);
+    const int r = ssa_robust_chol6_t<SSA_CHOL_INLINE>(p.P + obj, ld, p.lam, U);
     if (r < 0) {
       code = SSA_ST_LINALG | (predict ? 0 : SSA_ST_IN_UPDATE);
     } else {
@@ -643,7 +646,7 @@ __device__ __forceinline__ void ut_body(const KParams& p, long loc, long obj, co
     if (nan) code |= SSA_ST_NAN;
     if (p.resample) {
       double U[SSA_NP];
-      const int r2 = ssa_robust_chol6(Pn, 1, p.lam, U);
+      const int r2 = ssa_robust_chol6_t<SSA_CHOL_INLINE>(Pn, 1, p.lam, U);
       if (r2 < 0) code |= SSA_ST_LINALG;
       else {
         if (r2 > 0) p.infl[obj] += 1;

@@ -54,7 +54,8 @@ SSA_HD double ssa_pow10_infl(int t) {  // t = 0..15  <->  i = -6..9
 // row update scaled by the reciprocal of the pivot).  Returns 1 on success, 0 if a pivot is <= 0
 // or NaN (dpotrf info > 0 -> scipy LinAlgError) or if any entry is non-finite (scipy check_finite
 // -> ValueError); both are swallowed by robust_cholesky's bare except.
-SSA_HD int ssa_chol6(double* a /* 21, in: A, out: U */) {
+template <bool INL>
+SSA_HD int ssa_chol6_t(double* a /* 21, in: A, out: U */) {
   int ok = 1;
 #pragma unroll
   for (int e = 0; e < SSA_NP; ++e) ok &= (ssa_fabs(a[e]) <= 1.79769313486231570815e+308);
@@ -64,9 +65,9 @@ SSA_HD int ssa_chol6(double* a /* 21, in: A, out: U */) {
 #pragma unroll
     for (int k = 0; k < j; ++k) d = ssa_fma(-a[ssa_pidx(k, j)], a[ssa_pidx(k, j)], d);
     ok &= (d > 0.0);
-    const double ujj = ssa_sqrt(d);
+    const double ujj = ssa_sqrt_t<INL>(d);
     a[ssa_pidx(j, j)] = ujj;
-    const double inv = ssa_div(1.0, ujj);
+    const double inv = ssa_div_t<INL>(1.0, ujj);
 #pragma unroll
     for (int c = j + 1; c < 6; ++c) {
       double s = a[ssa_pidx(j, c)];
@@ -78,11 +79,14 @@ SSA_HD int ssa_chol6(double* a /* 21, in: A, out: U */) {
   return ok;
 }
 
+SSA_HD int ssa_chol6(double* a) { return ssa_chol6_t<false>(a); }
+
 // robust_cholesky((lambda+n) * P).  P is read through (ptr, stride) so the caller can keep it in
 // global SoA memory or in shared memory; it is re-read on the (rare) inflation retries instead of
 // being held in registers.  Returns the number of the successful attempt: 0 = plain, t+1 = with
 // +10**(t-6) on the diagonal, -1 = all 17 attempts failed (LinAlgError).
-SSA_HD int ssa_robust_chol6(const double* P, long stride, double lam, double* U) {
+template <bool INL>
+SSA_HD int ssa_robust_chol6_t(const double* P, long stride, double lam, double* U) {
   for (int t = -1; t < 16; ++t) {  // one copy of the factorisation in the instruction stream
 #pragma unroll
     for (int e = 0; e < SSA_NP; ++e) U[e] = ssa_mul(lam, P[e * stride]);
@@ -91,10 +95,11 @@ SSA_HD int ssa_robust_chol6(const double* P, long stride, double lam, double* U)
 #pragma unroll
       for (int j = 0; j < 6; ++j) U[ssa_pidx(j, j)] = U[ssa_pidx(j, j)] + eps;
     }
-    if (ssa_chol6(U)) return t + 1;
+    if (ssa_chol6_t<INL>(U)) return t + 1;
   }
   return -1;
 }
+SSA_HD int ssa_robust_chol6(const double* P, long stride, double lam, double* U) { return ssa_robust_chol6_t<false>(P, stride, lam, U); }
 
 // Sigma point number `k` (0..12), component j, from x and the packed factor.
 // s0 = x ; s_{1+r} = x - (-U[r,:]) = x + U[r,:] ; s_{7+r} = x - U[r,:]
