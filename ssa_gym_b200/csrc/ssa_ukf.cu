@@ -472,7 +472,7 @@ constexpr int kObjThreads = SSA_OBJ_THREADS;  // block size of the per-object ke
 #define SSA_LB_FAC 4
 #endif
 #ifndef SSA_LB_HX
-#define SSA_LB_HX 8
+#define SSA_LB_HX 10
 #endif
 
 // Programmatic dependent launch: the five kernels of a step form a chain on one stream.  Each kernel lets its
