@@ -135,6 +135,13 @@ int ssa_ukf_reset(ssa_ukf* h, const double* x_true, const double* x_filter, cons
 /* per-step host inputs: actions int32[E] and/or z_noise double[N][3] (SS2:219-221 draws them at reset) */
 int ssa_ukf_upload(ssa_ukf* h, int field, const void* host, size_t bytes, void* stream);
 int ssa_ukf_download(ssa_ukf* h, int field, void* host, size_t bytes, void* stream); /* blocks until copied */
+/* Every per-step output in ONE device-to-host copy (the drop-in env reads ~16 arrays after each step, SS2:278-322:
+ * x_true, x_filter, P_filter, obs, delta_pos/vel, sigma_pos/vel, z_true, y, S, sigmas_h, status, visibility).
+ * Layout of `host` (ssa_ukf_snapshot_bytes(h) bytes): double [N][118] = x_true 6 | x_filter 6 | P 36 | obs 12 |
+ * delta_pos, delta_vel, sigma_pos, sigma_vel | z_true 3 | y 3 | S 9 | sigmas_h 39; int32 status [N]; uint8 visible
+ * [N]; uint8 updated [N].  Blocks until copied.                                                                 */
+size_t ssa_ukf_snapshot_bytes(const ssa_ukf* h);
+int ssa_ukf_snapshot(ssa_ukf* h, void* host, size_t bytes, void* stream);
 /* raw device pointer of a field (device SoA layout) for zero-copy consumers (torch, NCCL) */
 int ssa_ukf_device_ptr(ssa_ukf* h, int field, void** dptr, size_t* bytes);
 

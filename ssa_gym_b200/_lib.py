@@ -68,6 +68,8 @@ PROTOTYPES = {
     "ssa_ukf_env_reduce": (_I, [c_void_p, c_void_p, _I, c_void_p]),
     "ssa_ukf_scores": (_I, [c_void_p, c_void_p]),
     "ssa_ukf_diagnostics": (_I, [c_void_p, c_void_p]),
+    "ssa_ukf_snapshot_bytes": (ctypes.c_size_t, [c_void_p]),
+    "ssa_ukf_snapshot": (_I, [c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
     "ssa_orbit_gen_eval": (_I, [c_void_p, _I, c_void_p, _I, _D, c_void_p, c_void_p, _D, _D, _I, _I, c_void_p, c_void_p, c_void_p, _I]),
     "ssa_ukf_sync": (_I, [c_void_p, c_void_p]),
     "ssa_ukf_launch_count": (_L, [c_void_p]),

@@ -1565,6 +1565,42 @@ __global__ void ssa_packed_to_pfull(const double* __restrict__ src, double* __re
   const int i = r < c ? r : c, j = r < c ? c : r;
   dst[t] = src[ssa_pidx(i, j) * ld + n];
 }
+// ssa_ukf_snapshot: every per-step output of the step in the host layout of the reference's history arrays, packed
+// into ONE contiguous block (one thread per object):
+//   doubles [N][118] = x_true 6 | x_filter 6 | P 36 (full, mirrored) | obs 12 | dpos dvel spos svel | z_true 3 | y 3 |
+//                      S 9 | sigmas_h 39          then int32 status [N], uint8 visible [N], uint8 updated [N]
+constexpr int kSnapDoubles = 118;
+struct SnapParams {
+  const double *xt, *x, *P, *obs, *dpos, *dvel, *spos, *svel, *z_true, *y, *S, *sigmas_h;
+  const int32_t* status; const uint8_t *visible, *updated;
+  long ld; int N;
+  double* out;
+};
+__global__ void ssa_snapshot_kernel(const SnapParams p) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  double* o = p.out + n * kSnapDoubles;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { o[i] = p.xt[i * p.ld + n]; o[6 + i] = p.x[i * p.ld + n]; }
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) o[12 + 6 * r + c] = p.P[ssa_pidx(r < c ? r : c, r < c ? c : r) * p.ld + n];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) o[48 + i] = p.obs[n * 12 + i];
+  o[60] = p.dpos[n]; o[61] = p.dvel[n]; o[62] = p.spos[n]; o[63] = p.svel[n];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { o[64 + i] = p.z_true[n * 3 + i]; o[67 + i] = p.y[n * 3 + i]; }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) o[70 + i] = p.S[n * 9 + i];
+  for (int i = 0; i < 39; ++i) o[79 + i] = p.sigmas_h[n * 39 + i];
+  int32_t* st = (int32_t*)(p.out + (long)p.N * kSnapDoubles);
+  st[n] = p.status[n];
+  uint8_t* u8 = (uint8_t*)(st + p.N);
+  u8[n] = p.visible[n];
+  u8[p.N + n] = p.updated[n];
+}
+
 // FP64 pipe microbenchmark: 8 independent DFMA chains per thread.
 __global__ void __launch_bounds__(256) ssa_dfma_peak_kernel(double* out, int iters, double a, double b) {
   double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
@@ -1761,6 +1797,7 @@ struct ssa_ukf {
   int32_t *status, *infl, *actions, *greedy;
   uint8_t *visible, *updated, *innov_flags, *done;
   double* diag;     // [N][2] NEES, NIS of the last ssa_ukf_diagnostics call
+  void* snap;       // device block of ssa_ukf_snapshot (allocated on first use)
   size_t stage_bytes;
 };
 
@@ -1908,6 +1945,7 @@ int ssa_ukf_destroy(ssa_ukf* h) {
     cudaFreeHost(h->ro.hout); cudaFreeHost(h->ro.hin);
     for (int i = 0; i < 2; ++i) if (h->ro.gexec[i]) cudaGraphExecDestroy(h->ro.gexec[i]);
   }
+  cudaFree(h->snap);
   cudaFree(h->stage);
   cudaFree(h->scratch);
   cudaFree(h->status);
@@ -2569,6 +2607,30 @@ int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stre
   ssa_env_reduce_kernel<<<(unsigned)p.E, 128, 0, st>>>(p);
   h->launches++;
   CK(cudaGetLastError());
+  return SSA_OK;
+}
+
+size_t ssa_ukf_snapshot_bytes(const ssa_ukf* h) {
+  return h ? (size_t)h->cfg.n_objects * (kSnapDoubles * sizeof(double) + sizeof(int32_t) + 2) : 0;
+}
+
+int ssa_ukf_snapshot(ssa_ukf* h, void* host, size_t bytes, void* stream) {
+  if (!h || !host) return SSA_EINVAL;
+  const size_t need = ssa_ukf_snapshot_bytes(h);
+  if (bytes != need) { snprintf(g_err, sizeof(g_err), "ssa_ukf_snapshot: got %zu bytes, want %zu", bytes, need); return SSA_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  if (!h->snap) CK(cudaMalloc(&h->snap, need));
+  SnapParams p;
+  p.xt = h->xt; p.x = h->x; p.P = h->P; p.obs = h->obs; p.dpos = h->dpos; p.dvel = h->dvel; p.spos = h->spos; p.svel = h->svel;
+  p.z_true = h->z_true; p.y = h->y; p.S = h->S; p.sigmas_h = h->sigmas_h;
+  p.status = h->status; p.visible = h->visible; p.updated = h->updated;
+  p.ld = h->ld; p.N = h->cfg.n_objects; p.out = (double*)h->snap;
+  ssa_snapshot_kernel<<<(unsigned)((p.N + 127) / 128), 128, 0, st>>>(p);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(host, h->snap, need, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return SSA_OK;
 }
 

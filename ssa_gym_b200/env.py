@@ -171,14 +171,16 @@ class SSA_Tasker_Env(Env):
         return self.obs[0]
 
     def _pull(self, i):
-        d = self.ukf.download
-        self.x_true[i] = d(F.F_X_TRUE)
-        self.x_filter[i] = d(F.F_X_FILTER)
-        self.P_filter[i] = d(F.F_P_FILTER)
-        self.obs[i] = d(F.F_OBS)
-        self.delta_pos[i], self.delta_vel[i] = d(F.F_DELTA_POS), d(F.F_DELTA_VEL)
-        self.sigma_pos[i], self.sigma_vel[i] = d(F.F_SIGMA_POS), d(F.F_SIGMA_VEL)
-        self._visible_now = d(F.F_VISIBLE).astype(bool)
+        """All history rows of step i in one device-to-host copy (ssa_ukf_snapshot)."""
+        v = self.ukf.snapshot()
+        self.x_true[i] = v["x_true"]
+        self.x_filter[i] = v["x_filter"]
+        self.P_filter[i] = v["P_filter"]
+        self.obs[i] = v["obs"]
+        self.delta_pos[i], self.delta_vel[i] = v["delta_pos"], v["delta_vel"]
+        self.sigma_pos[i], self.sigma_vel[i] = v["sigma_pos"], v["sigma_vel"]
+        self._visible_now = v["visible"].astype(bool)
+        return v
 
     def step(self, a):
         step_s = time.time()
@@ -194,19 +196,19 @@ class SSA_Tasker_Env(Env):
         self.ukf.upload(F.F_ACTIONS, np.array([a], dtype=np.int32))
         self.ukf.upload(F.F_Z_NOISE, self.z_noise[i])
         self.ukf.step(self.trans_matrix[i], flags)
-        self._pull(i)
-        status = self.ukf.download(F.F_STATUS)
+        snap = self._pull(i)
+        status = snap["status"].copy()
         self.runtime['perform predictions'] += time.time() - s
         if np.any(status & F.ST_TRUTHEXC):
             # the reference propagates an uncaught numba exception out of step() here (SS2:266)
             raise ArithmeticError("fx raised while propagating a true state")
         if do_update and not (a in self.failed_filters_id):
             if not (status[a] & F.ST_FAILED) or (status[a] & F.ST_IN_UPDATE):
-                self.z_true[i, a] = self.ukf.download(F.F_Z_TRUE)[a]
-            if self.ukf.download(F.F_UPDATED)[a]:
-                self.y[i, a] = self.ukf.download(F.F_Y)[a]
-                self.S[i, a] = self.ukf.download(F.F_S)[a]
-                self.sigmas_h[i] = self.ukf.download(F.F_SIGMAS_H)[a]
+                self.z_true[i, a] = snap["z_true"][a]
+            if snap["updated"][a]:
+                self.y[i, a] = snap["y"][a]
+                self.S[i, a] = snap["S"][a]
+                self.sigmas_h[i] = snap["sigmas_h"][a]
                 self.obs_taken[i] = True
         for j in np.where(status & F.ST_FAILED)[0]:
             if j not in self.failed_filters_id:

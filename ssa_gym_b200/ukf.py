@@ -268,6 +268,24 @@ class BatchedUKF:
         _lib.check(self.lib.ssa_ukf_scores(self.h, stream), "ssa_ukf_scores")
         return self.download(_lib.F_SCORES, stream=stream)
 
+    def snapshot(self, stream=None):
+        """Every per-step output of the last step in one device-to-host copy; returns a dict of numpy views into a
+        host block that the next snapshot() overwrites."""
+        if getattr(self, "_snap", None) is None:
+            N = self.N
+            nbytes = int(self.lib.ssa_ukf_snapshot_bytes(self.h))
+            buf = np.empty(nbytes, dtype=np.uint8)
+            d = buf[:N * 118 * 8].view(np.float64).reshape(N, 118)
+            st = buf[N * 118 * 8:N * 118 * 8 + 4 * N].view(np.int32)
+            u8 = buf[N * 118 * 8 + 4 * N:]
+            self._snap = (buf, {"x_true": d[:, 0:6], "x_filter": d[:, 6:12], "P_filter": d[:, 12:48].reshape(N, 6, 6),
+                                "obs": d[:, 48:60], "delta_pos": d[:, 60], "delta_vel": d[:, 61], "sigma_pos": d[:, 62],
+                                "sigma_vel": d[:, 63], "z_true": d[:, 64:67], "y": d[:, 67:70], "S": d[:, 70:79].reshape(N, 3, 3),
+                                "sigmas_h": d[:, 79:118].reshape(N, 13, 3), "status": st, "visible": u8[:N], "updated": u8[N:]})
+        buf, views = self._snap
+        _lib.check(self.lib.ssa_ukf_snapshot(self.h, _ptr(buf), buf.nbytes, stream), "ssa_ukf_snapshot")
+        return views
+
     def diagnostics(self, stream=None):
         """Consistency diagnostics of the current state: (nees [N], nis [N] (NaN where not updated), flags uint8 [N]:
         0x80 valid | bit a: |y_a| < sqrt(S_aa) | bit 3+a: |y_a| < 2 sqrt(S_aa)).  NIS / flags need SSA_STEP_RECORD."""

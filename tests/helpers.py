@@ -303,6 +303,14 @@ class TwinBackedUKF:
              F.F_UPDATED: st.updated, F.F_STATUS: st.status, F.F_INFLATIONS: st.infl}
         return m[field].copy()
 
+    def snapshot(self, stream=None):
+        st = self.st
+        return {"x_true": st.x_true.copy(), "x_filter": st.x.copy(), "P_filter": st.P.copy(), "obs": st.obs.copy(),
+                "delta_pos": st.dpos.copy(), "delta_vel": st.dvel.copy(), "sigma_pos": st.spos.copy(),
+                "sigma_vel": st.svel.copy(), "z_true": st.z_true.copy(), "y": st.y.copy(), "S": st.S.copy(),
+                "sigmas_h": st.sigmas_h.copy(), "status": st.status.copy(), "visible": st.visible.copy(),
+                "updated": st.updated.copy()}
+
     def sync(self, stream=None):
         pass
 

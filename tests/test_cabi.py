@@ -13,7 +13,7 @@ from ssa_gym_b200 import _build, _lib
 def header_functions():
     src = open(os.path.join(H.ROOT, "include", "ssa_ukf.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"\b(?:int|long|const char\*)\s+\*?\s*(ssa_[a-z0-9_]+)\s*\(", src)
+    names = re.findall(r"\b(?:int|long|size_t|const char\*)\s+\*?\s*(ssa_[a-z0-9_]+)\s*\(", src)
     return sorted(set(names))
 
 
