@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c3"])
     ap.add_argument("--envs", type=int, default=4096, help="c3: parallel environments per GPU")
+    ap.add_argument("--gather", action="store_true", help="c3, N>1: also all_gather rewards and observations over NCCL every step (a learner on one device)")
     ap.add_argument("--rng", default="device", choices=["device", "host"], help="c3: episodic RNG mode of VecSSATaskerEnv")
     ap.add_argument("--objects", type=int, default=0, help="override objects per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -248,6 +249,13 @@ def run_c3(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1: what a learner on one device needs - per-env rewards and observations of every rank, gathered
+    # with one NCCL all_gather each from the episodic mode's device output block, asynchronously every step
+    rew_view = env.ukf.torch_view(F.F_ROLLOUT_REWARD) if (world > 1 and a.rng == "device" and a.gather) else None
+    obs_view = env.ukf.torch_view(F.F_ROLLOUT_OBS) if rew_view is not None else None
+    g_rew = torch.zeros(world * E, dtype=torch.float64, device="cuda") if rew_view is not None else None
+    g_obs = torch.zeros((world * E * m, 12), dtype=torch.float64, device="cuda") if rew_view is not None else None
+    works = []
     n_done = 0
     for w in range(max(a.warmup, 3)):
         _, _, d, _ = env.vector_step(env.greedy_actions())
@@ -262,6 +270,11 @@ def run_c3(a):
     for s in range(a.steps):
         obs, r, d, _ = env.vector_step(env.greedy_actions())
         n_done += int(d.sum())
+        if rew_view is not None:
+            works.append(dist.all_gather_into_tensor(g_rew, rew_view, async_op=True))
+            works.append(dist.all_gather_into_tensor(g_obs, obs_view, async_op=True))
+    for w_ in works:
+        w_.wait()
     e1.record(stream)
     barrier()
     t_wall = time.perf_counter() - tw0
@@ -291,6 +304,9 @@ def run_c3(a):
                                      "PCIe bound, not FP64 bound"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "extra": {"episodes_finished_in_timed_region": n_done, "construct_and_first_reset_s": t_construct,
+                          "nccl_gather_per_step": (None if rew_view is None else
+                                                   {"reward_bytes_per_rank": 8 * E, "obs_bytes_per_rank": 96 * E * m,
+                                                    "gathered_reward_matches_rank0": bool(np.array_equal(g_rew[:E].cpu().numpy(), r))}),
                           "wall_s_timed_region": t_wall}}
         print(json.dumps(line))
     if world > 1:
@@ -307,7 +323,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_obj = a.objects or (20000 if a.workload == "c2" else 1_000_000 // max(world, 1))
     wl_name = ("C2: 20000-orbit catalog per GPU, UKF predict+update of every object per step" if a.workload == "c2"
-               else f"C4: 1M-object catalog sharded over {world} GPU(s), {n_obj} objects per rank")
+               else f"C4: 1M-object catalog sharded over {world} GPU(s), {n_obj} objects per rank, per-step UKF + shard reward "
+                    f"terms + NCCL all_gather of them")
     config = {"workload": wl_name, "objects_per_gpu": n_obj, "dt_s": 20.0, "obs_type": "aer",
               "sigma_points": "merwe alpha=1e-4 beta=2 kappa=-3", "trans_matrix": "SOFA Cel2Ter06aXY (tests.py:107-109)",
               "l2": "flushed between timed steps (256 MiB write)"}
@@ -371,6 +388,23 @@ def main():
     torch.cuda.synchronize()
     peak_tf = fp64_peak_tflops(local_rank, sp)
 
+    # C4 (BASELINE.json config 4: "per-step UKF + reward, NCCL gather of rewards"): every step also reduces the shard's
+    # reward terms on the device (ssa_ukf_catalog_stats) and all-gathers the 5 doubles per rank over NCCL,
+    # asynchronously (the next step does not wait for it); the gathered values are checked after the timed region.
+    c4_gather = (a.workload == "c4")
+    gathered, works = None, []
+    if c4_gather:
+        ukf.catalog_stats(index_offset=rank * n_obj, stream=sp)
+        stats_view = ukf.torch_view(F.F_CATALOG_STATS)
+        gathered = torch.zeros(world * 5, dtype=torch.float64, device="cuda")
+
+    def reward_gather():
+        ukf.catalog_stats(index_offset=rank * n_obj, stream=sp)
+        if world > 1:
+            works.append(dist.all_gather_into_tensor(gathered, stats_view, async_op=True))
+        else:
+            gathered.copy_(stats_view, non_blocking=True)
+
     # ---- timed: exactly K steps, per-step CUDA events on the launching stream, L2 flushed between steps ---
     sampler = ClockSampler(local_rank)
     launches0 = ukf.launch_count
@@ -384,8 +418,12 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         ukf.step(M, flags, stream=sp)
+        if c4_gather:
+            reward_gather()
         e1.record(stream)
         evs.append((e0, e1))
+    for w_ in works:
+        w_.wait()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
@@ -393,6 +431,16 @@ def main():
     launches = ukf.launch_count - launches0
     status = ukf.download(F.F_STATUS)
     n_failed = int((status & 1).sum())
+    c4_check = None
+    if c4_gather:  # the gathered shard terms of the LAST timed step against a host recomputation of this rank's shard
+        g = gathered.cpu().numpy().reshape(world, 5)
+        dpos_h, tr_h = ukf.download(F.F_DELTA_POS), ukf.download(F.F_TRACE)
+        mine = g[rank]
+        assert mine[0] == dpos_h.max() and mine[2] == n_obj and mine[3] == tr_h.max() and mine[4] == rank * n_obj + int(np.argmax(tr_h))
+        assert mine[1] == float(((dpos_h < 1e4).astype(int) + (dpos_h < 1e7).astype(int)).sum())
+        best = int(np.argmax(g[:, 3]))
+        c4_check = {"max_delta_pos_m": float(g[:, 0].max()), "trinary_reward": float(g[:, 1].sum() / g[:, 2].sum() / 2),
+                    "argmax_trace_object": int(g[best, 4]), "gathered_ranks": int(world)}
 
     # per-kernel durations of the step (CUDA events between the launches, L2 flushed before each step)
     kms = []
@@ -508,7 +556,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "extra": {"ms_per_step_back_to_back_no_flush": b2b_ms, "wall_s_timed_region": t_wall, "failed_filters": n_failed,
-                      "ms_per_step_of_each_rank": per_rank,
+                      "ms_per_step_of_each_rank": per_rank, "c4_reward_gather": c4_check,
                       "step_ms_min": float(np.min(step_ms)), "step_ms_max": float(np.max(step_ms))},
         }
         if not a.no_cpu_baseline:

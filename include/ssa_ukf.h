@@ -98,6 +98,9 @@ enum ssa_field {
   SSA_F_UPDATED = 22, SSA_F_TRANS_ENV = 23, SSA_F_STEP_INDEX = 24, SSA_F_ENV_STATS = 25,
   SSA_F_DIAG = 26,        /* double [N][2]: NEES, NIS (NaN where the object was not updated) - ssa_ukf_diagnostics */
   SSA_F_INNOV_FLAGS = 27, /* uint8 [N]: 0x80 valid | bit a: |y_a| < sqrt(S_aa) | bit 3+a: |y_a| < 2 sqrt(S_aa) */
+  SSA_F_CATALOG_STATS = 28, /* double [5]: max delta_pos, sum of trinary counts, objects, max trace P, its index */
+  SSA_F_ROLLOUT_OBS = 29,   /* device views of the episodic mode's output block: obs [N][12] ...              */
+  SSA_F_ROLLOUT_REWARD = 30, /* ... and reward [E] (for an NCCL gather onto a learner's device)                 */
   SSA_F_COUNT_
 };
 
@@ -221,6 +224,11 @@ int ssa_ukf_scores(ssa_ukf* h, void* stream);
 int ssa_orbit_gen_eval(const double* cand, int K, const double* trans_table, int n, double step_s, const double obs_itrs[3],
                        const double T[9], double obs_limit, double min_alt, int first_window, int max_gap, uint8_t* accept,
                        double* elev, double* alt, int device);
+/* Catalog mode (C4: one shard of a large catalog per GPU): the shard's reward terms over ALL its objects, left in
+ * device memory (SSA_F_CATALOG_STATS, 5 doubles) so that the shards can be combined with one small all_gather:
+ * max delta_pos (SS2:329-331), sum of the trinary counts (results.py:431-433) and the object count, the largest
+ * trace P and its index + index_offset (agents.py:8, first maximum wins).                                        */
+int ssa_ukf_catalog_stats(ssa_ukf* h, long index_offset, void* stream);
 /* Consistency diagnostics of the current state: per object NEES = (x_true - x)^T P^-1 (x_true - x)
  * (SS2:436-446 anees), and for the objects updated by the last step run with SSA_STEP_RECORD the NIS
  * y^T S^-1 y (SS2:564-569) and the innovation-bound flags (SS2:598-604) -> SSA_F_DIAG, SSA_F_INNOV_FLAGS.      */

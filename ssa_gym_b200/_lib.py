@@ -23,7 +23,8 @@ TASKER_NAIVE_GREEDY, TASKER_VISIBLE_GREEDY, TASKER_POS_ERROR_GREEDY, TASKER_VEL_
 
 (F_X_TRUE, F_X_FILTER, F_P_FILTER, F_OBS, F_DELTA_POS, F_DELTA_VEL, F_SIGMA_POS, F_SIGMA_VEL, F_TRACE,
  F_Z_TRUE, F_Y, F_S, F_SIGMAS_H, F_Z_NOISE, F_VISIBLE, F_STATUS, F_INFLATIONS, F_ACTIONS, F_REWARD, F_DONE,
- F_GREEDY, F_SCORES, F_UPDATED, F_TRANS_ENV, F_STEP_INDEX, F_ENV_STATS, F_DIAG, F_INNOV_FLAGS) = range(28)
+ F_GREEDY, F_SCORES, F_UPDATED, F_TRANS_ENV, F_STEP_INDEX, F_ENV_STATS, F_DIAG, F_INNOV_FLAGS, F_CATALOG_STATS,
+ F_ROLLOUT_OBS, F_ROLLOUT_REWARD) = range(31)
 
 
 class SsaUkfCfg(ctypes.Structure):
@@ -68,6 +69,7 @@ PROTOTYPES = {
     "ssa_ukf_env_reduce": (_I, [c_void_p, c_void_p, _I, c_void_p]),
     "ssa_ukf_scores": (_I, [c_void_p, c_void_p]),
     "ssa_ukf_diagnostics": (_I, [c_void_p, c_void_p]),
+    "ssa_ukf_catalog_stats": (_I, [c_void_p, _L, c_void_p]),
     "ssa_ukf_snapshot_bytes": (ctypes.c_size_t, [c_void_p]),
     "ssa_ukf_snapshot": (_I, [c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
     "ssa_orbit_gen_eval": (_I, [c_void_p, _I, c_void_p, _I, _D, c_void_p, c_void_p, _D, _D, _I, _I, c_void_p, c_void_p, c_void_p, _I]),

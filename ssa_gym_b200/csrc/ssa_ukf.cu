@@ -1494,6 +1494,57 @@ __global__ void ssa_orbit_accept_kernel(const uint8_t* __restrict__ flags, int K
   accept[c] = (uint8_t)ok;
 }
 
+// ---- catalog mode (C4): per-shard reward terms over ALL objects of the handle ----------------------------------------
+// {max delta_pos, sum of trinary counts (results.py:431-433), number of objects, max trace P, its index (first maximum
+// wins, np.argmax)} -> 5 doubles, reduced in two deterministic stages (per-block partials, then one block).
+constexpr int kStatBlocks = 296;
+struct CatPart { double max_dpos; double max_trace; long arg_trace; long tri; };
+__device__ __forceinline__ CatPart cat_merge(CatPart a, CatPart b) {
+  CatPart r;
+  r.max_dpos = b.max_dpos > a.max_dpos ? b.max_dpos : a.max_dpos;
+  const bool takeb = b.arg_trace >= 0 && (a.arg_trace < 0 || b.max_trace > a.max_trace || (b.max_trace == a.max_trace && b.arg_trace < a.arg_trace));
+  r.max_trace = takeb ? b.max_trace : a.max_trace;
+  r.arg_trace = takeb ? b.arg_trace : a.arg_trace;
+  r.tri = a.tri + b.tri;
+  return r;
+}
+__device__ __forceinline__ CatPart cat_block_reduce(CatPart v) {
+  __shared__ CatPart sm[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    CatPart w;
+    w.max_dpos = __shfl_xor_sync(0xffffffffu, v.max_dpos, o);
+    w.max_trace = __shfl_xor_sync(0xffffffffu, v.max_trace, o);
+    w.arg_trace = __shfl_xor_sync(0xffffffffu, v.arg_trace, o);
+    w.tri = __shfl_xor_sync(0xffffffffu, v.tri, o);
+    v = cat_merge(v, w);
+  }
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = cat_merge(v, sm[w]);
+  return v;
+}
+__global__ void __launch_bounds__(256) ssa_cat_stats_stage1(const double* __restrict__ dpos, const double* __restrict__ trace, long N,
+                                                            CatPart* part) {
+  CatPart v{-1.0, 0.0, -1, 0};
+  for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long)gridDim.x * blockDim.x) {
+    const double d = dpos[n];
+    CatPart w{d, trace[n], n, (long)((d < 1e4) + (d < 1e7))};
+    v = cat_merge(v, w);
+  }
+  v = cat_block_reduce(v);
+  if (threadIdx.x == 0) part[blockIdx.x] = v;
+}
+__global__ void __launch_bounds__(256) ssa_cat_stats_stage2(const CatPart* __restrict__ part, int nparts, long N, long index_offset,
+                                                            double* out) {
+  CatPart v{-1.0, 0.0, -1, 0};
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) v = cat_merge(v, part[i]);
+  v = cat_block_reduce(v);
+  if (threadIdx.x == 0) {
+    out[0] = v.max_dpos; out[1] = (double)v.tri; out[2] = (double)N; out[3] = v.max_trace; out[4] = (double)(v.arg_trace + index_offset);
+  }
+}
+
 // reward.py:6-50 score terms, one thread per object
 __global__ void ssa_scores_kernel(const double* __restrict__ P, const double* __restrict__ dpos, double* out, long ld,
                                   int N, double dt) {
@@ -1798,6 +1849,7 @@ struct ssa_ukf {
   uint8_t *visible, *updated, *innov_flags, *done;
   double* diag;     // [N][2] NEES, NIS of the last ssa_ukf_diagnostics call
   void* snap;       // device block of ssa_ukf_snapshot (allocated on first use)
+  void* cat_part; double* cat_stats;  // ssa_ukf_catalog_stats: per-block partials, result [5]
   size_t stage_bytes;
 };
 
@@ -1946,6 +1998,7 @@ int ssa_ukf_destroy(ssa_ukf* h) {
     for (int i = 0; i < 2; ++i) if (h->ro.gexec[i]) cudaGraphExecDestroy(h->ro.gexec[i]);
   }
   cudaFree(h->snap);
+  cudaFree(h->cat_part);
   cudaFree(h->stage);
   cudaFree(h->scratch);
   cudaFree(h->status);
@@ -2021,6 +2074,15 @@ static int field_info(ssa_ukf* h, int field, void** p, size_t* bytes, int* soa_c
     case SSA_F_STEP_INDEX: *p = h->step_idx; *bytes = E * 4; break;
     case SSA_F_ENV_STATS: *p = h->env_stats; *bytes = E * 4 * 8; break;
     case SSA_F_DIAG: *p = h->diag; *bytes = N * 2 * 8; break;
+    case SSA_F_CATALOG_STATS:
+      if (!h->cat_stats) { snprintf(g_err, sizeof(g_err), "call ssa_ukf_catalog_stats first"); return SSA_EINVAL; }
+      *p = h->cat_stats; *bytes = 5 * 8; break;
+    case SSA_F_ROLLOUT_OBS:
+      if (!h->ro.init) { snprintf(g_err, sizeof(g_err), "episodic mode not configured"); return SSA_EINVAL; }
+      *p = h->ro.dout; *bytes = N * 12 * 8; break;
+    case SSA_F_ROLLOUT_REWARD:
+      if (!h->ro.init) { snprintf(g_err, sizeof(g_err), "episodic mode not configured"); return SSA_EINVAL; }
+      *p = h->ro.dout + 12 * N; *bytes = E * 8; break;
     case SSA_F_INNOV_FLAGS: *p = h->innov_flags; *bytes = N; break;
     default: snprintf(g_err, sizeof(g_err), "unknown field %d", field); return SSA_EINVAL;
   }
@@ -2631,6 +2693,24 @@ int ssa_ukf_snapshot(ssa_ukf* h, void* host, size_t bytes, void* stream) {
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(host, h->snap, need, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return SSA_OK;
+}
+
+int ssa_ukf_catalog_stats(ssa_ukf* h, long index_offset, void* stream) {
+  if (!h) return SSA_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(h->device));
+  if (!h->cat_part) {
+    CK(cudaMalloc(&h->cat_part, sizeof(CatPart) * kStatBlocks + 8 * sizeof(double)));
+    h->cat_stats = (double*)((CatPart*)h->cat_part + kStatBlocks);
+  }
+  const long N = h->cfg.n_objects;
+  int nb = (int)((N + 255) / 256);
+  nb = nb > kStatBlocks ? kStatBlocks : nb;
+  ssa_cat_stats_stage1<<<nb, 256, 0, st>>>(h->dpos, h->trace, N, (CatPart*)h->cat_part);
+  ssa_cat_stats_stage2<<<1, 256, 0, st>>>((const CatPart*)h->cat_part, nb, N, index_offset, h->cat_stats);
+  h->launches += 2;
+  CK(cudaGetLastError());
   return SSA_OK;
 }
 

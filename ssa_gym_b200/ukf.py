@@ -102,6 +102,8 @@ class BatchedUKF:
             _lib.F_SCORES: ((self.N, 6), np.float64), _lib.F_TRANS_ENV: ((self.n_envs, 3, 3), np.float64),
             _lib.F_STEP_INDEX: ((self.n_envs,), np.int32), _lib.F_ENV_STATS: ((self.n_envs, 4), np.float64),
             _lib.F_DIAG: ((self.N, 2), np.float64), _lib.F_INNOV_FLAGS: ((self.N,), np.uint8),
+            _lib.F_CATALOG_STATS: ((5,), np.float64), _lib.F_ROLLOUT_OBS: ((self.N, 12), np.float64),
+            _lib.F_ROLLOUT_REWARD: ((self.n_envs,), np.float64),
         }
 
     # -- lifetime ---------------------------------------------------------------------------------
@@ -285,6 +287,11 @@ class BatchedUKF:
         buf, views = self._snap
         _lib.check(self.lib.ssa_ukf_snapshot(self.h, _ptr(buf), buf.nbytes, stream), "ssa_ukf_snapshot")
         return views
+
+    def catalog_stats(self, index_offset=0, stream=None):
+        """Catalog mode: reduce this shard's reward terms on the device (SSA_F_CATALOG_STATS: max delta_pos, trinary
+        count sum, objects, max trace, global index of it); asynchronous, read with download / torch_view."""
+        _lib.check(self.lib.ssa_ukf_catalog_stats(self.h, int(index_offset), stream), "ssa_ukf_catalog_stats")
 
     def diagnostics(self, stream=None):
         """Consistency diagnostics of the current state: (nees [N], nis [N] (NaN where not updated), flags uint8 [N]:

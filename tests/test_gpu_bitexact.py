@@ -315,3 +315,26 @@ def test_diagnostics_kernel_equals_twin():
     assert st.updated.sum() > 0 and (st.updated == 0).sum() > 0
     assert H.bits_equal(nees_g, nees) and H.bits_equal(nis_g, nis) and np.array_equal(fl_g, fl)
     ukf.close()
+
+
+def test_catalog_stats_reduction_exact():
+    """ssa_ukf_catalog_stats (C4 reward terms of a shard: max delta_pos, trinary count sum, argmax trace with
+    first-maximum-wins and a global index offset) against numpy on the downloaded arrays: integer and max work, exact."""
+    N, steps = 70001, 2
+    cat, x, P0, zn = H.c2_inputs(20000, steps)
+    from ssa_gym_b200.catalog import tiled_catalog
+    cat = tiled_catalog(N, cat, seed=5)
+    x = cat + np.random.RandomState(0).normal(size=(N, 6)) * np.array([1e5] * 3 + [1e2] * 3)
+    zn = np.random.RandomState(1).normal(size=(steps, N, 3)) * np.array([H.arcsec2rad, H.arcsec2rad, 1e3])
+    ukf = _gpu_run({}, cat, x, P0, zn, [FULL] * steps)
+    ukf.catalog_stats(index_offset=1000000)
+    got = ukf.download(F.F_CATALOG_STATS)
+    dpos, tr = ukf.download(F.F_DELTA_POS), ukf.download(F.F_TRACE)
+    assert got[0] == dpos.max() and got[1] == float(((dpos < 1e4).astype(int) + (dpos < 1e7).astype(int)).sum())
+    assert got[2] == N and got[3] == tr.max() and got[4] == 1000000 + int(np.argmax(tr))
+    # ties: first maximum wins
+    tv = ukf.torch_view(F.F_TRACE)
+    tv[123] = tv[60000] = float(tr.max()) * 2
+    ukf.catalog_stats(index_offset=0)
+    assert ukf.download(F.F_CATALOG_STATS)[4] == 123
+    ukf.close()
