@@ -338,3 +338,33 @@ def test_catalog_stats_reduction_exact():
     ukf.catalog_stats(index_offset=0)
     assert ukf.download(F.F_CATALOG_STATS)[4] == 123
     ukf.close()
+
+
+@pytest.mark.parametrize("graph", ["1", "0"])
+def test_step_graph_cache_many_flag_combinations(graph, monkeypatch):
+    """ssa_ukf_step replays the kernel chain as a cached CUDA graph per flag combination (4 slots, the k_hx node
+    re-parameterised with every step's trans_matrix).  Seven different flag combinations interleaved (evictions), a
+    different trans_matrix every step: bit-exact against the twin, and identical with plain launches (graph=0)."""
+    monkeypatch.setenv("SSA_UKF_STEP_GRAPH", graph)
+    N = 2500
+    combos = [FULL, F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_EPILOGUE, F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE,
+              F.STEP_UPDATE_ALL | F.STEP_EPILOGUE, F.STEP_TRUTH | F.STEP_EPILOGUE, F.STEP_EPILOGUE,
+              F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE | F.STEP_RECORD]
+    seq = [combos[i % len(combos)] for i in range(16)] + [FULL, combos[1], FULL]
+    cat, x, P0, zn = H.c2_inputs(N, len(seq))
+    cfg = H.make_cfg(N, obs_limit_deg=10.0)
+    Ms = [H.CEL2TER06AXY @ _rotz(2e-3 * s) for s in range(len(seq))]
+    ukf = BatchedUKF(n_envs=1, m=N, dt=20.0, Q=np.array(cfg.Q).reshape(6, 6), R=np.array(cfg.R).reshape(3, 3),
+                     obs_lla=[np.radians(H.OBSERVER_DEG[0]), np.radians(H.OBSERVER_DEG[1]), H.OBSERVER_DEG[2]],
+                     obs_limit_rad=np.radians(10.0))
+    ukf.reset(cat, x, P0)
+    st = H.HostState(cat, x, P0)
+    for s, flags in enumerate(seq):
+        ukf.upload(F.F_Z_NOISE, zn[s])
+        ukf.step(Ms[s], flags)
+        H.cpu_step("twin", cfg, st, Ms[s], flags, z_noise=zn[s])
+        if s % 5 == 4 or s == len(seq) - 1:
+            assert H.bits_equal(ukf.download(F.F_OBS), st.obs) and H.bits_equal(ukf.download(F.F_X_TRUE), st.x_true), s
+            assert np.array_equal(ukf.download(F.F_VISIBLE), st.visible) and np.array_equal(ukf.download(F.F_STATUS), st.status), s
+    _compare_all(ukf, st)
+    ukf.close()
