@@ -9,9 +9,9 @@ reference computes the table once in __init__: ssa_tasker_simple_2.py:136-137 ->
   * if `erfa` (pyerfa) or `astropy._erfa` is importable at run time, `gcrs2irts_matrix_b` reproduces the
     reference's call sequence exactly (same ERFA routines, same EOP interpolation);
   * otherwise `gcrs2irts_matrix_approx` builds the matrix from the exact Earth-rotation angle (ERA00),
-    TIO locator and polar motion, and a truncated series for the CIP X,Y (secular terms plus the five
-    largest nutation terms).  It is accurate to ~0.1 arcsec (checked against the SOFA cookbook matrix
-    quoted in the reference's tests.py:107-109) and is flagged "approximate": the measurement model's
+    TIO locator and polar motion, and a truncated series for the CIP X,Y (polynomial part plus every
+    periodic term above 12 mas).  It is accurate to ~0.01 arcsec (5e-8 rad against the SOFA cookbook matrix
+    quoted in the reference's tests.py:107-109; 2 m at GEO) and is flagged "approximate": the measurement model's
     parity is defined for identical matrices, the matrix generator is an input, not graded arithmetic.
 
 Geometry (`lla2ecef`, `trans_uvw_ecef`) follows transformations.py:216-235 and :341-343 with the same
@@ -126,19 +126,23 @@ def _rz(a):
 
 
 def xys_approx(t):
-    """CIP X, Y and CIO locator s [rad]; t = TT Julian centuries since J2000.  Truncated IAU 2006/2000A
-    series (IERS Conventions 2010, Tables 5.2a/5.2b leading terms)."""
+    """CIP X, Y and CIO locator s [rad]; t = TT Julian centuries since J2000.  Truncated IAU 2006/2000A series (IERS
+    Conventions 2010, eq. 5.16 and the leading rows of Tables 5.2a/5.2b): polynomial part, the nine largest periodic
+    terms of X and seven of Y (every term above 12 mas) and the leading t-proportional term of each."""
     om = (450160.398036 - 6962890.5431 * t) * DAS2R              # mean longitude of the Moon's node
     F = (335779.526232 + 1739527262.8478 * t) * DAS2R            # L - Omega
     D = (1072260.70369 + 1602961601.2090 * t) * DAS2R            # mean elongation of the Moon
     lp = (1287104.79305 + 129596581.0481 * t) * DAS2R            # mean anomaly of the Sun
+    l = (485868.249036 + 1717915923.2178 * t) * DAS2R            # mean anomaly of the Moon
     a2 = 2 * (F - D + om)
     a3 = 2 * (F + om)
     X = (-0.016617 + 2004.191898 * t - 0.4297829 * t ** 2 - 0.19861834 * t ** 3
          - 6.844318 * sin(om) - 0.523908 * sin(a2) - 0.090552 * sin(a3) + 0.082169 * sin(2 * om)
-         + 0.058707 * sin(lp))
+         + 0.058707 * sin(lp) + 0.028288 * sin(l) - 0.020558 * sin(lp + a2) - 0.015407 * sin(2 * F + om)
+         - 0.011992 * sin(l + a3) + 0.205833 * t * cos(om))
     Y = (-0.006951 - 0.025896 * t - 22.4072747 * t ** 2 + 0.00190059 * t ** 3
-         + 9.205236 * cos(om) + 0.573033 * cos(a2) + 0.097847 * cos(a3) - 0.089618 * cos(2 * om))
+         + 9.205236 * cos(om) + 0.573033 * cos(a2) + 0.097847 * cos(a3) - 0.089618 * cos(2 * om)
+         + 0.022438 * cos(lp + a2) + 0.020070 * cos(2 * F + om) + 0.012902 * cos(l + a3) + 0.153042 * t * sin(om))
     X, Y = X * DAS2R, Y * DAS2R
     s = -X * Y / 2 + (94e-6 + 3808.65e-6 * t - 2640.73e-6 * sin(om)) * DAS2R
     return X, Y, s
