@@ -2,9 +2,12 @@
 //
 // Two device implementations of the step live here, both bit-identical to the host twin
 // (tests/twin/twin.cpp):
-//  * the SPLIT PIPELINE (default): five launches per step — k_factor, k_fx, k_ut, k_hx, k_update — one thread per
-//    object for the small linear algebra, one thread per (sigma point, object) for the propagation `fx` and the
-//    measurement `hx` (>85 % of the fp64 work), objects fastest-varying so every access is coalesced;
+//  * the SPLIT PIPELINE (default): five kernels per step — k_factor, k_fx, k_ut, k_hx, k_update(_staged) — one
+//    thread per object for the small linear algebra, one thread per (sigma point, object) for the propagation `fx`
+//    and the measurement `hx` (>85 % of the fp64 work), objects fastest-varying so every access is coalesced; the
+//    update stages its operand tile with 2-D TMA loads (cp.async.bulk.tensor + mbarrier), the chain is linked by
+//    programmatic dependent launch (griddepcontrol) and replayed as a CUDA graph (ssa_ukf_step, _step_pinned,
+//    _rollout_step);
 //  * the TEAM KERNEL ssa_step_kernel (SSA_UKF_KERNEL=team): one launch, one object per 16-lane team (lanes 0..12
 //    own the sigma points, lane 13 the TRUE state), sigma set staged in a 1.7 KB shared-memory workspace per
 //    team, Cholesky / 3x3 inverse evaluated redundantly per lane.
@@ -13,6 +16,10 @@
 // HBM layout: struct-of-arrays fp64, leading dimension ld = N rounded up to 32:
 //   xt[6][ld]  x[6][ld]  P[21][ld] (packed upper triangle)  + per-object scalars [ld]
 // AoS only where the reference's own array layout is the interface (obs[N][12], z_noise[N][3], ...).
+//
+// Also here: the device-resident episodic mode (k_env_reset / k_env_begin: vectorised reset and on-the-fly noise with
+// the counter-based generator of ssa_rng.h), the per-env and per-shard reward reductions, consistency diagnostics,
+// the single-copy snapshot of the drop-in env's histories and the catalog generator's acceptance kernels.
 //
 // No tensor cores: nothing here is a dense contraction (13-term sums of 6x6 outer products).
 // No libdevice transcendental, no implicit FMA contraction (compiled with -fmad=false, every FMA is
