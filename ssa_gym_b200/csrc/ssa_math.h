@@ -65,7 +65,7 @@
   X(QS2, 2.02094576023350569471e+00) X(QS1, -2.40339491173441421878e+00)                               \
   X(PIO4_HI, 7.85398163397448278999e-01) X(ONE, 1.0)                                                   \
   X(MU, 398600441800000.0) X(MU_INV, 1.0 / 398600441800000.0)                                          \
-  X(TOL8, 1e-8) X(TOL12, 1e-12) X(NEWTON_TOL, 1.48e-08) X(P2_52, 4503599627370496.0) X(DELTA99, 1.0 - 1e-2)                        \
+  X(TOL8, 1e-8) X(TOL12, 1e-12) X(HYP101, 1.0 + 1e-2) X(NEWTON_TOL, 1.48e-08) X(P2_52, 4503599627370496.0) X(DELTA99, 1.0 - 1e-2)                        \
   X(INV_TWOPI, 1.0 / 6.28318530717958623200e+00)
 
 enum {

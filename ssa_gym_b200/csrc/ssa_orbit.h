@@ -386,6 +386,80 @@ SSA_HD_NOINLINE int ssa_fx_general(const double* x, double tof, double* out) {
 //   * algebraically equal forms that save divisions: n = sqrt(k/a^3), M = M0 + n dt, |r'| = a(1 - e cos E),
 //     sqrt(px^2 + py^2) = |r| h_xy, reciprocals of |r|, |h|, h_xy formed once.
 // 1 atan2 + ~5.5 sincos + ~11 divisions instead of 7 atan2 + acos + 11 sincos + ~30 divisions.
+// Streamlined strong-hyperbolic propagation (ecc > 1 + delta, farnocchia.py:911-917, 994-1001).  Filter estimates that
+// an update pushed beyond escape speed are the usual way a state leaves the elliptic fast path (two or three objects
+// of the C2 catalog from step ~100 on, with eccentricities up to 1e4); through the literal restatement each of their
+// propagations costs ~3x a normal one and its warp lengthens k_fx by 6-14 us.  Same construction as the elliptic
+// path: e sinh F0 = r.v / sqrt(k |a|), e cosh F0 = r v^2 / k - 1 give F0 (the reference's logarithm), M0 = e sinh F0 -
+// F0, M = M0 + n tof, Newton from asinh(M / e) exactly as M_to_F, then cos nu = (e - cosh F)/(e cosh F - 1),
+// sin nu = sqrt(e^2 - 1) sinh F / (e cosh F - 1), |r'| = |a| (e cosh F - 1), and the rotation from the vectors.
+// Called with the quantities ssa_fx has already formed; a real function: only stray lanes come here.
+SSA_HD_NOINLINE int ssa_fx_hyperbolic(const double* x, double tof, double* out) {
+  const double k = SSA_C(MU), kinv = SSA_C(MU_INV);
+  const double* r = x;
+  const double* v = x + 3;
+  double h[3];
+  h[0] = ssa_fma(r[1], v[2], -ssa_mul(r[2], v[1]));
+  h[1] = ssa_fma(r[2], v[0], -ssa_mul(r[0], v[2]));
+  h[2] = ssa_fma(r[0], v[1], -ssa_mul(r[1], v[0]));
+  const double rr = ssa_dot3(r, r), vv = ssa_dot3(v, v), rv = ssa_dot3(r, v), hh = ssa_dot3(h, h);
+  const double rn = ssa_sqrt(rr), hn = ssa_sqrt(hh);
+  const double hxy2 = ssa_fma(h[1], h[1], ssa_mul(h[0], h[0]));
+  const bool planar = (hxy2 == 0.0);
+  const double inv_rn = ssa_div(1.0, rn), inv_hn = ssa_div(1.0, hn);
+  const double c1 = vv - ssa_mul(k, inv_rn);
+  const double e0 = ssa_mul(ssa_fma(c1, r[0], -ssa_mul(rv, v[0])), kinv);
+  const double e1 = ssa_mul(ssa_fma(c1, r[1], -ssa_mul(rv, v[1])), kinv);
+  const double e2 = ssa_mul(ssa_fma(c1, r[2], -ssa_mul(rv, v[2])), kinv);
+  const double ecc = ssa_sqrt(ssa_fma(e2, e2, ssa_fma(e1, e1, ssa_mul(e0, e0))));
+  const double ci = ssa_mul(h[2], inv_hn);
+  const double p = ssa_mul(hh, kinv);
+  const double em2 = ssa_fma(ecc, ecc, -1.0);          // e^2 - 1 > 0
+  const double na = ssa_div(p, em2);                    // |a|
+  const double e_sh = ssa_div(rv, ssa_sqrt(ssa_mul(k, na)));
+  const double e_ch = ssa_fma(ssa_mul(rn, vv), kinv, -1.0);
+  const double F0 = ssa_mul(ssa_log(ssa_div(e_ch + e_sh, e_ch - e_sh)), 0.5);   // farnocchia.py:299-301
+  const double sq = ssa_sqrt(em2);
+  const double inv_e = ssa_div(1.0, ecc);
+  const double d0 = ssa_div(1.0, e_ch - 1.0);           // 1 / (e cosh F0 - 1)
+  const double cnu0 = ssa_mul(ecc - ssa_mul(e_ch, inv_e), d0);
+  const double snu0 = ssa_mul(ssa_mul(sq, ssa_mul(e_sh, inv_e)), d0);
+  const double n = ssa_sqrt(ssa_div(k, ssa_mul(ssa_mul(na, na), na)));
+  const double M0 = e_sh - F0;
+  const double M = ssa_fma(n, tof, M0);
+  const double F1 = ssa_newton_hyperbolic(ssa_asinh(ssa_div(M, ecc)), M, ecc);   // M_to_F, farnocchia.py:604-622
+  const double sh = ssa_sinh(F1), ch = ssa_cosh(F1);
+  const double den = ssa_fma(ecc, ch, -1.0);
+  const double d1 = ssa_div(1.0, den);
+  const double cnu = ssa_mul(ecc - ch, d1), snu = ssa_mul(ssa_mul(sq, sh), d1);
+  const double px = planar ? r[0] : ssa_fma(r[1], h[0], -ssa_mul(r[0], h[1]));
+  const double py =
+      planar ? r[1] : ssa_mul(ssa_fma(r[2], hxy2, -ssa_mul(h[2], ssa_fma(r[1], h[1], ssa_mul(r[0], h[0])))), inv_hn);
+  const double hxy = ssa_sqrt(hxy2);
+  const double inv_hxy = ssa_div(1.0, planar ? 1.0 : hxy);
+  const double inv_rho = ssa_mul(inv_rn, inv_hxy);
+  const double cu0 = ssa_mul(px, inv_rho), su0 = ssa_mul(py, inv_rho);
+  const double cw = ssa_fma(cu0, cnu0, ssa_mul(su0, snu0)), sw = ssa_fma(su0, cnu0, -ssa_mul(cu0, snu0));
+  const double cO = planar ? 1.0 : -ssa_mul(h[1], inv_hxy), sO = planar ? 0.0 : ssa_mul(h[0], inv_hxy);
+  const double si = ssa_mul(hxy, inv_hn);
+  const double rp = ssa_mul(na, den);
+  const double vp = ssa_sqrt(ssa_div(k, p));
+  const double rx = ssa_mul(cnu, rp), ry = ssa_mul(snu, rp);
+  const double vx = ssa_mul(-snu, vp), vy = ssa_mul(ecc + cnu, vp);
+  const double m00 = cO, m01 = ssa_mul(-sO, ci);
+  const double m10 = sO, m11 = ssa_mul(cO, ci);
+  const double a00 = ssa_fma(m00, cw, ssa_mul(m01, sw)), a01 = ssa_fma(m01, cw, -ssa_mul(m00, sw));
+  const double a10 = ssa_fma(m10, cw, ssa_mul(m11, sw)), a11 = ssa_fma(m11, cw, -ssa_mul(m10, sw));
+  const double a20 = ssa_mul(si, sw), a21 = ssa_mul(si, cw);
+  out[0] = ssa_fma(rx, a00, ssa_mul(ry, a01));
+  out[1] = ssa_fma(rx, a10, ssa_mul(ry, a11));
+  out[2] = ssa_fma(rx, a20, ssa_mul(ry, a21));
+  out[3] = ssa_fma(vx, a00, ssa_mul(vy, a01));
+  out[4] = ssa_fma(vx, a10, ssa_mul(vy, a11));
+  out[5] = ssa_fma(vx, a20, ssa_mul(vy, a21));
+  return 0;
+}
+
 SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   const double k = SSA_C(MU), kinv = SSA_C(MU_INV);
   const double* r = x;
@@ -418,7 +492,13 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
     // the literal restatement.
     fast = ((ecc >= SSA_C(TOL8)) || (ecc < SSA_C(TOL12))) && (ecc < SSA_C(DELTA99)) && (planar || ci < 1.0);
   }
-  if (!fast) return ssa_fx_general(x, tof, out);
+  if (!fast) {
+    // strong hyperbolic regime with a well-defined plane: the streamlined hyperbolic path (finite e only; the band
+    // [0.99, 1.01], degenerate and non-finite states keep the literal restatement with its exact failure semantics)
+    const bool hyper = (rn > 0.0) && (hn > 0.0) && (hxy2 > 0.0 || h[2] > 0.0) && (ecc > SSA_C(HYP101)) && (ecc < 1e12) &&
+                       (planar || ci < 1.0);
+    return hyper ? ssa_fx_hyperbolic(x, tof, out) : ssa_fx_general(x, tof, out);
+  }
 
   const double p = ssa_mul(hh, kinv);
   const double ome2 = ssa_fma(-ecc, ecc, 1.0);

@@ -62,6 +62,36 @@ def test_fx_planar_and_circular_regimes(c2):
     assert np.all(t[:, 2] == 0) and np.all(t[:, 5] == 0)
 
 
+def test_fx_strong_hyperbolic_regime():
+    """Filter estimates that an update pushed beyond escape speed (e up to 1e4 in the C2 run) take the streamlined
+    hyperbolic path of the product (ssa_fx_hyperbolic); the oracle follows the reference's literal strong-hyperbolic
+    branch (farnocchia.py:299-301, 911-917, 994-1001).  e in (1.01, 1e4), every inclination, forward and backward."""
+    from ssa_gym_b200.catalog import coe2rv
+    rng = np.random.RandomState(3)
+    n = 4000
+    for elo, ehi in ((1.0101, 1.05), (1.05, 1.5), (1.5, 5.0), (5.0, 100.0), (100.0, 1e4)):
+        ecc = rng.uniform(elo, ehi, n)
+        rp = rng.uniform(6378137.0 + 300e3, 42164e3, n)
+        inc, raan, argp = rng.uniform(0.0, 3.1, n), rng.uniform(0, 6.28, n), rng.uniform(0, 6.28, n)
+        nu = rng.uniform(-1, 1, n) * np.arccos(-1 / ecc) * 0.95
+        states = coe2rv(rp * (1 + ecc), ecc, inc, raan, argp, nu)
+        for dt in (20.0, -600.0, 86400.0):
+            o, eo = H.lib_fx("oracle", states, dt)
+            t, et = H.lib_fx("twin", states, dt)
+            assert not eo.any() and not et.any() and np.isfinite(o).all() and np.isfinite(t).all()
+            rn = np.linalg.norm(o[:, :3], axis=1)[:, None]
+            vn = np.linalg.norm(o[:, 3:], axis=1)[:, None]
+            err = np.concatenate([np.abs(t[:, :3] - o[:, :3]) / rn, np.abs(t[:, 3:] - o[:, 3:]) / vn], 1)
+            assert err.max() < 1e-11 and np.median(err) < 1e-14
+    # energy and angular momentum are conserved along the hyperbola, and fx(fx(x, dt), -dt) returns
+    mu = 398600441800000.0
+    t, _ = H.lib_fx("twin", states, 600.0)
+    en = lambda s_: 0.5 * np.sum(s_[:, 3:] ** 2, 1) - mu / np.linalg.norm(s_[:, :3], axis=1)
+    assert np.max(np.abs(en(t) - en(states)) / np.abs(en(states))) < 1e-11
+    b, _ = H.lib_fx("twin", t, -600.0)
+    assert np.max(np.abs(b[:, :3] - states[:, :3]) / np.linalg.norm(states[:, :3], axis=1)[:, None]) < 1e-10
+
+
 def test_fx_invariants_at_full_size(c2):
     """Size-independent properties of two-body propagation: energy and angular momentum are conserved and
     fx(fx(x, dt), -dt) returns to x."""
