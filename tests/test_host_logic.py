@@ -109,3 +109,44 @@ def test_env_config_contract():
     assert cfg["alpha"] == 0.0001 and cfg["beta"] == 2.0 and cfg["kappa"] == -3
     assert cfg["fx"].__name__ == "fx_xyz_farnocchia" and cfg["msqrt"].__name__ == "robust_cholesky"
     assert ssa_gym_b200.ENV_ID == "ssa_tasker_simple-v2"
+
+
+def test_agents_match_the_oracle_restatement():
+    """ssa_gym_b200.agents (one selection rule, several scores) against oracle/env_oracle.py's line-by-line restatement
+    of agents.py:7-81 on random environments, including ties (first maximum wins) and the 'only object 0 is visible'
+    quirk of agents.py:37.  Integer work: every decision must be identical, and so must the use of the generators."""
+    from oracle import env_oracle as EO
+    from ssa_gym_b200 import agents as A
+
+    class Space:
+        def __init__(self, m, seed):
+            self.m, self.r = m, np.random.RandomState(seed)
+
+        def sample(self):
+            return self.r.randint(self.m)
+
+    class Env:
+        pass
+
+    rng = np.random.RandomState(0)
+    names = [n for n in ("agent_naive_greedy", "agent_visible_greedy", "agent_pos_error_greedy", "agent_vel_error_greedy",
+                         "agent_shannon", "agent_visible_greedy_aer", "agent_naive_random") if hasattr(EO, n)]
+    assert len(names) >= 4
+    for trial in range(300):
+        m, i = rng.randint(2, 12), rng.randint(1, 5)
+        P = np.array([[np.diag(rng.uniform(1, 10, 6)) for _ in range(m)] for _ in range(i + 1)])
+        if trial % 7 == 0:
+            P[i, 1] = P[i, 0]
+        vis = np.where(rng.rand(m) < (0.5 if trial % 5 else 0.1))[0]
+        if trial % 11 == 0:
+            vis = np.array([0])
+        dp, dv, obs = rng.uniform(0, 1e5, (i + 1, m)), rng.uniform(0, 1e2, (i + 1, m)), rng.uniform(0, 1, m * 4)
+        for nm in names:
+            outs = []
+            for mod in (A, EO):
+                e = Env()
+                e.P_filter, e.i, e.delta_pos, e.delta_vel = P, i, dp, dv
+                e.action_space = Space(m, trial)
+                e.visible_objects = lambda v=vis: v
+                outs.append((int(getattr(mod, nm)(obs, e)), e.action_space.r.randint(1 << 30)))   # decision + generator state
+            assert outs[0] == outs[1], (nm, trial, outs)
