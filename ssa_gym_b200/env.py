@@ -20,6 +20,7 @@ from datetime import datetime
 import numpy as np
 
 from . import _lib, dynamics
+from .episode import draw_episode, step_reward
 from .gym_shim import Env, seeding, spaces
 from .transformations import arcsec2rad, deg2rad, gcrs2irts_matrix_b, lla2ecef, load_eop_c04, time_table
 from .ukf import BatchedUKF, Q_discrete_white_noise_block
@@ -145,14 +146,11 @@ class SSA_Tasker_Env(Env):
         s = time.time()
         self.x_true[:], self.x_filter[:], self.P_filter[:], self.obs[:], self.sigmas_h[:] = [0] * 5
         self.z_true[:], self.y[:], self.S[:] = np.nan, np.nan, np.nan
-        for j in range(self.m):  # RNG draw order of SS2:206-209
-            self.x_true[0][j] = self.orbits[self.np_random.randint(low=0, high=self.orbits.shape[0]), :]
-            self.x_noise[j] = self.np_random.normal(size=6) * self.x_sigma
-            self.x_filter[0][j] = np.copy(self.x_true[0][j] + self.x_noise[j])
-            self.P_filter[0][j] = np.copy(self.P_0)
-        for i in range(self.n):  # SS2:219-221
-            for j in range(self.m):
-                self.z_noise[i, j] = self.np_random.normal(size=3) * self.z_sigma
+        # the random draws of the episode, in the reference's order (SS2:206-221)
+        self.x_true[0], self.x_noise[:], self.z_noise[:] = draw_episode(self.np_random, self.orbits, self.m, self.n,
+                                                                          self.x_sigma, self.z_sigma)
+        self.x_filter[0] = self.x_true[0] + self.x_noise
+        self.P_filter[0] = self.P_0
         self.scores[:], self.delta_pos[:], self.delta_vel[:], self.sigma_pos[:], self.sigma_vel[:] = [np.nan] * 5
         self.actions[:], self.obs_taken[:], self.failed_filters_id, self.visibility = 0, False, [], []
         self.failed_filters_msg = ["None"] * self.m
@@ -214,35 +212,8 @@ class SSA_Tasker_Env(Env):
             if j not in self.failed_filters_id:
                 self.filter_error(int(j), int(status[j]))
         s = time.time()
-        done = False
-        if self.reward_type == 'jones':
-            if np.max(self.delta_pos[i]) > 5e6:
-                done = True
-                self.rewards[i] = 0
-            elif np.max(self.delta_pos[i]) < 3e4:
-                done = True
-                self.rewards[i] = 1
-            elif i + 1 >= self.n:
-                done = True
-                self.rewards[i] = 0
-            else:
-                done = False
-                self.rewards[i] = 0
-        elif self.reward_type == 'trinary':
-            self.rewards[i] = np.mean(((self.delta_pos[i] < 1e4) * 1 + (self.delta_pos[i] < 1e7) * 1)) / 2
-        elif self.reward_type == 'shaped':
-            if np.max(self.delta_pos[i]) > 5e6:
-                done = True
-                self.rewards[i] = 0
-            elif np.max(self.delta_pos[i]) < 3e4:
-                done = True
-                self.rewards[i] = 1 - np.sum(self.rewards[:i])
-            elif a == np.argmax(self.sigma_pos[i - 1]):
-                self.rewards[i] = 1 / self.n
-            else:
-                self.rewards[i] = -1 / self.n
-        if i + 1 >= self.n:
-            done = True
+        self.rewards[i], done = step_reward(self.reward_type, i, self.n, a, self.delta_pos[i], self.sigma_pos[i - 1],
+                                            self.rewards[:i])
         self.runtime['Observations and Reward'] += time.time() - s
         self.runtime['step'] += time.time() - step_s
         if self.obs_returned == 'flatten':

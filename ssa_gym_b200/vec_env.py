@@ -20,6 +20,7 @@ vector_step in host mode against 0.45 ms in device mode).
 import numpy as np
 
 from . import _lib, dynamics
+from .episode import draw_episode
 from .gym_shim import seeding, spaces
 from .transformations import arcsec2rad, deg2rad, gcrs2irts_matrix_b, lla2ecef, load_eop_c04, time_table
 from .ukf import BatchedUKF, Q_discrete_white_noise_block
@@ -100,13 +101,10 @@ class VecSSATaskerEnv:
 
     def _draw(self, e):
         """The RNG draw sequence of SS2:206-221 for environment e."""
-        rng = self.np_randoms[e]
-        for j in range(self.m):
-            self.x_true0[e, j] = self.orbits[rng.randint(low=0, high=self.orbits.shape[0]), :]
-            noise = rng.normal(size=6) * self.x_sigma
-            self.x_filter0[e, j] = self.x_true0[e, j] + noise
-        # n*m successive normal(size=3) draws consume the stream exactly like one normal(size=(n, m, 3))
-        self.z_noise[e] = rng.normal(size=(self.n, self.m, 3)) * self.z_sigma
+        x_true0, x_noise, self.z_noise[e] = draw_episode(self.np_randoms[e], self.orbits, self.m, self.n, self.x_sigma,
+                                                          self.z_sigma)
+        self.x_true0[e] = x_true0
+        self.x_filter0[e] = x_true0 + x_noise
         self.i[e] = 0
         self.rewards_hist[e] = 0.0
         self.prev_spos_argmax[e] = 0  # argmax of the (all equal) sigma_pos[0]

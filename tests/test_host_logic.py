@@ -150,3 +150,43 @@ def test_agents_match_the_oracle_restatement():
                 e.visible_objects = lambda v=vis: v
                 outs.append((int(getattr(mod, nm)(obs, e)), e.action_space.r.randint(1 << 30)))   # decision + generator state
             assert outs[0] == outs[1], (nm, trial, outs)
+
+
+def test_episode_draws_consume_the_generator_like_the_reference():
+    """episode.draw_episode == the literal loop of SS2:206-221 (per object randint + normal(6), then n*m successive
+    normal(3) calls), number for number, and leaves the generator in the same state."""
+    from ssa_gym_b200.episode import draw_episode
+    orbits = np.random.RandomState(9).normal(size=(50, 6))
+    m, n = 7, 11
+    xs, zs = np.array([1e3] * 3 + [10.0] * 3), np.array([1e-5, 2e-5, 30.0])
+    a, b = np.random.RandomState(4), np.random.RandomState(4)
+    xt, xn, zn = draw_episode(a, orbits, m, n, xs, zs)
+    xt_r, xn_r, zn_r = np.empty((m, 6)), np.empty((m, 6)), np.empty((n, m, 3))
+    for j in range(m):
+        xt_r[j] = orbits[b.randint(low=0, high=orbits.shape[0]), :]
+        xn_r[j] = b.normal(size=6) * xs
+    for i in range(n):
+        for j in range(m):
+            zn_r[i, j] = b.normal(size=3) * zs
+    assert np.array_equal(xt, xt_r) and np.array_equal(xn, xn_r) and np.array_equal(zn, zn_r)
+    assert a.randint(1 << 30) == b.randint(1 << 30)
+
+
+def test_step_reward_rule():
+    """episode.step_reward against the branches of SS2:324-354 written out."""
+    from ssa_gym_b200.episode import step_reward
+    n = 20
+    near, mid, far = np.array([1e3, 2e4]), np.array([1e3, 4e4]), np.array([1e3, 6e6])
+    sig = np.array([1.0, 3.0])
+    hist = np.array([0.05, -0.05, 0.05])
+    assert step_reward('jones', 3, n, 0, near, sig, hist) == (1, True)
+    assert step_reward('jones', 3, n, 0, mid, sig, hist) == (0, False)
+    assert step_reward('jones', 3, n, 0, far, sig, hist) == (0, True)
+    assert step_reward('jones', n - 1, n, 0, mid, sig, hist) == (0, True)
+    r, d = step_reward('trinary', 3, n, 0, np.array([1e3, 5e6, 2e7]), sig, hist)
+    assert r == np.mean([2, 1, 0]) / 2 and d is False
+    assert step_reward('trinary', n - 1, n, 0, far, sig, hist)[1] is True
+    assert step_reward('shaped', 3, n, 1, mid, sig, hist) == (1 / n, False)
+    assert step_reward('shaped', 3, n, 0, mid, sig, hist) == (-1 / n, False)
+    assert step_reward('shaped', 3, n, 0, near, sig, hist) == (1 - hist.sum(), True)
+    assert step_reward('shaped', 3, n, 0, far, sig, hist) == (0, True)
