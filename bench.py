@@ -524,7 +524,7 @@ def main():
         traffic = None  # DRAM bytes per k_fx launch from the committed `ncu --set full` capture of this command
         try:
             if a.workload == "c2" and not a.objects and not team:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_d_ncu_full_c2_kernels.json")))["k_fx"]["dram_bytes_per_launch"]
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_e_ncu_full_c2_kernels.json")))["k_fx"]["dram_bytes_per_launch"]
         except Exception:
             traffic = None
         line = {
