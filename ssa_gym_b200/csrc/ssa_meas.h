@@ -26,15 +26,15 @@ typedef struct {
 
 // hx for the 'aer' observation type.  out = [az, el, range].  INL: inlined math (k_hx), same arithmetic.
 template <bool INL>
-SSA_HD void ssa_hx_aer_t(const double* x, const ssa_obs* o, double* out) {
+SSA_HD void ssa_hx_aer_m(const double* x, const double* M, const double* obs_itrs, const double* T, double* out) {
   // x_itrs = M @ x[:3]
   double xi[3], d[3], e[3];
   for (int i = 0; i < 3; ++i)
-    xi[i] = ssa_fma(o->M[3 * i + 2], x[2], ssa_fma(o->M[3 * i + 1], x[1], ssa_mul(o->M[3 * i], x[0])));
-  for (int i = 0; i < 3; ++i) d[i] = xi[i] - o->obs_itrs[i];
+    xi[i] = ssa_fma(M[3 * i + 2], x[2], ssa_fma(M[3 * i + 1], x[1], ssa_mul(M[3 * i], x[0])));
+  for (int i = 0; i < 3; ++i) d[i] = xi[i] - obs_itrs[i];
   // R_enz = T^T @ delta
   for (int i = 0; i < 3; ++i)
-    e[i] = ssa_fma(o->T[6 + i], d[2], ssa_fma(o->T[3 + i], d[1], ssa_mul(o->T[i], d[0])));
+    e[i] = ssa_fma(T[6 + i], d[2], ssa_fma(T[3 + i], d[1], ssa_mul(T[i], d[0])));
   const double r = ssa_sqrt_t<INL>(ssa_fma(d[2], d[2], ssa_fma(d[1], d[1], ssa_mul(d[0], d[0]))));
   double az = INL ? ssa_atan2_i(e[1], e[0]) : ssa_atan2(e[1], e[0]);
   if (az < 0.0) az = az + SSA_C(TWOPI);
@@ -42,6 +42,8 @@ SSA_HD void ssa_hx_aer_t(const double* x, const ssa_obs* o, double* out) {
   out[1] = INL ? ssa_asin_t<true>(ssa_div_i(e[2], r)) : ssa_asin(ssa_div(e[2], r));
   out[2] = r;
 }
+template <bool INL>
+SSA_HD void ssa_hx_aer_t(const double* x, const ssa_obs* o, double* out) { ssa_hx_aer_m<INL>(x, o->M, o->obs_itrs, o->T, out); }
 SSA_HD void ssa_hx_aer(const double* x, const ssa_obs* o, double* out) { ssa_hx_aer_t<false>(x, o, out); }
 
 // Geodetic altitude of an ECEF position (transformations.py:239-279 `ecef2lla`, the closed form of You (2000);

@@ -17,7 +17,8 @@
 // preserving), sin and cos of one angle come from one sincos, the zero third column of the
 // perifocal frame is never multiplied, and divisions by the constant mu become multiplications by
 // its reciprocal.  All of that changes results only at the last-ulp level; parity against the
-// reference functions is asserted in tests/test_fx_parity.py.
+// reference's own numba functions is asserted in tests/test_oracle_golden.py (golden vectors) and
+// tests/test_twin_vs_oracle.py (independent C oracle).
 //
 // Return value: SSA_FX_OK, or SSA_FX_EXC when the reference would have raised a Python exception
 // inside numba (failed `assert`, ZeroDivisionError, RuntimeError) — the environment turns both an
@@ -385,7 +386,9 @@ SSA_HD_NOINLINE int ssa_fx_general(const double* x, double tof, double* out) {
 //     below 1e-8 (acos(1 - 2^-53) = 1.49e-8).
 //   * algebraically equal forms that save divisions: n = sqrt(k/a^3), M = M0 + n dt, |r'| = a(1 - e cos E),
 //     sqrt(px^2 + py^2) = |r| h_xy, reciprocals of |r|, |h|, h_xy formed once.
-// 1 atan2 + ~5.5 sincos + ~11 divisions instead of 7 atan2 + acos + 11 sincos + ~30 divisions.
+//   * reciprocals shared: 1/|r|, 1/|h|, 1/h_xy come from one division, 1/p = k/|h|^2, 1/a = (1-e^2)/p,
+//     sqrt(k/p) = k/|h|, r.v/sqrt(k a) and sqrt(k/a^3) are products with sqrt(k a) and 1/a.
+// 1 atan2 + ~5.5 sincos + ~6 divisions + 6 square roots instead of 7 atan2 + acos + 11 sincos + ~30 divisions.
 // Streamlined strong-hyperbolic propagation (ecc > 1 + delta, farnocchia.py:911-917, 994-1001).  Filter estimates that
 // an update pushed beyond escape speed are the usual way a state leaves the elliptic fast path (two or three objects
 // of the C2 catalog from step ~100 on, with eccentricities up to 1e4); through the literal restatement each of their
@@ -475,15 +478,28 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   // inclination drawn from uniform(0, 0)).  rv2coe then calls the orbit equatorial and puts the node on the x axis.
   const bool planar = (hxy2 == 0.0);
   bool fast = (rn > 0.0) && (hn > 0.0) && (hxy2 > 0.0 || h[2] > 0.0);
-  double ecc = 0.0, e_ce = 0.0, ci = 0.0, inv_hn = 0.0, inv_rn = 0.0;
+  double ecc = 0.0, e_ce = 0.0, ci = 0.0, inv_hn = 0.0, inv_rn = 0.0, inv_hxy = 0.0, hxy = 0.0;
   if (fast) {
-    inv_rn = ssa_div_i(1.0, rn);
+    // the three reciprocals 1/|r|, 1/|h|, 1/h_xy from ONE division (t = 1 / (|r| |h| h_xy)); h_xy -> 1 for a planar orbit.
+    // Divisions and square roots are a third of the instructions of this function (~16 each, 8 of them FP64): every
+    // quotient below that has an algebraically equal product form uses it (all value-preserving to an ulp or two).
+    hxy = ssa_sqrt_i(hxy2);
+    const double hxy_s = planar ? 1.0 : hxy;
+    const double rh = ssa_mul(rn, hn);
+    const double t3 = ssa_div_i(1.0, ssa_mul(rh, hxy_s));
+    inv_hxy = ssa_mul(t3, rh);
+    const double t2 = ssa_mul(t3, hxy_s);  // 1 / (|r| |h|)
+    inv_rn = ssa_mul(t2, hn);
+    inv_hn = ssa_mul(t2, rn);
+    // one Newton step each (y += y (1 - d y)): the shared reciprocals are good to an ulp again
+    inv_rn = ssa_fma(inv_rn, ssa_fma(-rn, inv_rn, 1.0), inv_rn);
+    inv_hn = ssa_fma(inv_hn, ssa_fma(-hn, inv_hn, 1.0), inv_hn);
+    inv_hxy = ssa_fma(inv_hxy, ssa_fma(-hxy_s, inv_hxy, 1.0), inv_hxy);
     const double c1 = vv - ssa_mul(k, inv_rn);
     const double e0 = ssa_mul(ssa_fma(c1, r[0], -ssa_mul(rv, v[0])), kinv);
     const double e1 = ssa_mul(ssa_fma(c1, r[1], -ssa_mul(rv, v[1])), kinv);
     const double e2 = ssa_mul(ssa_fma(c1, r[2], -ssa_mul(rv, v[2])), kinv);
     ecc = ssa_sqrt_i(ssa_fma(e2, e2, ssa_fma(e1, e1, ssa_mul(e0, e0))));
-    inv_hn = ssa_div_i(1.0, hn);
     ci = ssa_mul(h[2], inv_hn);
     e_ce = ssa_fma(ssa_mul(rn, vv), kinv, -1.0);
     // Circular orbits: rv2coe drops the periapsis direction when ecc < 1e-8 (argp = 0, nu = argument of latitude)
@@ -501,17 +517,23 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   }
 
   const double p = ssa_mul(hh, kinv);
+  const double inv_p = ssa_mul(k, ssa_mul(inv_hn, inv_hn));  // 1/p = k / |h|^2
   const double ome2 = ssa_fma(-ecc, ecc, 1.0);
-  const double a = ssa_div_i(p, ome2);
-  const double e_se = ssa_div_i(rv, ssa_sqrt_i(ssa_mul(k, a)));
+  const double inv_ome2 = ssa_div_i(1.0, ome2);
+  double a = ssa_mul(p, inv_ome2);
+  a = ssa_fma(ssa_fma(-a, ome2, p), inv_ome2, a);  // residual correction: a = p / (1 - e^2) to half an ulp
+  double inv_a = ssa_mul(ome2, inv_p);
+  inv_a = ssa_fma(inv_a, ssa_fma(-a, inv_a, 1.0), inv_a);  // Newton step: 1/a to an ulp (n = sqrt(k a) / a^2 multiplies tof)
+  const double s_ka = ssa_sqrt_i(ssa_mul(k, a));
+  const double e_se = ssa_mul(ssa_mul(rv, s_ka), ssa_mul(inv_a, kinv));  // r.v / sqrt(k a)
   const double E0 = ssa_atan2_i(e_se, e_ce);
   const ssa_sc sc0 = ssa_sincos_i(E0);
   const double sq = ssa_sqrt_i(ome2);
   const double d0 = ssa_div_i(1.0, ssa_fma(-ecc, sc0.c, 1.0));
   const double cnu0 = ssa_mul(sc0.c - ecc, d0), snu0 = ssa_mul(ssa_mul(sq, sc0.s), d0);
   // mean motion and mean anomaly (farnocchia.py:874-875, 950-951)
-  // n = sqrt(k (1-e)^3 / q^3) with q = p/(1+e) = a (1-e)  ->  sqrt(k / a^3);  M = n (M0/n + tof) -> M0 + n tof
-  const double n = ssa_sqrt_i(ssa_div_i(k, ssa_mul(ssa_mul(a, a), a)));
+  // n = sqrt(k (1-e)^3 / q^3) with q = p/(1+e) = a (1-e)  ->  sqrt(k / a^3) = sqrt(k a) / a^2;  M = n (M0/n + tof) -> M0 + n tof
+  const double n = ssa_mul(s_ka, ssa_mul(inv_a, inv_a));
   const double M0 = ssa_fma(-ecc, sc0.s, E0);
   const double M = ssa_fma(n, tof, M0);
   int exc = 0;
@@ -533,14 +555,13 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
     }
   }
   const ssa_sc sc1 = ssa_sincos_i(E1);
-  const double d1 = ssa_div_i(1.0, ssa_fma(-ecc, sc1.c, 1.0));
+  const double den1 = ssa_fma(-ecc, sc1.c, 1.0);
+  const double d1 = ssa_div_i(1.0, den1);
   const double cnu = ssa_mul(sc1.c - ecc, d1), snu = ssa_mul(ssa_mul(sq, sc1.s), d1);
   // argument of latitude of the initial position: px = r.n, py = r.(h x n)/|h|, n = (-h_y, h_x, 0)
   const double px = planar ? r[0] : ssa_fma(r[1], h[0], -ssa_mul(r[0], h[1]));
   const double py =
       planar ? r[1] : ssa_mul(ssa_fma(r[2], hxy2, -ssa_mul(h[2], ssa_fma(r[1], h[1], ssa_mul(r[0], h[0])))), inv_hn);
-  const double hxy = ssa_sqrt_i(hxy2);
-  const double inv_hxy = ssa_div_i(1.0, planar ? 1.0 : hxy);
   const double inv_rho = ssa_mul(inv_rn, inv_hxy);  // sqrt(px^2 + py^2) = |r| h_xy: r lies in the orbital plane
   const double cu0 = ssa_mul(px, inv_rho), su0 = ssa_mul(py, inv_rho);
   const double cw = ssa_fma(cu0, cnu0, ssa_mul(su0, snu0)), sw = ssa_fma(su0, cnu0, -ssa_mul(cu0, snu0));
@@ -548,8 +569,8 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
   const double cO = planar ? 1.0 : -ssa_mul(h[1], inv_hxy), sO = planar ? 0.0 : ssa_mul(h[0], inv_hxy);
   const double si = ssa_mul(hxy, inv_hn);
   // perifocal position / velocity (farnocchia.py:70-72)
-  const double rp = ssa_mul(a, ssa_fma(-ecc, sc1.c, 1.0));  // p/(1 + e cos nu) = a (1 - e cos E)
-  const double vp = ssa_sqrt_i(ssa_div_i(k, p));
+  const double rp = ssa_mul(a, den1);     // p/(1 + e cos nu) = a (1 - e cos E)
+  const double vp = ssa_mul(k, inv_hn);   // sqrt(k/p) = k / |h|
   const double rx = ssa_mul(cnu, rp), ry = ssa_mul(snu, rp);
   const double vx = ssa_mul(-snu, vp), vy = ssa_mul(ecc + cnu, vp);
   const double m00 = cO, m01 = ssa_mul(-sO, ci);

@@ -998,277 +998,7 @@ __global__ void __launch_bounds__(32) k_update_staged(const KParams p, const __g
 constexpr int kUpdStagedSmem = UR_ROWS * 32 * 8 + 16;
 constexpr long kStagedMaxDefault = 1L << 40;
 
-// ---- team-mapped variants of the two per-object kernels (experiment, off by default) ------------------------
-// With C2-sized batches (20 000 objects) a thread-per-object kernel has only ~4 warps per SM and is a latency
-// chain (ncu: 6 % issue slots).  These variants give every object a 16-lane team, like ssa_step_kernel: 16x more
-// warps, the 13-term reductions spread over the lanes element by element (same fixed k = 0..12 order, so the
-// bits do not change), Cholesky / 3x3 inverse evaluated redundantly per lane.  MEASURED on B200 they LOSE at
-// every size (C2: k_ut 41 vs 12 us, k_update 56 vs 25 us; 125 k objects: 215 vs 37 us and 305 vs 77 us): the
-// team's strided scratch reads (one row per lane) and the redundant factorisations cost more than the extra
-// warps hide.  Kept behind SSA_UKF_TEAM_SMALL=1 as a third, independently written implementation that the
-// bit-exact tests cover.
-constexpr long kTeamMaxN = 131072;
-
-__global__ void __launch_bounds__(kCtaThreads) k_ut_team(const KParams p) {
-  __shared__ double ws_all[kTeamsPerCta * kWsStride];
-  const int lane32 = threadIdx.x & 31, lane = threadIdx.x & 15, team = threadIdx.x >> 4;
-  const unsigned tmask = 0xFFFFu << (lane32 & 16);
-  const long loc = (long)blockIdx.x * kTeamsPerCta + team;
-  if (loc >= p.Nc) return;
-  const long obj = p.obj0 + loc, ld = p.ld, lds = p.lds;
-  if (!(p.flags & SSA_STEP_PREDICT)) return;
-  double* ws = ws_all + team * kWsStride;
-  int st = p.status[obj];
-  if (st & SSA_ST_FAILED) return;
-  int code = p.code[obj];
-  if (!code && p.exc[obj]) code = SSA_ST_FXEXC;
-  int infl_add = 0;
-  if (!code) {
-    // stage the propagated sigma set: lane k owns row k
-    double f[6];
-    if (lane < 13) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) { f[i] = p.F[(lane * 6 + i) * lds + loc]; ws[WS_SG + lane * 6 + i] = f[i]; }
-    }
-    team_sync(tmask);
-    if (lane < 6) ws[WS_XB + lane] = ssa_wmean13(ws + WS_SG, 6, lane, p.Wm);
-    team_sync(tmask);
-    double x[6];
-    int nan = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { x[i] = ws[WS_XB + i]; nan |= ssa_isnan(x[i]); }
-    if (lane < 13) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) ws[WS_SG + lane * 6 + i] = f[i] - x[i];
-    }
-    team_sync(tmask);
-    {
-      const int i = c_pi[lane], j = c_pj[lane];
-      ws[WS_PN + lane] = ssa_wcov13(ws + WS_SG, 6, i, ws + WS_SG, 6, j, p.Wc) + __ldg(p.qr + lane);
-      if (lane < 5) {
-        const int i2 = c_pi[16 + lane], j2 = c_pj[16 + lane];
-        ws[WS_PN + 16 + lane] = ssa_wcov13(ws + WS_SG, 6, i2, ws + WS_SG, 6, j2, p.Wc) + __ldg(p.qr + 16 + lane);
-      }
-    }
-    team_sync(tmask);
-    if (lane < 6) p.x[lane * ld + obj] = x[lane];
-    p.P[lane * ld + obj] = ws[WS_PN + lane];
-    if (lane < 5) p.P[(16 + lane) * ld + obj] = ws[WS_PN + 16 + lane];
-    if (nan) code |= SSA_ST_NAN;
-    if (p.resample) {
-      double U[SSA_NP];
-      const int r2 = ssa_robust_chol6(ws + WS_PN, 1, p.lam, U);
-      if (r2 < 0) code |= SSA_ST_LINALG;
-      else {
-        if (r2 > 0) infl_add = 1;
-        // every lane holds the same factor: lanes 0..15 store elements 0..15, lanes 0..4 the rest
-        double ue = 0.0, ue2 = 0.0;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) ue = (lane == e) ? U[e] : ue;
-#pragma unroll
-        for (int e = 16; e < SSA_NP; ++e) ue2 = (lane == e - 16) ? U[e] : ue2;
-        p.U[lane * lds + loc] = ue;
-        if (lane < 5) p.U[(16 + lane) * lds + loc] = ue2;
-      }
-    }
-  }
-  if (code) {
-    team_sync(tmask);
-    if (lane < 6) p.x[lane * ld + obj] = lane < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL;
-    {
-      const int i = c_pi[lane], j = c_pj[lane];
-      p.P[lane * ld + obj] = (i == j) ? (i < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL) : 0.0;
-      if (lane < 5) {
-        const int i2 = c_pi[16 + lane], j2 = c_pj[16 + lane];
-        p.P[(16 + lane) * ld + obj] = (i2 == j2) ? (i2 < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL) : 0.0;
-      }
-    }
-    if (lane == 0) p.status[obj] = st | SSA_ST_FAILED | code;
-  }
-  if (lane == 0) {
-    p.code[obj] = code;
-    if (infl_add) p.infl[obj] += 1;
-  }
-}
-
-__global__ void __launch_bounds__(kCtaThreads) k_update_team(const KParams p) {
-  __shared__ double ws_all[kTeamsPerCta * kWsStride];
-  const int lane32 = threadIdx.x & 31, lane = threadIdx.x & 15, team = threadIdx.x >> 4;
-  const unsigned tmask = 0xFFFFu << (lane32 & 16);
-  const long loc = (long)blockIdx.x * kTeamsPerCta + team;
-  if (loc >= p.Nc) return;
-  const long obj = p.obj0 + loc, ld = p.ld, lds = p.lds;
-  const int flags = p.flags;
-  double* ws = ws_all + team * kWsStride;
-  int st = p.status[obj];
-  bool want_upd = (flags & SSA_STEP_UPDATE_ALL) != 0;
-  if (flags & SSA_STEP_UPDATE_ACT) want_upd = want_upd || (p.actions[obj / p.m] == (int)(obj % p.m));
-  int updated = 0, code = 0;
-  // stage x, xt, P
-  if (lane < 6) { ws[WS_XB + lane] = p.x[lane * ld + obj]; ws[WS_XT + lane] = p.xt[lane * ld + obj]; }
-  ws[WS_PN + lane] = p.P[lane * ld + obj];
-  if (lane < 5) ws[WS_PN + 16 + lane] = p.P[(16 + lane) * ld + obj];
-  team_sync(tmask);
-  double x[6], xt[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) { x[i] = ws[WS_XB + i]; xt[i] = ws[WS_XT + i]; }
-  bool dirty = false;  // x / P changed and must be written back
-  if (want_upd && !(st & SSA_ST_FAILED)) {
-    double zt[3];
-    const int visible = p.visible[obj];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) zt[a] = (p.obs_type == SSA_OBS_AER) ? p.ZT[a * lds + loc] : xt[a];
-    if (p.z_true && lane < 3) p.z_true[obj * 3 + lane] = zt[lane];
-    if (p.code[obj]) {
-      code = p.code[obj];
-    } else if (visible) {
-      double z[3], zp[3], zk[3] = {0, 0, 0}, rz[3];
-#pragma unroll
-      for (int a = 0; a < 3; ++a) z[a] = zt[a] + (p.z_noise ? p.z_noise[obj * 3 + a] : 0.0);
-      if (lane < 13) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          zk[a] = p.ZS[(lane * 3 + a) * lds + loc];
-          ws[WS_ZZ + lane * 3 + a] = (p.obs_type == SSA_OBS_AER) ? p.UVW[(lane * 3 + a) * lds + loc] : zk[a];
-        }
-      }
-      team_sync(tmask);
-      if (lane < 3) ws[WS_ZM + lane] = ssa_wmean13(ws + WS_ZZ, 3, lane, p.Wm);
-      team_sync(tmask);
-      if (p.obs_type == SSA_OBS_AER) {
-        double zm[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) zm[a] = ws[WS_ZM + a];
-        ssa_uvw2aer(zm, zp);
-        ssa_residual_aer(zk, zp, rz);
-      } else {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) { zp[a] = ws[WS_ZM + a]; rz[a] = zk[a] - zp[a]; }
-      }
-      if (lane < 13) {
-        double sk[6];
-        if (p.resample) load_sigma(p, loc, lane, x, sk);
-        else {
-#pragma unroll
-          for (int i = 0; i < 6; ++i) sk[i] = p.F[(lane * 6 + i) * lds + loc];
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a) ws[WS_ZZ + lane * 3 + a] = rz[a];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) ws[WS_SG + lane * 6 + i] = sk[i] - x[i];
-      }
-      team_sync(tmask);
-#pragma unroll
-      for (int round = 0; round < 2; ++round) {
-        const int e = lane + 16 * round;
-        if (e < 6) {
-          const int a = c_sa[e], b = c_sb[e];
-          double sv;
-          if (p.obs_type == SSA_OBS_AER) sv = ssa_wouter13(ws + WS_ZZ, 3, a, ws + WS_ZZ, 3, b, p.Wc);
-          else sv = ssa_wcov13(ws + WS_ZZ, 3, a, ws + WS_ZZ, 3, b, p.Wc);
-          ws[WS_SS + 3 * a + b] = sv + __ldg(p.qr + 21 + 3 * a + b);
-          if (a != b) {
-            double s2 = sv;
-            if (p.obs_type != SSA_OBS_AER) s2 = ssa_wcov13(ws + WS_ZZ, 3, b, ws + WS_ZZ, 3, a, p.Wc);
-            ws[WS_SS + 3 * b + a] = s2 + __ldg(p.qr + 21 + 3 * b + a);
-          }
-        } else if (e < 24) {
-          const int i = (e - 6) / 3, a = (e - 6) % 3;
-          ws[WS_PX + (e - 6)] = ssa_wouter13(ws + WS_SG, 6, i, ws + WS_ZZ, 3, a, p.Wc);
-        }
-      }
-      team_sync(tmask);
-      double Sm[9], SI[9], yr[3];
-#pragma unroll
-      for (int e = 0; e < 9; ++e) Sm[e] = ws[WS_SS + e];
-      const int ok = ssa_inv3(Sm, SI);
-      if (p.obs_type == SSA_OBS_AER) ssa_residual_aer(z, zp, yr);
-      else {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) yr[a] = z[a] - zp[a];
-      }
-      if (lane < 6) {
-        double K[3];
-        const double px0 = ws[WS_PX + lane * 3], px1 = ws[WS_PX + lane * 3 + 1], px2 = ws[WS_PX + lane * 3 + 2];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          K[a] = ssa_fma(px2, SI[6 + a], ssa_fma(px1, SI[3 + a], ssa_mul(px0, SI[a])));
-          ws[WS_KK + lane * 3 + a] = K[a];
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-          ws[WS_TT + a * 6 + lane] = ssa_fma(Sm[3 * a + 2], K[2], ssa_fma(Sm[3 * a + 1], K[1], ssa_mul(Sm[3 * a], K[0])));
-        ws[WS_XB + lane] = x[lane < 6 ? lane : 0] + ssa_fma(K[2], yr[2], ssa_fma(K[1], yr[1], ssa_mul(K[0], yr[0])));
-      }
-      team_sync(tmask);
-#pragma unroll
-      for (int round = 0; round < 2; ++round) {
-        const int e = lane + 16 * round;
-        if (e < 21) {
-          const int i = c_pi[e], j = c_pj[e];
-          const double kt = ssa_fma(ws[WS_KK + i * 3 + 2], ws[WS_TT + 12 + j],
-                                    ssa_fma(ws[WS_KK + i * 3 + 1], ws[WS_TT + 6 + j], ssa_mul(ws[WS_KK + i * 3], ws[WS_TT + j])));
-          ws[WS_PN + e] = ws[WS_PN + e] - kt;
-        }
-      }
-      int nan = 0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) { x[i] = ws[WS_XB + i]; nan |= ssa_isnan(x[i]); }
-      if (p.y && lane < 3) p.y[obj * 3 + lane] = yr[lane];
-      if (p.S && lane < 9) p.S[obj * 9 + lane] = Sm[lane];
-      if (p.sigmas_h && lane < 13) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) p.sigmas_h[obj * 39 + lane * 3 + a] = zk[a];
-      }
-      updated = 1;
-      dirty = true;
-      if (!ok) code = SSA_ST_LINALG | SSA_ST_IN_UPDATE;
-      else if (nan) code = SSA_ST_NAN | SSA_ST_IN_UPDATE;
-      team_sync(tmask);
-    }
-    if (code) {
-      st |= SSA_ST_FAILED | code;
-      if (lane < 6) ws[WS_XB + lane] = lane < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL;
-      {
-        const int i = c_pi[lane], j = c_pj[lane];
-        ws[WS_PN + lane] = (i == j) ? (i < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL) : 0.0;
-        if (lane < 5) {
-          const int i2 = c_pi[16 + lane], j2 = c_pj[16 + lane];
-          ws[WS_PN + 16 + lane] = (i2 == j2) ? (i2 < 3 ? SSA_XFAIL_POS : SSA_XFAIL_VEL) : 0.0;
-        }
-      }
-      team_sync(tmask);
-#pragma unroll
-      for (int i = 0; i < 6; ++i) x[i] = ws[WS_XB + i];
-      dirty = true;
-      if (lane == 0) p.status[obj] = st;
-    }
-  }
-  if (lane == 13 && p.updated) p.updated[obj] = (uint8_t)updated;
-  if (lane == 0 && p.status_out) p.status_out[obj] = st;
-  team_sync(tmask);
-  if (dirty) {
-    if (lane < 6) p.x[lane * ld + obj] = ws[WS_XB + lane];
-    p.P[lane * ld + obj] = ws[WS_PN + lane];
-    if (lane < 5) p.P[(16 + lane) * ld + obj] = ws[WS_PN + 16 + lane];
-  }
-  if (flags & SSA_STEP_EPILOGUE) {
-    if (lane < 12) {
-      const int d = lane < 6 ? 0 : lane - 6;
-      p.obs[obj * 12 + lane] = lane < 6 ? ws[WS_XB + lane] : ws[WS_PN + ssa_pidx(d, d)];
-    }
-    if (lane == 12 || lane == 13) {
-      const int o = (lane == 12) ? 0 : 3;
-      const double d0 = x[o] - xt[o], d1 = x[o + 1] - xt[o + 1], d2 = x[o + 2] - xt[o + 2];
-      const double dd = ssa_sqrt(ssa_fma(d2, d2, ssa_fma(d1, d1, ssa_mul(d0, d0))));
-      const double sp = (lane == 12) ? ssa_sqrt((ws[WS_PN + 0] + ws[WS_PN + 6]) + ws[WS_PN + 11])
-                                     : ssa_sqrt((ws[WS_PN + 15] + ws[WS_PN + 18]) + ws[WS_PN + 20]);
-      if (lane == 12) { p.dpos[obj] = dd; p.spos[obj] = sp; }
-      else { p.dvel[obj] = dd; p.svel[obj] = sp; }
-    }
-    if (lane == 14) p.trace[obj] = ssa_trace6(ws + WS_PN, 1);
-  }
-}
+#include "ssa_tile.cuh"
 
 // ---- per-environment reductions: reward/done and greedy taskers ------------------------------------
 struct EnvParams {
@@ -1802,9 +1532,9 @@ struct ssa_ukf {
   int32_t *code, *exc;
   long chunk;     // objects per chunk of the split pipeline (scratch capacity); N when everything fits in L2
   long staged_max;  // chunks up to this many objects use the TMA-staged k_update (default: all)
-  CUtensorMap tm_z, tm_u, tm_s;
+  CUtensorMap tm_z, tm_u, tm_s, tm_x;
   int pdl;  // programmatic dependent launch of the step's kernel chain (SSA_UKF_PDL=0 turns it off)
-  int team_small; // SSA_UKF_TEAM_SMALL=1: team-mapped UT / update kernels for batches <= kTeamMaxN (slower; tests)
+  int use_tile;   // tile kernels (default); SSA_UKF_KERNEL=split selects the five-kernel split pipeline
   int use_team;   // SSA_UKF_KERNEL=team selects the fused 16-lane team kernel instead of the split pipeline
   // double-buffered host pipeline (ssa_ukf_step_host)
   struct {
@@ -1961,8 +1691,8 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
   {
     const char* kv = getenv("SSA_UKF_KERNEL");
     h->use_team = (kv && strcmp(kv, "team") == 0) ? 1 : 0;
-    const char* ts = getenv("SSA_UKF_TEAM_SMALL");
-    h->team_small = (ts && strcmp(ts, "1") == 0) ? 1 : 0;
+    h->use_tile = (kv && strcmp(kv, "split") == 0) ? 0 : 1;
+    cudaFuncSetAttribute(k_update_tile<SSA_TILE, kTileThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateTile<SSA_TILE>));
     const char* gv = getenv("SSA_UKF_STEP_GRAPH");
     h->sg.on = (gv && strcmp(gv, "0") == 0) ? 0 : 1;
     const char* pv = getenv("SSA_UKF_PDL");
@@ -1973,7 +1703,8 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
     cudaFuncSetAttribute(k_update_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdStagedSmem);
     // tensor maps of the two SoA tensors (scratch [180][lds], state [33][ld]); one map per box height
     const int rc = make_tmap(&h->tm_z, h->scratch, lds, SC_ROWS, 81) |
-                   make_tmap(&h->tm_u, h->scratch, lds, SC_ROWS, 21) | make_tmap(&h->tm_s, h->xt, ld, ST_ROWS, ST_ROWS);
+                   make_tmap(&h->tm_u, h->scratch, lds, SC_ROWS, 21) | make_tmap(&h->tm_s, h->xt, ld, ST_ROWS, ST_ROWS) |
+                   make_tmap(&h->tm_x, h->xt, ld, ST_ROWS, 12);
     if (rc) { ssa_ukf_destroy(h); return set_err("cuTensorMapEncodeTiled", cudaErrorUnknown); }
   }
   if ((e = cudaMalloc(&h->visible, 3 * ld + E)) != cudaSuccess) { ssa_ukf_destroy(h); return set_err("cudaMalloc(u8)", e); }
@@ -2237,25 +1968,32 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
     const unsigned gobj = (unsigned)((p.Nc + kSplitThreads - 1) / kSplitThreads);
     const unsigned gobj2 = (unsigned)((p.Nc + kObjThreads - 1) / kObjThreads);
     const unsigned gfx = (unsigned)((p.Nc + kFxThreads - 1) / kFxThreads);
+    const unsigned gtile = (unsigned)((p.Nc + SSA_TILE - 1) / SSA_TILE);
     cudaEvent_t* evc = (ev && o0 == 0) ? ev : nullptr;
     const bool pdl = h->pdl && !ev;
+    // the tile kernels keep the sigma sets in shared memory; the book-version filter (sigmas_f kept across calls)
+    // and the RL-mode update of one tasked object per environment use the split kernels
+    const bool tile = h->use_tile && p.resample;
     if (predict || update) { launch_chain(pdl, k_factor, gobj2, kObjThreads, 0, st, p); h->launches++; }
     if (evc) CK(cudaEventRecord(evc[1], st));
-    if (predict || truth) { launch_chain(pdl, k_fx, dim3(gfx, 14), kFxThreads, 0, st, p); h->launches++; }
+    if (predict || truth) {
+      if (tile) launch_chain(pdl, k_predict_tile<SSA_TILE, kTileThreads>, gtile, kTileThreads, 0, st, p, h->tm_x, h->tm_u);
+      else launch_chain(pdl, k_fx, dim3(gfx, 14), kFxThreads, 0, st, p);
+      h->launches++;
+    }
     if (evc) CK(cudaEventRecord(evc[2], st));
-    const bool small = h->team_small && p.Nc <= kTeamMaxN;
     const bool staged = p.Nc <= h->staged_max;
-    const unsigned gteam = (unsigned)((p.Nc + kTeamsPerCta - 1) / kTeamsPerCta);
     if (predict) {
-      if (small) k_ut_team<<<gteam, kCtaThreads, 0, st>>>(p);
+      if (tile) launch_chain(pdl, k_refactor, gobj2, kObjThreads, 0, st, p);
       else launch_chain(pdl, k_ut, gobj2, kObjThreads, 0, st, p);
       h->launches++;
     }
     if (evc) CK(cudaEventRecord(evc[3], st));
-    if (update || epi) { launch_chain(pdl, k_hx, dim3(gfx, 14), kFxThreads, 0, st, p); h->launches++; }
+    const bool tile_upd = tile && (flags & SSA_STEP_UPDATE_ALL);
+    if ((update || epi) && !tile_upd) { launch_chain(pdl, k_hx, dim3(gfx, 14), kFxThreads, 0, st, p); h->launches++; }
     if (evc) CK(cudaEventRecord(evc[4], st));
     if (update || epi) {
-      if (small) k_update_team<<<gteam, kCtaThreads, 0, st>>>(p);
+      if (tile_upd) launch_chain(pdl, k_update_tile<SSA_TILE, kTileThreads>, gtile, kTileThreads, sizeof(UpdateTile<SSA_TILE>), st, p, h->tm_s, h->tm_u);
       else if (staged && p.resample && (flags & SSA_STEP_UPDATE_ALL))
         launch_chain(pdl, k_update_staged, (unsigned)((p.Nc + 31) / 32), 32, kUpdStagedSmem, st, p, h->tm_z, h->tm_u, h->tm_s);
       else launch_chain(pdl, k_update, gobj, kSplitThreads, 0, st, p);
@@ -2300,7 +2038,8 @@ int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
       cudaGraphNodeType ty;
       cudaKernelNodeParams kp;
       if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel &&
-          cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func == (void*)k_hx) {
+          cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess &&
+          (kp.func == (void*)k_hx || kp.func == (void*)k_update_tile<SSA_TILE, kTileThreads>)) {
         h->sg.hx_node[gi] = nodes[i];
         h->sg.hx_params[gi] = kp;
       }
@@ -2313,7 +2052,7 @@ int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
   }
   if (h->sg.hx_node[gi]) {  // this step's trans_matrix
     memcpy(h->sg.p[gi].ob.M, M, 9 * sizeof(double));
-    void* args[1] = {&h->sg.p[gi]};
+    void* args[3] = {&h->sg.p[gi], &h->tm_s, &h->tm_u};  // k_hx takes the first, k_update_tile all three
     cudaKernelNodeParams kp = h->sg.hx_params[gi];
     kp.kernelParams = args;
     kp.extra = nullptr;
@@ -2518,7 +2257,7 @@ int ssa_ukf_rollout_config(ssa_ukf* h, const double* orbits, int n_orbits, const
   }
   CK(cudaSetDevice(h->device));
   const size_t N = h->cfg.n_objects, E = h->cfg.n_envs;
-  for (int i = 0; i < h->sg.n; ++i) { cudaGraphExecDestroy(h->sg.gexec[i]); cudaGraphDestroy(h->sg.graph[i]); }
+  // (the cached graphs of ssa_ukf_step stay valid: every pointer they captured belongs to the handle)
   if (h->ro.init) {
     cudaFree(h->ro.dbuf); cudaFree(h->ro.ibuf); cudaFree(h->ro.dout); cudaFreeHost(h->ro.hout); cudaFreeHost(h->ro.hin);
     for (int i = 0; i < 2; ++i) if (h->ro.gexec[i]) { cudaGraphExecDestroy(h->ro.gexec[i]); h->ro.gexec[i] = nullptr; }

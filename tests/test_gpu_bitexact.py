@@ -14,13 +14,12 @@ from ssa_gym_b200.ukf import BatchedUKF
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["split", "split_teamsmall", "team"], autouse=False)
+@pytest.fixture(params=["tile", "split", "team"], autouse=False)
 def kernel(request, monkeypatch):
-    """Every device implementation of the step: the split five-kernel pipeline (default), the same pipeline with
-    the team-mapped UT/update kernels (SSA_UKF_TEAM_SMALL=1), and the fused 16-lane team kernel
-    (SSA_UKF_KERNEL=team).  The handle reads the variables at creation."""
-    monkeypatch.setenv("SSA_UKF_KERNEL", "team" if request.param == "team" else "split")
-    monkeypatch.setenv("SSA_UKF_TEAM_SMALL", "1" if request.param == "split_teamsmall" else "0")
+    """Every device implementation of the step: the tile kernels (default: sigma sets in shared memory), the split
+    five-kernel pipeline (SSA_UKF_KERNEL=split) and the fused 16-lane team kernel (SSA_UKF_KERNEL=team).  The handle
+    reads the variable at creation."""
+    monkeypatch.setenv("SSA_UKF_KERNEL", request.param)
     return request.param
 
 F = _lib
@@ -269,11 +268,12 @@ def _rotz(a):
     return np.array([[c, s_, 0.0], [-s_, c, 0.0], [0.0, 0.0, 1.0]])
 
 
+@pytest.mark.parametrize("impl", ["tile", "split"])
 @pytest.mark.parametrize("chunk", ["640", "4000"])
-def test_chunked_execution_bitexact(chunk, monkeypatch):
+def test_chunked_execution_bitexact(chunk, impl, monkeypatch):
     """Large batches run in L2-sized chunks (SSA_UKF_CHUNK objects per chunk, env-aligned in RL mode).  Forcing
     tiny chunks (ragged last chunk) must not change a single bit, in catalog mode and in RL mode."""
-    monkeypatch.setenv("SSA_UKF_KERNEL", "split")
+    monkeypatch.setenv("SSA_UKF_KERNEL", impl)
     monkeypatch.setenv("SSA_UKF_CHUNK", chunk)
     N, steps = 9001, 3
     cat, x, P0, zn = H.c2_inputs(N, steps)

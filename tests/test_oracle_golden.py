@@ -38,7 +38,9 @@ def test_fx_against_reference_numba(which):
         assert not exc.any()
         err = rel_state_err(out, g["fx_out"][k])
         assert err.max() < 1e-12, (which, dt, err.max())
-        assert np.median(err) < 1e-15
+        # the median sits at the rounding floor: one ulp in the mean motion n moves the position by eps * n * dt, and
+        # n * dt is 6..100 rad at dt = 86400 s (the twin's streamlined path: 1.0e-15 there, 2.2e-16 at dt <= 600 s)
+        assert np.median(err) < 1e-15 * max(1.0, float(dt) / 43200.0)
 
 
 def test_fx_known_answers_survey_appendix_d():

@@ -134,9 +134,8 @@ def test_gpu_bitexact_on_stress_inputs():
     zn = np.random.RandomState(4).normal(size=(4, n, 3)) * np.array([H.arcsec2rad, H.arcsec2rad, 1e3])
     flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE | F.STEP_RECORD
     import os
-    for kernel in ("split", "split_teamsmall", "team"):
-        os.environ["SSA_UKF_KERNEL"] = "team" if kernel == "team" else "split"
-        os.environ["SSA_UKF_TEAM_SMALL"] = "1" if kernel == "split_teamsmall" else "0"
+    for kernel in ("tile", "split", "team"):
+        os.environ["SSA_UKF_KERNEL"] = kernel
         for dt in (20.0, 6000.0):
             cfg = H.make_cfg(n, dt=dt)
             st = H.HostState(cat, xf, P)
@@ -155,4 +154,3 @@ def test_gpu_bitexact_on_stress_inputs():
             assert (st.status & 1).sum() > 100 and st.infl.sum() > 50
             ukf.close()
     os.environ.pop("SSA_UKF_KERNEL", None)
-    os.environ.pop("SSA_UKF_TEAM_SMALL", None)
