@@ -1,16 +1,18 @@
 #!/usr/bin/env python
 """bench.py — the headline metric of BASELINE.json on B200: RSO UKF predict+update per second.
 
-A "step" = one pass of the hot path (truth fx + UKF predict + UKF update + obs/error epilogue) over
-one batch of synthetic input: the C2 workload of SURVEY.md 8(d) — a 20 000-orbit catalog, every object
-predicted and updated once per step (ssa_tasker_simple_2.py:243-367 for every RSO).  One process per
-GPU; every rank owns an independent 20 000-object catalog (weak scaling, no data-path collective —
-objects never couple); rank 0 prints ONE JSON line.
+A "step" = one pass of the hot path (truth fx + UKF predict + UKF update + obs/error epilogue) over the whole
+catalog.  Default workload = BASELINE.json configs[3] (SURVEY.md 8d "C4"): a 1 000 000-object synthetic catalog,
+every object predicted and updated once per step, sharded in contiguous blocks over the N ranks (STRONG scaling:
+the catalog is fixed, N = 1 holds all of it on one GPU); every step also reduces the shard's reward terms on the
+device (ssa_ukf_catalog_stats) and all-gathers them over NCCL — both inside the timed CUDA events.  Objects never
+couple, so that gather is the only collective.  Rank 0 prints ONE JSON line; C2 (the 20 000-orbit
+catalog) and C3 (4 096 vectorised environments) are measured briefly on rank 0 and reported under `extra`.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c4] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c3] [--impl reference]
 
-`--impl reference` times the CPU oracle port of the reference's algorithm (oracle/ukf_oracle.c, OpenMP
-over all host cores) on the same workload — the reference itself is pure Python around filterpy and
+`--impl reference` times the CPU oracle port of the reference's algorithm (oracle/ukf_oracle.c, OpenMP over all
+host cores) on a bounded sample of the same workload — the reference itself is pure Python around filterpy and
 cannot be built or installed offline (DESIGN.md "Reference arm").
 """
 import argparse
@@ -27,17 +29,28 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# Algorithmic cost per unit (one object: truth fx + predict + update + epilogue), DESIGN.md §3, under SURVEY 8(d)'s
-# counting convention (add/mul/cmp = 1, fma = 2, div = sqrt = 10, sin = cos = 40, atan2 = 80, asin = 70, mod = 10).
-# Two figures: the algorithm AS IMPLEMENTED here (streamlined fx: 0.90 kflop; update without the redundant
-# residual evaluations: 6.9 kflop; factorisations + UT: 1.7 kflop) and the reference's literal sequence (SURVEY: 1.85
-# kflop per fx, 39 kflop per unit).  `roofline.frac` uses the first (conservative, consistent with ncu's FP64 pipe
-# utilisation); the second is reported as `frac_reference_algorithm`.
-FLOP_FX = 0.90e3
-FLOP_PER_UNIT = 14 * FLOP_FX + 6.9e3 + 1.7e3      # 21.2 kflop
+# Algorithmic cost per unit (one object: truth fx + predict + update + epilogue) under SURVEY 8(d)'s counting convention
+# (add/mul/cmp = 1, fma = 2, div = sqrt = 10, sin = cos = 40, atan2 = 80, asin = 70, mod = 10).
+#   * SURVEY 8(d), the reference's literal sequence — the figure `roofline.frac` uses: fx 1.85 kflop; unit 39 kflop
+#     = 14 fx 25.9 k + 2 Cholesky 0.64 k + 2 sigma draws 0.14 k + unscented transform 0.85 k + update 11 k + epilogue 0.1 k.
+#     Per kernel: k_predict_tile = 14 fx + 1 sigma draw + UT = 26.8 k; k_update_tile = 1 sigma draw + update + epilogue = 11.2 k;
+#     k_factor / k_refactor = 0.32 k each.
+#   * the algorithm AS IMPLEMENTED here (secondary key `frac_as_implemented`): streamlined fx 0.86 kflop (6 divisions,
+#     6 square roots, 1 atan2, 5.5 sincos), update without the redundant residual evaluations 6.9 kflop, factorisations + UT
+#     1.7 kflop => 20.6 kflop.
 FLOP_FX_REF = 1.85e3
 FLOP_PER_UNIT_REF = 39.0e3
-BYTES_PER_UNIT = 48 + 168 + 48 + 24 + 4 + 48 + 168 + 48 + 96 + 40 + 4 + 2   # packed-P SoA layout: 698 B
+FLOP_PREDICT_TILE_REF = 14 * FLOP_FX_REF + 0.07e3 + 0.85e3
+FLOP_UPDATE_TILE_REF = 11.0e3 + 0.07e3 + 0.1e3
+FLOP_FX = 0.86e3
+FLOP_PER_UNIT = 14 * FLOP_FX + 6.9e3 + 1.7e3
+# Algorithmic bytes.  SURVEY 8(d): 920 B per object-step (full 6x6 covariance: read x 48 + P 288 + x_true 48 + z_noise 24,
+# write x 48 + P 288 + x_true 48 + obs 96 + 4 error scalars 32).  The packed-covariance layout used here moves 698 B:
+# read x 48 + P 168 + xt 48 + z_noise 24 + status 4; write x 48 + P 168 + xt 48 + obs 96 + 5 scalars 40 + status 4 + flags 2.
+BYTES_PER_UNIT_REF = 920
+BYTES_PER_UNIT = 48 + 168 + 48 + 24 + 4 + 48 + 168 + 48 + 96 + 40 + 4 + 2
+BYTES_PREDICT_TILE = (48 + 48 + 168) * 2   # k_predict_tile: reads xt, x, U; writes xt, x, P (packed) = 528 B / object
+N_CATALOG = 1_000_000
 CEL2TER06AXY = [+0.973104317697536, +0.230363826239128, -0.000703163481769,
                 -0.230363800456036, +0.973104570632801, +0.000118545368117,
                 +0.000711560162594, +0.000046626402444, +0.999999745754024]
@@ -49,33 +62,36 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c3"])
+    ap.add_argument("--workload", default="c4", choices=["c2", "c4", "c3"])
     ap.add_argument("--envs", type=int, default=4096, help="c3: parallel environments per GPU")
     ap.add_argument("--gather", action="store_true", help="c3, N>1: also all_gather rewards and observations over NCCL every step (a learner on one device)")
     ap.add_argument("--rng", default="device", choices=["device", "host"], help="c3: episodic RNG mode of VecSSATaskerEnv")
-    ap.add_argument("--objects", type=int, default=0, help="override objects per rank")
+    ap.add_argument("--objects", type=int, default=0, help="override the catalog size (c4: whole job, c2: per rank)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short C2 / C3 measurements reported under `extra`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     return ap.parse_args()
 
 
-def workload_inputs(n_objects, rank, steps):
+def workload_inputs(n_objects, rank, steps, lo=0, hi=None):
+    """Synthetic inputs of SURVEY 8(d).  n_objects <= 20000: C2 (the 20 000-orbit catalog, every rank the same
+    workload).  Larger: C4, the catalog tiled to n_objects with RandomState(2) jitter; [lo, hi) selects a rank's
+    contiguous shard of it (every rank draws the same whole-catalog streams and slices, so the job's inputs do not
+    depend on the number of ranks)."""
     from ssa_gym_b200.catalog import synthetic_catalog, tiled_catalog
     from ssa_gym_b200.transformations import arcsec2rad
+    hi = n_objects if hi is None else hi
     if n_objects <= 20000:
-        # C2 is ONE workload (the 20 000-orbit catalog, RandomState(0) filter errors, RandomState(1) noise):
-        # in a weak-scaling run every rank steps that same workload.  With rank-dependent seeds the max-over-ranks
-        # time measured the seeds, not the scaling: a realisation in which a few filter estimates are pushed to
-        # e >= 0.99 sends those sigma points through the literal all-regime propagation, and one such warp in the
-        # last wave of k_fx lengthens a 60 us step by 10-15 us (measured: ranks 2 and 6 of 8 at 75 / 70 us).
         cat = synthetic_catalog(n_objects, seed=0)
-        rank = 0
     else:
-        cat = tiled_catalog(n_objects, synthetic_catalog(20000, 0), seed=2 + rank)
-    x = cat + np.random.RandomState(1000 + rank).normal(size=(n_objects, 6)) * np.array([1e5] * 3 + [1e2] * 3)
+        cat = tiled_catalog(n_objects, synthetic_catalog(20000, 0), seed=2)
+    x = cat + np.random.RandomState(1000).normal(size=(n_objects, 6)) * np.array([1e5] * 3 + [1e2] * 3)
     P0 = np.diag([1e10] * 3 + [1e4] * 3)
-    zn = np.random.RandomState(2000 + rank).normal(size=(steps, n_objects, 3)) * np.array([arcsec2rad, arcsec2rad, 1e3])
-    return cat, x, P0, zn
+    rs = np.random.RandomState(2000)
+    zn = np.empty((steps, hi - lo, 3))
+    for s_ in range(steps):  # slice by slice: the whole-catalog slice is only a temporary
+        zn[s_] = rs.normal(size=(n_objects, 3))[lo:hi] * np.array([arcsec2rad, arcsec2rad, 1e3])
+    return np.ascontiguousarray(cat[lo:hi]), np.ascontiguousarray(x[lo:hi]), P0, zn
 
 
 class ClockSampler:
@@ -214,11 +230,12 @@ def make_cfg(N):
     return c
 
 
-def run_c3(a):
+def c3_measure(a, rank, local_rank, world, steps, warmup, gather):
     """BASELINE.json config 3: E parallel environments x default RSO count, one vectorised env step per call, actions
     from the device-side greedy tasker, obs [E, m*12] fp64 handed to the host every step (the RLlib rollout shape).
     Metric: env-steps per second through the public API (VecSSATaskerEnv.vector_step), i.e. end to end by
-    construction: every step copies the actions host->device and obs / reward / done device->host."""
+    construction: every step copies the actions host->device and obs / reward / done device->host.  Returns the
+    JSON line as a dict (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from ssa_gym_b200 import env_config, _lib as F
@@ -226,13 +243,6 @@ def run_c3(a):
     from ssa_gym_b200.transformations import gcrs2irts_matrix_approx, time_table
     from ssa_gym_b200.ukf import fp64_peak_tflops
     from ssa_gym_b200.vec_env import VecSSATaskerEnv
-    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the UKF hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     E = a.envs
     cfg = dict(env_config)
     cfg["orbits"] = synthetic_catalog(20000, 0)
@@ -243,21 +253,22 @@ def run_c3(a):
     t_construct = time.perf_counter() - t0
     stream = torch.cuda.current_stream()
     sp = ctypes.c_void_p(stream.cuda_stream)
+    multi = world > 1 and gather is not None
 
     def barrier():
-        if world > 1:
+        if multi:
             dist.barrier()
         torch.cuda.synchronize()
 
     # N > 1: what a learner on one device needs - per-env rewards and observations of every rank, gathered
     # with one NCCL all_gather each from the episodic mode's device output block, asynchronously every step
-    rew_view = env.ukf.torch_view(F.F_ROLLOUT_REWARD) if (world > 1 and a.rng == "device" and a.gather) else None
+    rew_view = env.ukf.torch_view(F.F_ROLLOUT_REWARD) if (multi and a.rng == "device" and gather) else None
     obs_view = env.ukf.torch_view(F.F_ROLLOUT_OBS) if rew_view is not None else None
     g_rew = torch.zeros(world * E, dtype=torch.float64, device="cuda") if rew_view is not None else None
     g_obs = torch.zeros((world * E * m, 12), dtype=torch.float64, device="cuda") if rew_view is not None else None
     works = []
     n_done = 0
-    for w in range(max(a.warmup, 3)):
+    for w in range(max(warmup, 3)):
         _, _, d, _ = env.vector_step(env.greedy_actions())
     peak_tf = fp64_peak_tflops(local_rank, sp)
     sampler = ClockSampler(local_rank)
@@ -267,7 +278,8 @@ def run_c3(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     tw0 = time.perf_counter()
-    for s in range(a.steps):
+    r = None
+    for s in range(steps):
         obs, r, d, _ = env.vector_step(env.greedy_actions())
         n_done += int(d.sum())
         if rew_view is not None:
@@ -281,83 +293,217 @@ def run_c3(a):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = env.ukf.launch_count - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
+    nw = world if multi else 1
+    if multi:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    val = E * world * a.steps / (ms * 1e-3)
-    flop_env_step = m * (14 * FLOP_FX + 2.0e3) + 6.9e3   # m predicts (14 fx + factorisations/UT) + one update
+        ms = float(t.item())
+    val = E * nw * steps / (ms * 1e-3)
+    flop_env_step = m * (14 * FLOP_FX_REF + 1.7e3) + 11.0e3   # m predicts (14 fx + factorisations / UT) + one update, SURVEY 8(d)
+    line = None
     if rank == 0:
         line = {"metric": "env-steps per second (vectorised ssa_tasker_simple_2, RL mode)", "value": val, "unit": "env-steps/s",
-                "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps,
+                "n_gpus": nw, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms / steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"C3: {E} parallel envs x {m} RSOs per GPU, vector_step + device greedy tasker, obs to host",
                            "envs_per_gpu": E, "rso_count": m, "episode_steps": cfg["steps"], "rng": a.rng, "reward_type": cfg["reward_type"],
                            "l2": f"inputs/outputs larger than nothing to flush: every step moves {E * m * 12 * 8} B of fresh obs over PCIe"},
                 "object_predicts_per_s": val * m,
                 "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * E,
-                        "d2h_bytes_per_step": E * m * 12 * 8 + E * 8 + E * 16 + E, "ms_per_step": ms / a.steps,
+                        "d2h_bytes_per_step": E * m * 12 * 8 + E * 8 + E * 16 + E, "ms_per_step": ms / steps,
                         "api": "VecSSATaskerEnv.vector_step (ssa_ukf_rollout_step)" if a.rng == "device" else "VecSSATaskerEnv.vector_step"},
-                "roofline": {"bound": "fp64", "kernel": "whole env step", "achieved": val / world * flop_env_step / 1e12, "peak": peak_tf,
-                             "unit": "TFLOP/s", "frac": val / world * flop_env_step / 1e12 / peak_tf, "traffic": None,
-                             "note": "RL-mode step = m predicts + 1 update per env; at E*m = 40960 objects the step is launch/latency and "
-                                     "PCIe bound, not FP64 bound"},
+                "roofline": {"bound": "fp64", "kernel": "whole env step", "achieved": val / nw * flop_env_step / 1e12, "peak": peak_tf,
+                             "unit": "TFLOP/s", "frac": val / nw * flop_env_step / 1e12 / peak_tf, "traffic": None,
+                             "note": "RL-mode step = m predicts + 1 update per env (SURVEY 8d: 287 kflop at m = 10); at E*m = 40960 "
+                                     "objects the step is launch/latency and PCIe bound, not FP64 bound"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "extra": {"episodes_finished_in_timed_region": n_done, "construct_and_first_reset_s": t_construct,
                           "nccl_gather_per_step": (None if rew_view is None else
                                                    {"reward_bytes_per_rank": 8 * E, "obs_bytes_per_rank": 96 * E * m,
                                                     "gathered_reward_matches_rank0": bool(np.array_equal(g_rew[:E].cpu().numpy(), r))}),
                           "wall_s_timed_region": t_wall}}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    env.close() if hasattr(env, "close") else None
+    return line
+
+
+def c2_measure(local_rank, steps, warmup):
+    """BASELINE.json config 2 on THIS rank's GPU: the 20 000-orbit catalog, every object predicted and updated once per
+    step; per-step CUDA events, L2 flushed between steps.  Returns a small dict."""
+    import torch
+    from ssa_gym_b200 import _lib as F
+    from ssa_gym_b200.ukf import BatchedUKF
+    n = 20000
+    cat, x, P0, zn = workload_inputs(n, 0, 4)
+    cfg = make_cfg(n)
+    ukf = BatchedUKF(n_envs=1, m=n, dt=20.0, Q=np.array(cfg.Q).reshape(6, 6), R=np.array(cfg.R).reshape(3, 3),
+                     obs_lla=[np.radians(38.828198), np.radians(-77.305352), 20.0], obs_limit_rad=np.radians(-90.0),
+                     device=local_rank)
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    ukf.reset(cat, x, P0, stream=sp)
+    M = np.array(CEL2TER06AXY)
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE
+    zn_dev = torch.from_numpy(zn).cuda()
+    zview = ukf.torch_view(F.F_Z_NOISE)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for w in range(max(warmup, 3)):
+        zview.copy_(zn_dev[w % 4], non_blocking=True)
+        ukf.step(M, flags, stream=sp)
+    torch.cuda.synchronize()
+    l0 = ukf.launch_count
+    evs = []
+    for s in range(steps):
+        zview.copy_(zn_dev[s % 4], non_blocking=True)
+        flush.fill_(s & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ukf.step(M, flags, stream=sp)
+        e1.record(stream)
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in evs]))
+    out = {"workload": "C2: 20000-orbit catalog on one GPU, UKF predict+update of every object per step",
+           "value": n / (ms * 1e-3), "unit": "object-updates/s", "ms_per_step": ms, "steps": steps,
+           "gpu_launches": int(ukf.launch_count - l0), "failed_filters": int((ukf.download(F.F_STATUS) & 1).sum()),
+           "l2": "flushed between timed steps (256 MiB write)"}
+    ukf.close()
+    del flush
+    return out
+
+
+def python_reference_style_baseline(seconds):
+    """the reference's own execution style — one filterpy-shaped UKF object per RSO driven by
+    Python loops (numpy restatement of filterpy, oracle/filterpy_restated.py; fx / hx evaluated per call through the C
+    oracle, as the reference calls its numba functions), first in ONE process (how the reference runs an env), then one
+    worker process per host core (its only parallelism: one env per Ray worker, rl_agents/RLLib_PPO_training.py:17)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    one = _python_style_worker((0, seconds / 2))
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_python_style_worker, [(i + 1, seconds / 2) for i in range(cores)])
+    return {"single_process": {"value": one[0] / one[1], "unit": "object-updates/s", "cores": 1, "object_updates": one[0], "seconds": one[1]},
+            "one_env_per_core": {"value": float(sum(r[0] / r[1] for r in res)), "unit": "object-updates/s", "cores": cores,
+                                 "object_updates": int(sum(r[0] for r in res))},
+            "kind": "port", "what": "numpy restatement of filterpy's UnscentedKalmanFilter (predict + update per object in a "
+                                    "Python loop, m = 10 objects per env, default env_config), fx / hx per call through oracle/liboracle.so"}
+
+
+def _python_style_worker(arg):
+    seed, seconds = arg
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import dynamics_restated as D
+    from oracle.env_oracle import OracleEnv
+    from ssa_gym_b200 import env_config
+    from ssa_gym_b200.catalog import synthetic_catalog
+    from ssa_gym_b200.transformations import gcrs2irts_matrix_approx, time_table
+    oracle_lib()
+    cfg = dict(env_config)
+    cfg["orbits"] = synthetic_catalog(2000, 0)
+    cfg["reward_type"] = "trinary"   # 'jones' ends an episode within a handful of steps; the filter work per step is the same
+    tm = gcrs2irts_matrix_approx(time_table(cfg["t_0"], cfg["time_step"], cfg["steps"]))
+    env = OracleEnv(cfg, D.oracle_fx_callable(), tm)
+    env.seed(seed)
+    env.reset()
+    t0 = time.perf_counter()
+    n = 0
+    k = 0
+    while time.perf_counter() - t0 < seconds:
+        _, _, done, _ = env.step(k % env.m)
+        k += 1
+        n += env.m   # m predicts (+ one update) per env step, counted as m object-updates: generous to this baseline
+        if done:
+            env.reset()
+    return n, time.perf_counter() - t0
 
 
 def main():
     a = parse()
-    if a.workload == "c3" and a.impl != "reference":
-        return run_c3(a)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    n_obj = a.objects or (20000 if a.workload == "c2" else 1_000_000 // max(world, 1))
-    wl_name = ("C2: 20000-orbit catalog per GPU, UKF predict+update of every object per step" if a.workload == "c2"
-               else f"C4: 1M-object catalog sharded over {world} GPU(s), {n_obj} objects per rank, per-step UKF + shard reward "
-                    f"terms + NCCL all_gather of them")
-    config = {"workload": wl_name, "objects_per_gpu": n_obj, "dt_s": 20.0, "obs_type": "aer",
-              "sigma_points": "merwe alpha=1e-4 beta=2 kappa=-3", "trans_matrix": "SOFA Cel2Ter06aXY (tests.py:107-109)",
-              "l2": "flushed between timed steps (256 MiB write)"}
+    if a.gpus != world:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit(f"bench.py --gpus {a.gpus}: launch one rank per GPU, e.g. python -m torch.distributed.run --nnodes=1 "
+                             f"--nproc-per-node {a.gpus} --master-addr 127.0.0.1 bench.py --gpus {a.gpus} ...")
+        raise SystemExit(f"bench.py: --gpus {a.gpus} does not match WORLD_SIZE {world}")
 
     if a.impl == "reference":
-        if rank != 0:
-            return 0
-        cat, x, P0, zn = workload_inputs(n_obj, 0, max(a.steps, 1) + 1)
-        cfg = make_cfg(n_obj)
-        for w in range(max(a.warmup, 0)):
-            pass
-        val, done, threads, dt = run_oracle_steps(cfg, cat, x, P0, zn, a.steps)
-        line = {"impl": "reference", "metric": "RSO UKF predict+update per second", "value": val, "unit": "object-updates/s",
-                "n_gpus": a.gpus, "steps": done, "warmup": a.warmup, "ms_per_step": dt / done * 1e3, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": "object-updates/s", "cores": threads, "kind": "port",
-                                 "sample": f"{done} steps x {n_obj} objects (the full per-GPU batch), oracle/ukf_oracle.c, OpenMP"},
-                "e2e": {"value": val, "unit": "object-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
+        return run_reference_arm(a, rank, world)
 
     import torch
     import torch.distributed as dist
-    from ssa_gym_b200 import _lib
-    from ssa_gym_b200.ukf import BatchedUKF, fp64_peak_tflops
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the UKF hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        if a.workload == "c3":
+            line = c3_measure(a, rank, local_rank, world, a.steps, a.warmup, a.gather)
+            if rank == 0:
+                print(json.dumps(line))
+        else:
+            run_catalog(a, rank, local_rank, world)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+    return 0
 
+
+def catalog_layout(a, world, rank):
+    """(total objects of the job, this rank's [lo, hi), workload name, scaling)"""
+    from ssa_gym_b200.dist import shard_bounds
+    if a.workload == "c2":
+        n = a.objects or 20000
+        return n * world, 0, n, f"C2: {n}-orbit catalog per GPU, UKF predict+update of every object per step", "weak"
+    total = a.objects or N_CATALOG
+    lo, hi = shard_bounds(total, world, rank)
+    name = (f"C4: {total}-object synthetic catalog sharded over {world} GPU(s) in contiguous blocks, per-step UKF predict+update of "
+            f"every object + shard reward terms (ssa_ukf_catalog_stats) + NCCL all_gather of them, all inside the timed events")
+    return total, lo, hi, name, "strong"
+
+
+def run_reference_arm(a, rank, world):
+    """The reference's CPU implementation of the path on the box's host cores: the oracle port (the reference is pure
+    Python around filterpy and cannot be installed offline), all host threads, a bounded sample of the arm's workload."""
+    if rank != 0:
+        return 0
+    total, _, _, name, scaling = catalog_layout(a, world, 0)
+    n_s = min(total, 200_000)   # bounded sample: the first 200 000 objects of the catalog (a step of the whole 1M takes ~0.5 s)
+    cat, x, P0, zn = workload_inputs(total, 0, 4, 0, n_s)
+    cfg = make_cfg(n_s)
+    for w in range(max(a.warmup, 1)):   # warm-up passes: page-in, OpenMP thread pool, clocks
+        run_oracle_steps(cfg, cat, x, P0, zn, 1)
+    val, done, threads, dt = run_oracle_steps(cfg, cat, x, P0, zn, a.steps, budget_s=120.0)
+    line = {"impl": "reference", "metric": "RSO UKF predict+update per second", "value": val, "unit": "object-updates/s",
+            "n_gpus": a.gpus, "steps": done, "warmup": max(a.warmup, 1), "ms_per_step": dt / done * 1e3 * (total / n_s),
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "objects_total": total, "dt_s": 20.0, "obs_type": "aer",
+                       "sigma_points": "merwe alpha=1e-4 beta=2 kappa=-3", "trans_matrix": "SOFA Cel2Ter06aXY (tests.py:107-109)"},
+            "cpu_baseline": {"value": val, "unit": "object-updates/s", "cores": threads, "kind": "port",
+                             "sample": f"{done} steps x the first {n_s} objects of the {total}-object catalog, oracle/ukf_oracle.c "
+                                       f"(reference operation order, libm), OpenMP over {threads} host threads; ms_per_step is scaled to the whole catalog"},
+            "e2e": {"value": val, "unit": "object-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def run_catalog(a, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from ssa_gym_b200 import _lib
+    from ssa_gym_b200.ukf import BatchedUKF, fp64_peak_tflops
     F = _lib
-    cat, x, P0, zn = workload_inputs(n_obj, rank, 8)
+    total, lo, hi, wl_name, scaling = catalog_layout(a, world, rank)
+    n_obj = hi - lo
+    c4 = a.workload == "c4"
+    config = {"workload": wl_name, "objects_total": total, "objects_per_gpu": n_obj, "dt_s": 20.0, "obs_type": "aer",
+              "sigma_points": "merwe alpha=1e-4 beta=2 kappa=-3", "trans_matrix": "SOFA Cel2Ter06aXY (tests.py:107-109)",
+              "l2": "flushed between timed steps (256 MiB write)"}
+    if c4:
+        cat, x, P0, zn = workload_inputs(total, rank, 8, lo, hi)
+    else:
+        cat, x, P0, zn = workload_inputs(n_obj, rank, 8)
     cfg = make_cfg(n_obj)
     ukf = BatchedUKF(n_envs=1, m=n_obj, dt=20.0, Q=np.array(cfg.Q).reshape(6, 6), R=np.array(cfg.R).reshape(3, 3),
                      obs_lla=[np.radians(38.828198), np.radians(-77.305352), 20.0], obs_limit_rad=np.radians(-90.0),
@@ -381,29 +527,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # C4 (BASELINE.json config 4: "per-step UKF + reward, NCCL gather of rewards"): every step reduces the shard's reward
+    # terms on the device (ssa_ukf_catalog_stats: 2 small kernels) and all-gathers the 5 doubles per rank over NCCL.
+    # The collective is enqueued stream-ordered (async_op=False makes the launching stream wait for it), so the step's
+    # closing event is recorded after the gather has completed: the gather is inside every step's timed interval.
+    gathered = torch.zeros(world * 5, dtype=torch.float64, device="cuda") if c4 else None
+    stats_view = None
+    if c4:
+        ukf.catalog_stats(index_offset=lo, stream=sp)
+        stats_view = ukf.torch_view(F.F_CATALOG_STATS)
+
+    def reward_gather():
+        ukf.catalog_stats(index_offset=lo, stream=sp)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, stats_view)
+        else:
+            gathered.copy_(stats_view, non_blocking=True)
+
     # ---- warm-up -----------------------------------------------------------------------------------
     for w in range(max(a.warmup, 3)):
         load_noise(w)
         ukf.step(M, flags, stream=sp)
+        if c4:
+            reward_gather()
     torch.cuda.synchronize()
     peak_tf = fp64_peak_tflops(local_rank, sp)
-
-    # C4 (BASELINE.json config 4: "per-step UKF + reward, NCCL gather of rewards"): every step also reduces the shard's
-    # reward terms on the device (ssa_ukf_catalog_stats) and all-gathers the 5 doubles per rank over NCCL,
-    # asynchronously (the next step does not wait for it); the gathered values are checked after the timed region.
-    c4_gather = (a.workload == "c4")
-    gathered, works = None, []
-    if c4_gather:
-        ukf.catalog_stats(index_offset=rank * n_obj, stream=sp)
-        stats_view = ukf.torch_view(F.F_CATALOG_STATS)
-        gathered = torch.zeros(world * 5, dtype=torch.float64, device="cuda")
-
-    def reward_gather():
-        ukf.catalog_stats(index_offset=rank * n_obj, stream=sp)
-        if world > 1:
-            works.append(dist.all_gather_into_tensor(gathered, stats_view, async_op=True))
-        else:
-            gathered.copy_(stats_view, non_blocking=True)
 
     # ---- timed: exactly K steps, per-step CUDA events on the launching stream, L2 flushed between steps ---
     sampler = ClockSampler(local_rank)
@@ -418,12 +566,10 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         ukf.step(M, flags, stream=sp)
-        if c4_gather:
+        if c4:
             reward_gather()
         e1.record(stream)
         evs.append((e0, e1))
-    for w_ in works:
-        w_.wait()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
@@ -432,15 +578,18 @@ def main():
     status = ukf.download(F.F_STATUS)
     n_failed = int((status & 1).sum())
     c4_check = None
-    if c4_gather:  # the gathered shard terms of the LAST timed step against a host recomputation of this rank's shard
+    if c4:  # the gathered shard terms of the LAST timed step against a host recomputation of this rank's shard
         g = gathered.cpu().numpy().reshape(world, 5)
         dpos_h, tr_h = ukf.download(F.F_DELTA_POS), ukf.download(F.F_TRACE)
         mine = g[rank]
-        assert mine[0] == dpos_h.max() and mine[2] == n_obj and mine[3] == tr_h.max() and mine[4] == rank * n_obj + int(np.argmax(tr_h))
+        assert mine[0] == dpos_h.max() and mine[2] == n_obj and mine[3] == tr_h.max() and mine[4] == lo + int(np.argmax(tr_h))
         assert mine[1] == float(((dpos_h < 1e4).astype(int) + (dpos_h < 1e7).astype(int)).sum())
+        assert g[:, 2].sum() == total
         best = int(np.argmax(g[:, 3]))
         c4_check = {"max_delta_pos_m": float(g[:, 0].max()), "trinary_reward": float(g[:, 1].sum() / g[:, 2].sum() / 2),
-                    "argmax_trace_object": int(g[best, 4]), "gathered_ranks": int(world)}
+                    "argmax_trace_object": int(g[best, 4]), "gathered_ranks": int(world), "objects_gathered": int(g[:, 2].sum()),
+                    "bytes_per_rank_per_step": 40, "in_timed_events": True,
+                    "checked": "every rank's gathered row of the last step == host recomputation from its downloaded shard"}
 
     # per-kernel durations of the step (CUDA events between the launches, L2 flushed before each step)
     kms = []
@@ -457,6 +606,8 @@ def main():
     e0.record(stream)
     for s in range(a.steps):
         ukf.step(M, flags, stream=sp)
+        if c4:
+            reward_gather()
     e1.record(stream)
     barrier()
     b2b_ms = e0.elapsed_time(e1) / a.steps
@@ -464,7 +615,7 @@ def main():
     # ---- e2e: the user-facing call with HOST buffers: every step ONE H2D copy of that step's inputs (z_noise +
     # trans_matrix) from the handle's pinned input block, the kernel chain (one captured graph launch), ONE D2H copy
     # of obs / delta_pos / status into the pinned output block (ssa_ukf_step_pinned: double-buffered, the copies
-    # overlap the neighbouring steps' kernels).  The two pinned input blocks hold two of the pre-drawn noise slices.
+    # overlap the neighbouring steps' kernels); C4 adds the shard reward terms + their NCCL gather every step.
     io = ukf.host_io()
     for b_ in range(2):
         io[b_]["z_noise"][:] = zn[b_]
@@ -480,6 +631,8 @@ def main():
         b_ = ukf.next_parity
         io[b_]["M"][:] = M.reshape(9)  # this step's trans_matrix[i] (72 B) travels with the noise
         ukf.step_pinned(flags, stream=sp)
+        if c4 and world > 1:
+            reward_gather()
     ukf.host_join(stream=sp)
     e1.record(stream)
     barrier()
@@ -492,18 +645,38 @@ def main():
     d2h = io[0]["obs"].nbytes + (ukf.ld + ukf.ld // 2) * 8
 
     # ---- reduce over ranks (max time) --------------------------------------------------------------
-    t = torch.tensor([total_ms, b2b_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, b2b_ms, e2e_ms] + [float(v) for v in kms], dtype=torch.float64, device="cuda")
     per_rank = [total_ms / a.steps]
     if world > 1:
         allr = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allr, t)
         per_rank = [float(r_[0]) / a.steps for r_ in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, b2b_ms, e2e_ms = [float(v) for v in t.tolist()]
+    tl = [float(v) for v in t.tolist()]
+    total_ms, b2b_ms, e2e_ms = tl[:3]
+    kms = np.array(tl[3:])
     ms_per_step = total_ms / a.steps
-    units = n_obj * world
+    units = total
     value = units / (ms_per_step * 1e-3)
     e2e_val = units / (e2e_ms * 1e-3)
+
+    # ---- short C2 / C3 sub-measurements on rank 0 (the other ranks wait) ---------------------------------------
+    extra_c2 = extra_c3 = None
+    tile = os.environ.get("SSA_UKF_KERNEL", "tile") not in ("split", "team")
+    if rank == 0 and not a.no_extra:
+        ukf_mem_free = None
+        try:
+            if a.workload != "c2":
+                extra_c2 = c2_measure(local_rank, 50, 5)
+            import copy
+            a3 = copy.copy(a)
+            l3 = c3_measure(a3, 0, local_rank, 1, 30, 5, None)
+            extra_c3 = {k: l3[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "object_predicts_per_s")}
+            extra_c3["workload"] = l3["config"]["workload"]
+            extra_c3["e2e_bytes_per_step"] = {"h2d": l3["e2e"]["h2d_bytes_per_step"], "d2h": l3["e2e"]["d2h_bytes_per_step"]}
+        except Exception as ex:  # the headline must not be lost to a failure of an extra
+            extra_c3 = {"error": repr(ex)}
+    barrier()
 
     if rank == 0:
         peaks = {}
@@ -513,62 +686,82 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         kern_ms = float(np.mean(step_ms))
-        ach_tf = FLOP_PER_UNIT * n_obj / (kern_ms * 1e-3) / 1e12
-        ach_gb = BYTES_PER_UNIT * n_obj / (kern_ms * 1e-3) / 1e9
         team = os.environ.get("SSA_UKF_KERNEL") == "team"
-        # dominant kernel: k_fx = 14 fx per object x 1.85 kflop = 25.9 kflop per object per launch
-        fx_ms = float(kms[0] if team else kms[1])
-        fx_flop = (FLOP_PER_UNIT if team else 14 * FLOP_FX) * n_obj
-        fx_tf = fx_flop / (fx_ms * 1e-3) / 1e12
-        fx_tf_ref = (FLOP_PER_UNIT_REF if team else 14 * FLOP_FX_REF) * n_obj / (fx_ms * 1e-3) / 1e12
-        traffic = None  # DRAM bytes per k_fx launch from the committed `ncu --set full` capture of this command
+        # dominant kernel: k_predict_tile (14 two-body propagations + unscented transform per object); split pipeline: k_fx
+        dom_ms = float(kms[0] if team else kms[1])
+        dom_name = "ssa_step_kernel" if team else ("k_predict_tile" if tile else "k_fx")
+        dom_flop_ref = (FLOP_PER_UNIT_REF if team else (FLOP_PREDICT_TILE_REF if tile else 14 * FLOP_FX_REF)) * n_obj
+        dom_flop_impl = (FLOP_PER_UNIT if team else (14 * FLOP_FX + (0.9e3 if tile else 0.0))) * n_obj
+        dom_tf = dom_flop_ref / (dom_ms * 1e-3) / 1e12
+        # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at this shard size
+        traffic = traffic_step = None
         try:
-            if a.workload == "c2" and not a.objects and not team:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_e_ncu_full_c2_kernels.json")))["k_fx"]["dram_bytes_per_launch"]
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_kernels.json")))
+            ent = cap.get(str(n_obj))
+            if ent and tile and not team:
+                traffic = ent["k_predict_tile"]["dram_bytes_per_launch"]
+                traffic_step = sum(v["dram_bytes_per_launch"] for v in ent.values() if isinstance(v, dict) and "dram_bytes_per_launch" in v)
         except Exception:
-            traffic = None
+            pass
+        step_tf = FLOP_PER_UNIT_REF * n_obj / (kern_ms * 1e-3) / 1e12
+        step_gb = BYTES_PER_UNIT_REF * n_obj / (kern_ms * 1e-3) / 1e9
         line = {
             "metric": "RSO UKF predict+update per second", "value": value, "unit": "object-updates/s",
             "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
-            "roofline": {"bound": "fp64", "kernel": "ssa_step_kernel" if team else "k_fx",
-                         "achieved": fx_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": fx_tf / peak_tf,
-                         "traffic": traffic, "algorithmic_bytes": 936 * n_obj, "kernel_ms": fx_ms, "kernel_share_of_step": fx_ms / float(np.sum(kms)),
-                         "step_kernels_ms": {"factor": float(kms[0]), "fx": float(kms[1]), "ut": float(kms[2]),
-                                             "hx": float(kms[3]), "update": float(kms[4])},
-                         "frac_reference_algorithm": fx_tf_ref / peak_tf,
-                         "whole_step": {"achieved": ach_tf, "frac": ach_tf / peak_tf, "flop_per_object": FLOP_PER_UNIT,
-                                        "frac_reference_algorithm": ach_tf * FLOP_PER_UNIT_REF / FLOP_PER_UNIT / peak_tf},
-                         "note": "dominant kernel k_fx (14 two-body propagations per object): achieved = 14 x 0.90 kflop "
-                                 "(the streamlined fx as implemented, SURVEY 8d counting convention) x objects / mean "
-                                 "CUDA-event duration of that kernel; frac_reference_algorithm prices the same launch at "
-                                 "the reference's literal 1.85 kflop per fx / 39 kflop per unit; peak = DFMA microbenchmark "
-                                 "measured live in this run (ssa_ukf_fp64_peak; FP64 is not in MEASURED_PEAKS.json) - "
-                                 "'of measured'; whole_step = all 5 kernels, 21.2 kflop/object",
-                         "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
-                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"}},
+            "roofline": {"bound": "fp64", "kernel": dom_name, "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": dom_tf / peak_tf, "traffic": traffic,
+                         "algorithmic_flop_per_launch": dom_flop_ref, "algorithmic_bytes_per_launch": BYTES_PREDICT_TILE * n_obj if tile else None,
+                         "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / float(np.sum(kms)),
+                         "frac_as_implemented": dom_flop_impl / (dom_ms * 1e-3) / 1e12 / peak_tf,
+                         "step_kernels_ms": ({"k_factor": float(kms[0]), "k_predict_tile": float(kms[1]), "k_refactor": float(kms[2]),
+                                              "k_update_tile": float(kms[4])} if tile and not team else
+                                             {"factor": float(kms[0]), "fx": float(kms[1]), "ut": float(kms[2]), "hx": float(kms[3]),
+                                              "update": float(kms[4])}),
+                         "whole_step": {"achieved": step_tf, "frac": step_tf / peak_tf, "flop_per_object": FLOP_PER_UNIT_REF,
+                                        "frac_as_implemented": step_tf * FLOP_PER_UNIT / FLOP_PER_UNIT_REF / peak_tf,
+                                        "algorithmic_bytes": BYTES_PER_UNIT_REF * n_obj, "traffic": traffic_step,
+                                        "hbm": {"achieved": step_gb, "peak": hbm_peak, "unit": "GB/s", "frac": step_gb / hbm_peak,
+                                                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"}},
+                         "note": "SURVEY 8(d) counting (div = sqrt = 10, sin = cos = 40, atan2 = 80 flop ...): dominant kernel "
+                                 "k_predict_tile = 14 fx x 1.85 kflop + sigma draw + unscented transform = 26.8 kflop per object per launch, "
+                                 "divided by the mean CUDA-event duration of that kernel in this run (per rank: its shard); whole_step = "
+                                 "39 kflop and 920 B per object over the mean step; frac_as_implemented prices the streamlined arithmetic "
+                                 "actually executed (20.6 kflop per object); peak = DFMA microbenchmark measured live in this run "
+                                 "(ssa_ukf_fp64_peak; FP64 is not in MEASURED_PEAKS.json); traffic = DRAM bytes of the kernel / of the "
+                                 "step's kernels from the committed ncu capture (profiles/r02_ncu_kernels.json) when one exists for this shard size"},
             "e2e": {"value": e2e_val, "unit": "object-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "gpu_launches": int(e2e_launches),
-                    "api": "BatchedUKF.step_pinned (ssa_ukf_step_pinned): pinned host I/O blocks, 1 H2D + 1 graph launch + 1 D2H per step",
+                    "ms_per_step": e2e_ms, "gpu_launches": int(e2e_launches), "bytes_are": "per rank",
+                    "api": "BatchedUKF.step_pinned (ssa_ukf_step_pinned): pinned host I/O blocks, 1 H2D + 1 graph launch + 1 D2H per step"
+                           + (" + shard reward terms + NCCL all_gather" if (c4 and world > 1) else ""),
+                    "limiter": f"PCIe / host memory: every step moves {(h2d + d2h) * world / 1e6:.1f} MB between the GPUs and pinned host "
+                               f"memory ({(h2d + d2h) * world / (e2e_ms * 1e-3) / 1e9:.1f} GB/s aggregate), the kernels alone need {ms_per_step:.3f} ms",
                     "l2": "not flushed: the filter state is device-resident between steps by design; every step's inputs arrive "
                           "from pinned host memory and its outputs leave to pinned host memory inside the timed region"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "extra": {"ms_per_step_back_to_back_no_flush": b2b_ms, "wall_s_timed_region": t_wall, "failed_filters": n_failed,
                       "ms_per_step_of_each_rank": per_rank, "c4_reward_gather": c4_check,
-                      "step_ms_min": float(np.min(step_ms)), "step_ms_max": float(np.max(step_ms))},
+                      "step_ms_min": float(np.min(step_ms)), "step_ms_max": float(np.max(step_ms)),
+                      "c2": extra_c2, "c3": extra_c3},
         }
-        if not a.no_cpu_baseline:
-            catc, xc, P0c, znc = workload_inputs(n_obj, 0, 4)
-            val, done, threads, dtc = run_oracle_steps(cfg, catc, xc, P0c, znc, 10 ** 6, budget_s=a.cpu_seconds)
+        if not a.no_cpu_baseline and world >= 1:
+            n_s = min(n_obj, 200_000)
+            if c4:
+                catc, xc, P0c, znc = workload_inputs(total, 0, 4, 0, n_s)
+            else:
+                catc, xc, P0c, znc = workload_inputs(n_s, 0, 4)
+            val, done, threads, dtc = run_oracle_steps(make_cfg(n_s), catc, xc, P0c, znc, 10 ** 6, budget_s=a.cpu_seconds)
             line["cpu_baseline"] = {"value": val, "unit": "object-updates/s", "cores": threads, "kind": "port",
-                                    "sample": f"{done} steps x {n_obj} objects in {dtc:.1f} s, oracle/ukf_oracle.c (reference "
-                                              f"operation order, libm), OpenMP over host threads"}
+                                    "sample": f"{done} steps x the first {n_s} objects of the catalog in {dtc:.1f} s, oracle/ukf_oracle.c "
+                                              f"(reference operation order, libm), OpenMP over host threads"}
+            try:
+                line["cpu_baseline"]["reference_style_python"] = python_reference_style_baseline(a.cpu_seconds)
+            except Exception as ex:
+                line["cpu_baseline"]["reference_style_python"] = {"error": repr(ex)}
         print(json.dumps(line))
     ukf.close()
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 
