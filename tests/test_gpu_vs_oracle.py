@@ -68,6 +68,22 @@ def test_fused_step_c2_against_oracle():
             assert np.array_equal(ukf.download(F.F_STATUS), so.status)
             zt = ukf.download(F.F_Z_TRUE)
             assert np.max(np.abs(zt[:, :2] - so.z_true[:, :2])) < 1e-11 and np.max(np.abs(zt[:, 2] - so.z_true[:, 2]) / so.z_true[:, 2]) < 1e-12
+        # covariance, innovation covariance, innovation: dimensionless (P by sqrt(P_ii P_jj), S likewise, y in sigmas).
+        # The bounds are the conditioning of the reference's own filter, not a choice: against exact arithmetic its
+        # double-precision run is off by 1e-4 (median) in a covariance after the first 1-arcsec update and by O(1) in the
+        # worst element (tests/test_exact_truth.py); two faithful builds of its formulas differ by the same amounts.
+        Pg, Sg, yg = ukf.download(F.F_P_FILTER), ukf.download(F.F_S), ukf.download(F.F_Y)
+        d = np.sqrt(np.abs(np.einsum("nii->ni", so.P)))
+        eP = np.abs(Pg - so.P) / (d[:, :, None] * d[:, None, :])
+        dS = np.sqrt(np.einsum("nii->ni", so.S))
+        eS, ey = np.abs(Sg - so.S) / (dS[:, :, None] * dS[:, None, :]), np.abs(yg - so.y) / dS
+        lim = {0: (1e-5, 3e-2, 1e-6, 1e-4), 1: (1e-3, 1e-1, 1e-3, 1e-2)}[s]
+        assert np.median(eP) < lim[0] and np.quantile(eP, 0.99) < lim[1], (s, np.median(eP), np.quantile(eP, 0.99))
+        assert np.median(eS) < lim[2] and np.median(ey) < lim[3], (s, np.median(eS), np.median(ey))
+        # K is not an output; x = x_pred + K y pins it: the updated state within the same envelope
+        xg_s = ukf.download(F.F_X_FILTER)
+        ex = np.abs(xg_s[:, :3] - so.x[:, :3]) / np.linalg.norm(so.x_true[:, :3], axis=1)[:, None]
+        assert np.median(ex) < (1e-7 if s == 0 else 1e-6), (s, np.median(ex))
     assert (ukf.download(F.F_STATUS) & 1).sum() == 0
     assert abs(np.median(ukf.download(F.F_DELTA_POS)) / np.median(so.dpos) - 1) < 0.05
     ukf.close()
