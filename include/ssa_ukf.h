@@ -109,7 +109,9 @@ enum ssa_field {
 #define SSA_TASKER_VISIBLE_GREEDY 1   /* argmax trace P over visible objects       agents.py:35-42 */
 #define SSA_TASKER_POS_ERROR_GREEDY 2 /* argmax delta_pos over visible objects     agents.py:66-72 */
 #define SSA_TASKER_VEL_ERROR_GREEDY 3 /* argmax delta_vel over visible objects     agents.py:75-81 */
-#define SSA_N_TASKERS 4
+#define SSA_TASKER_VISIBLE_GREEDY_AER 4 /* argmax of the 'aer' observation's trace column (nan/inf -> 0.001) over visible objects  agents.py:57-63 */
+#define SSA_TASKER_SHANNON 5          /* argmax log(det P_i / det P_{i-1}) over visible objects   agents.py:15-26 */
+#define SSA_N_TASKERS 6
 /* a visible-* tasker returns -1 when the reference would fall back to action_space.sample()
  * (`not np.any(visible)` — also true when the only visible index is 0, agents.py:37).            */
 
@@ -233,6 +235,11 @@ int ssa_ukf_catalog_stats(ssa_ukf* h, long index_offset, void* stream);
  * (SS2:436-446 anees), and for the objects updated by the last step run with SSA_STEP_RECORD the NIS
  * y^T S^-1 y (SS2:564-569) and the innovation-bound flags (SS2:598-604) -> SSA_F_DIAG, SSA_F_INNOV_FLAGS.      */
 int ssa_ukf_diagnostics(ssa_ukf* h, void* stream);
+/* Innovation whiteness statistics of B innovation series: y [n_series][n][3] with a validity mask
+ * valid [n_series][n] (an observation was taken at that step / the object was the tasked one), host buffers in and out.
+ *   dw  [n_series][3]            Durbin-Watson statistic over the valid entries in order     SS2:782-832 innovation_dw_test
+ *   acf [n_series][3][nlags+1]   autocorrelation, statsmodels acf(missing='conservative')    SS2:655-668 autocorrelation    */
+int ssa_innovation_stats(const double* y, const uint8_t* valid, int n_series, int n, int nlags, double* dw, double* acf, int device);
 
 int ssa_ukf_sync(ssa_ukf* h, void* stream);
 /* number of kernel launches issued through this handle so far (bench.py `gpu_launches`) */

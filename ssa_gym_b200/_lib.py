@@ -18,8 +18,9 @@ REWARD_JONES, REWARD_TRINARY, REWARD_SHAPED = 0, 1, 2
 ST_FAILED, ST_LINALG, ST_NAN, ST_FXEXC, ST_TRUTHEXC, ST_IN_UPDATE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 STEP_TRUTH, STEP_PREDICT, STEP_UPDATE_ALL, STEP_UPDATE_ACT, STEP_EPILOGUE, STEP_RECORD = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 STEP_M_PER_ENV = 0x40
-N_TASKERS = 4
-TASKER_NAIVE_GREEDY, TASKER_VISIBLE_GREEDY, TASKER_POS_ERROR_GREEDY, TASKER_VEL_ERROR_GREEDY = 0, 1, 2, 3
+N_TASKERS = 6
+(TASKER_NAIVE_GREEDY, TASKER_VISIBLE_GREEDY, TASKER_POS_ERROR_GREEDY, TASKER_VEL_ERROR_GREEDY, TASKER_VISIBLE_GREEDY_AER,
+ TASKER_SHANNON) = range(6)
 
 (F_X_TRUE, F_X_FILTER, F_P_FILTER, F_OBS, F_DELTA_POS, F_DELTA_VEL, F_SIGMA_POS, F_SIGMA_VEL, F_TRACE,
  F_Z_TRUE, F_Y, F_S, F_SIGMAS_H, F_Z_NOISE, F_VISIBLE, F_STATUS, F_INFLATIONS, F_ACTIONS, F_REWARD, F_DONE,
@@ -70,6 +71,7 @@ PROTOTYPES = {
     "ssa_ukf_scores": (_I, [c_void_p, c_void_p]),
     "ssa_ukf_diagnostics": (_I, [c_void_p, c_void_p]),
     "ssa_ukf_catalog_stats": (_I, [c_void_p, _L, c_void_p]),
+    "ssa_innovation_stats": (_I, [c_void_p, c_void_p, _I, _I, _I, c_void_p, c_void_p, _I]),
     "ssa_ukf_snapshot_bytes": (ctypes.c_size_t, [c_void_p]),
     "ssa_ukf_snapshot": (_I, [c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
     "ssa_orbit_gen_eval": (_I, [c_void_p, _I, c_void_p, _I, _D, c_void_p, c_void_p, _D, _D, _I, _I, c_void_p, c_void_p, c_void_p, _I]),

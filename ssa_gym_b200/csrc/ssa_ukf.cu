@@ -1009,7 +1009,33 @@ struct EnvParams {
   int E, m, reward_type, n_steps, step_index;
   int increment;    // episodic mode: step_idx[e] += 1 before it is used (the device owns the counters)
   int greedy_only;  // refresh greedy / env_stats only (after an auto-reset); reward and done stay
+  const double* P; long ld;   // packed covariances (agent_shannon: determinants)
+  double* det_prev;           // [N] det P of the previous call (P_filter[i-1] of agents.py:24)
+  const uint8_t* reset_mask;  // episodic refresh after an auto-reset: only these environments restart their det history
 };
+
+// det of a packed symmetric 6x6 by LU with partial pivoting (numpy.linalg.det = LAPACK getrf + product of the pivots)
+__device__ double ssa_det6_packed(const double* P, long ld, long n) {
+  double a[6][6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 6; ++j) { a[i][j] = P[ssa_pidx(i, j) * ld + n]; a[j][i] = a[i][j]; }
+  double det = 1.0;
+  for (int c = 0; c < 6; ++c) {
+    int pv = c;
+    for (int i = c + 1; i < 6; ++i) if (fabs(a[i][c]) > fabs(a[pv][c])) pv = i;
+    if (pv != c) { for (int j = 0; j < 6; ++j) { const double t = a[c][j]; a[c][j] = a[pv][j]; a[pv][j] = t; } det = -det; }
+    det = ssa_mul(det, a[c][c]);
+    if (a[c][c] == 0.0) break;
+    const double rp = ssa_div(1.0, a[c][c]);
+    for (int i = c + 1; i < 6; ++i) {
+      const double l = ssa_mul(a[i][c], rp);
+      for (int j = c + 1; j < 6; ++j) a[i][j] = a[i][j] - ssa_mul(l, a[c][j]);
+    }
+  }
+  return det;
+}
 
 struct ArgMax { double v; int i; };
 __device__ __forceinline__ ArgMax am_better(ArgMax a, ArgMax b) {
@@ -1035,10 +1061,30 @@ __global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) 
   const int e = blockIdx.x;
   const long base = (long)e * p.m;
   ArgMax a_trace{0.0, -1}, a_vtrace{0.0, -1}, a_vdpos{0.0, -1}, a_vdvel{0.0, -1}, a_spos{0.0, -1}, a_dpos{0.0, -1};
+  ArgMax a_vaer{0.0, -1}, a_vshan{0.0, -1};
   int tri = 0, nvis = 0, vis_nonzero = 0;
+  const bool restart = p.greedy_only && (!p.reset_mask || p.reset_mask[e]);  // fresh episode: no previous covariance yet
   for (int j = threadIdx.x; j < p.m; j += blockDim.x) {
     const double dp = p.dpos[base + j], dv = p.dvel[base + j], sp = p.spos[base + j], tr = p.trace[base + j];
     const int vis = p.visible[base + j];
+    // agent_shannon (agents.py:15-26): log(det P_i / det P_{i-1}); the first call of an episode has no P_{i-1} (the
+    // reference reads row -1 of its history array there): the ratio is taken as 1
+    double shan = 0.0;
+    if (p.det_prev && !(p.greedy_only && !restart)) {
+      const double det = ssa_det6_packed(p.P, p.ld, base + j);
+      double prev = p.det_prev[base + j];
+      if (restart || prev != prev) prev = det;  // (NaN = never set: ssa_ukf_reset)
+      shan = ssa_log(ssa_div(det, prev));
+      p.det_prev[base + j] = det;
+    }
+    if (vis) {
+      // agent_visible_greedy_aer (agents.py:57-63): the 'aer' observation's trace column after nan_to_num (SS2:839)
+      const double tr_aer = (tr - tr == 0.0) ? tr : 0.001;
+      a_vaer = am_better(a_vaer, ArgMax{tr_aer, j});
+      // np.argmax treats NaN as the maximum (first NaN wins): a NaN score is ordered above everything
+      const double sh = (shan == shan) ? shan : ssa_from_hilo(0x7ff00000, 0);
+      a_vshan = am_better(a_vshan, ArgMax{sh, j});
+    }
     a_trace = am_better(a_trace, ArgMax{tr, j});
     a_spos = am_better(a_spos, ArgMax{sp, j});
     a_dpos = am_better(a_dpos, ArgMax{dp, j});
@@ -1051,9 +1097,10 @@ __global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) 
     }
     tri += (dp < 1e4) + (dp < 1e7);  // results.py:431-433
   }
-  __shared__ ArgMax sm[6][4];
+  __shared__ ArgMax sm[8][4];
   __shared__ int si[3][4];
-  ArgMax r[6] = {am_warp(a_trace), am_warp(a_vtrace), am_warp(a_vdpos), am_warp(a_vdvel), am_warp(a_spos), am_warp(a_dpos)};
+  ArgMax r[8] = {am_warp(a_trace), am_warp(a_vtrace), am_warp(a_vdpos), am_warp(a_vdvel), am_warp(a_spos), am_warp(a_dpos),
+                 am_warp(a_vaer), am_warp(a_vshan)};
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     tri += __shfl_xor_sync(0xffffffffu, tri, o);
@@ -1062,13 +1109,13 @@ __global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) 
   }
   const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
-    for (int q = 0; q < 6; ++q) sm[q][w] = r[q];
+    for (int q = 0; q < 8; ++q) sm[q][w] = r[q];
     si[0][w] = tri; si[1][w] = nvis; si[2][w] = vis_nonzero;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     const int nw = blockDim.x >> 5;
-    for (int q = 0; q < 6; ++q) for (int k = 1; k < nw; ++k) sm[q][0] = am_better(sm[q][0], sm[q][k]);
+    for (int q = 0; q < 8; ++q) for (int k = 1; k < nw; ++k) sm[q][0] = am_better(sm[q][0], sm[q][k]);
     for (int k = 1; k < nw; ++k) { si[0][0] += si[0][k]; si[1][0] += si[1][k]; si[2][0] |= si[2][k]; }
     const double max_dpos = sm[5][0].v;
     int step_i = p.step_index >= 0 ? p.step_index : p.step_idx[e];
@@ -1080,6 +1127,8 @@ __global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) 
     p.greedy[e * SSA_N_TASKERS + SSA_TASKER_VISIBLE_GREEDY] = any_vis ? sm[1][0].i : -1;
     p.greedy[e * SSA_N_TASKERS + SSA_TASKER_POS_ERROR_GREEDY] = any_vis ? sm[2][0].i : -1;
     p.greedy[e * SSA_N_TASKERS + SSA_TASKER_VEL_ERROR_GREEDY] = any_vis ? sm[3][0].i : -1;
+    p.greedy[e * SSA_N_TASKERS + SSA_TASKER_VISIBLE_GREEDY_AER] = any_vis ? sm[6][0].i : -1;
+    if (!(p.greedy_only && !restart)) p.greedy[e * SSA_N_TASKERS + SSA_TASKER_SHANNON] = any_vis ? sm[7][0].i : -1;
     const double trinary = ((double)si[0][0] / (double)p.m) / 2.0;
     p.env_stats[e * 4 + 0] = max_dpos;
     p.env_stats[e * 4 + 1] = trinary;
@@ -1183,6 +1232,50 @@ __global__ void ssa_diag_kernel(const double* __restrict__ xt, const double* __r
   }
   diag[2 * n + 1] = nis;
   flags[n] = (uint8_t)f;
+}
+
+// ---- innovation whiteness statistics (SS2:655-698 autocorrelation, SS2:782-832 innovation_dw_test) ---------
+// One block per (series, component) of B innovation series y[b][t][3], t < n, with a validity mask (an observation was
+// taken / the object was the tasked one).  Durbin-Watson: sum_t (e_t - e_{t-1})^2 / sum_t e_t^2 over the VALID entries in
+// order (the reference forms the series of the tasked steps first).  Autocorrelation: statsmodels acf(x, missing=
+// 'conservative', fft=False): the series is demeaned by the mean of its valid entries, the invalid entries count as zero,
+// acf[k] = sum_t x_t x_{t+k} / sum_t x_t^2 for k = 0..nlags.  All sums run in increasing t (deterministic).
+__global__ void __launch_bounds__(64) ssa_innov_stats_kernel(const double* __restrict__ y, const uint8_t* __restrict__ valid, int n, int nlags,
+                                                             double* __restrict__ dw, double* __restrict__ acf, double* __restrict__ work) {
+  const int b = blockIdx.x / 3, c = blockIdx.x % 3;
+  const double* yy = y + (long)b * n * 3 + c;
+  const uint8_t* vv = valid + (long)b * n;
+  double* xo = work + (long)blockIdx.x * n;   // demeaned series, zeros at the invalid entries
+  __shared__ double s_mean, s_acov0;
+  if (threadIdx.x == 0) {
+    double sum = 0.0, num = 0.0, den = 0.0, prev = 0.0;
+    int cnt = 0;
+    for (int t = 0; t < n; ++t) {
+      if (!vv[t]) continue;
+      const double e = yy[3L * t];
+      sum += e;
+      den = ssa_fma(e, e, den);
+      if (cnt) { const double d = e - prev; num = ssa_fma(d, d, num); }
+      prev = e;
+      ++cnt;
+    }
+    dw[blockIdx.x] = cnt ? ssa_div(num, den) : ssa_nan();
+    s_mean = cnt ? ssa_div(sum, (double)cnt) : 0.0;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n; t += blockDim.x) xo[t] = vv[t] ? (yy[3L * t] - s_mean) : 0.0;
+  __syncthreads();
+  for (int k = threadIdx.x; k <= nlags; k += blockDim.x) {
+    double acc = 0.0;
+    for (int t = 0; t + k < n; ++t) acc = ssa_fma(xo[t], xo[t + k], acc);
+    acf[(long)blockIdx.x * (nlags + 1) + k] = acc;
+    if (k == 0) s_acov0 = acc;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k <= nlags; k += blockDim.x) {
+    double* a = acf + (long)blockIdx.x * (nlags + 1) + k;
+    *a = ssa_div(*a, s_acov0);
+  }
 }
 
 // ---- catalog generator (envs/orbit_gen.py:47-75): acceptance rule of a batch of candidate orbits ------
@@ -1314,7 +1407,7 @@ __global__ void ssa_scores_kernel(const double* __restrict__ P, const double* __
     }
   }
   const double dt2 = dt * dt, dt6 = dt2 * dt2 * dt2;
-  out[n * 6 + 2] = pow(det * dt6, 1.0 / 12.0);  // score_scaled_det_P (host-side numpy uses np.power too)
+  out[n * 6 + 2] = ssa_exp(ssa_div(ssa_log(ssa_mul(det, dt6)), 12.0));  // score_scaled_det_P: (det P dt^6)^(1/12), NaN for det < 0 like np.power
   out[n * 6 + 3] = det;                          // score_det_P
   out[n * 6 + 4] = det3;                         // score_det_pos_P
   out[n * 6 + 5] = dpos[n];                      // |delta pos| (score_neg_max_pos_error = -max over objects)
@@ -1522,7 +1615,7 @@ struct ssa_ukf {
   long launches;
   // one slab for all fp64 SoA state
   double* slab;
-  double *xt, *x, *P, *dpos, *dvel, *spos, *svel, *trace;
+  double *xt, *x, *P, *dpos, *dvel, *spos, *svel, *trace, *det_prev;
   double *obs, *z_noise, *z_true, *y, *S, *sigmas_h, *scores, *reward, *env_stats;
   double* stage;  // staging for AoS<->SoA conversion ([N][39] doubles)
   double* qr;     // packed Q (21) + R (9)
@@ -1625,7 +1718,7 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
   h->ld = (N + 31) / 32 * 32;
   const long ld = h->ld;
   // fp64 slab: xt 6, x 6, P 21, dpos dvel spos svel trace 5 (SoA rows of ld) + AoS outputs
-  const size_t n_soa = (size_t)(6 + 6 + 21 + 5) * ld;
+  const size_t n_soa = (size_t)(6 + 6 + 21 + 5 + 1) * ld;
   const size_t n_aos = (size_t)N * (12 + 3 + 3 + 3 + 9 + 39 + 6 + 2) + (size_t)E * (1 + 4 + 9) + 32;
   cudaError_t e = cudaMalloc(&h->slab, (n_soa + n_aos) * sizeof(double));
   if (e != cudaSuccess) { delete h; return set_err("cudaMalloc(slab)", e); }
@@ -1635,6 +1728,7 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
   h->x = q; q += 6 * ld;
   h->P = q; q += 21 * ld;
   h->dpos = q; q += ld; h->dvel = q; q += ld; h->spos = q; q += ld; h->svel = q; q += ld; h->trace = q; q += ld;
+  h->det_prev = q; q += ld;
   h->obs = q; q += N * 12;
   h->z_noise = q; q += N * 3;
   h->z_true = q; q += N * 3;
@@ -1777,6 +1871,7 @@ int ssa_ukf_reset(ssa_ukf* h, const double* x_true, const double* x_filter, cons
   CK(cudaGetLastError());
   CK(cudaMemsetAsync(h->status, 0, sizeof(int32_t) * 2 * h->ld, st));
   CK(cudaMemsetAsync(h->visible, 0, 2 * h->ld, st));
+  CK(cudaMemsetAsync(h->det_prev, 0xFF, sizeof(double) * h->ld, st));  // NaN: no previous covariance yet (agent_shannon)
   CK(cudaStreamSynchronize(st));
   return SSA_OK;
 }
@@ -2232,15 +2327,18 @@ static void rollout_env_params(ssa_ukf* h, EnvParams* p, int increment, int gree
   p->env_stats = h->env_stats;
   p->E = h->cfg.n_envs; p->m = h->cfg.m; p->reward_type = h->cfg.reward_type; p->n_steps = h->cfg.n_steps;
   p->step_index = -1; p->step_idx = h->step_idx; p->increment = increment; p->greedy_only = greedy_only;
+  p->P = h->P; p->ld = h->ld; p->det_prev = h->det_prev;
+  p->reset_mask = nullptr;
 }
 
 // obs / errors / visibility of the current states + greedy taskers (after a reset)
-static int rollout_refresh(ssa_ukf* h, cudaStream_t st) {
+static int rollout_refresh(ssa_ukf* h, cudaStream_t st, int only_done) {
   StepOverride ov{h->ro.dout, h->ro.act_eff, h->ro.table, h->step_idx, 0, h->ro.n_table};
   int rc = step_impl(h, nullptr, SSA_STEP_EPILOGUE, st, nullptr, -1, &ov);
   if (rc) return rc;
   EnvParams ep;
   rollout_env_params(h, &ep, 0, 1);
+  if (only_done) ep.reset_mask = ep.done;  // the environments k_env_reset has just re-drawn
   ssa_env_reduce_kernel<<<(unsigned)ep.E, 128, 0, st>>>(ep);
   h->launches++;
   return SSA_OK;
@@ -2309,7 +2407,7 @@ int ssa_ukf_rollout_reset(ssa_ukf* h, void* stream) {
   rollout_params(h, &rp, 0);
   k_env_reset<<<(unsigned)rp.E, 128, 0, st>>>(rp);
   h->launches++;
-  int rc = rollout_refresh(h, st);
+  int rc = rollout_refresh(h, st, 0);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->ro.hout, h->ro.dout, h->ro.out_bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaGetLastError());
@@ -2333,7 +2431,7 @@ static int rollout_chain(ssa_ukf* h, cudaStream_t st, int auto_reset) {
   if (auto_reset) {
     k_env_reset<<<(unsigned)rp.E, 128, 0, st>>>(rp);
     h->launches++;
-    rc = rollout_refresh(h, st);
+    rc = rollout_refresh(h, st, 1);
     if (rc) return rc;
   }
   return SSA_OK;
@@ -2412,6 +2510,7 @@ int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stre
   p.step_index = step_index;
   p.step_idx = h->step_idx;
   p.increment = 0; p.greedy_only = 0;
+  p.P = h->P; p.ld = h->ld; p.det_prev = h->det_prev; p.reset_mask = nullptr;
   ssa_env_reduce_kernel<<<(unsigned)p.E, 128, 0, st>>>(p);
   h->launches++;
   CK(cudaGetLastError());
@@ -2508,6 +2607,34 @@ int ssa_orbit_gen_eval(const double* cand, int K, const double* trans_table, int
 #undef OG
 done:
   cudaFree(d_c); cudaFree(d_t); cudaFree(d_f); cudaFree(d_acc); cudaFree(d_e); cudaFree(d_a);
+  return rc;
+}
+
+int ssa_innovation_stats(const double* y, const uint8_t* valid, int n_series, int n, int nlags, double* dw, double* acf, int device) {
+  if (!y || !valid || n_series < 1 || n < 2 || nlags < 0 || nlags >= n || !dw || !acf) return SSA_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { snprintf(g_err, sizeof(g_err), "no CUDA device"); return SSA_ENODEV; }
+  CK(cudaSetDevice(device));
+  const size_t ny = (size_t)n_series * n * 3, nb = (size_t)n_series * 3;
+  double *d_y = nullptr, *d_dw = nullptr, *d_acf = nullptr, *d_w = nullptr;
+  uint8_t* d_v = nullptr;
+  int rc = SSA_OK;
+  cudaError_t e;
+#define IS(call) do { if ((e = (call)) != cudaSuccess) { rc = set_err(#call, e); goto done; } } while (0)
+  IS(cudaMalloc(&d_y, sizeof(double) * ny));
+  IS(cudaMalloc(&d_v, (size_t)n_series * n));
+  IS(cudaMalloc(&d_dw, sizeof(double) * nb));
+  IS(cudaMalloc(&d_acf, sizeof(double) * nb * (nlags + 1)));
+  IS(cudaMalloc(&d_w, sizeof(double) * nb * n));
+  IS(cudaMemcpy(d_y, y, sizeof(double) * ny, cudaMemcpyHostToDevice));
+  IS(cudaMemcpy(d_v, valid, (size_t)n_series * n, cudaMemcpyHostToDevice));
+  ssa_innov_stats_kernel<<<(unsigned)nb, 64>>>(d_y, d_v, n, nlags, d_dw, d_acf, d_w);
+  IS(cudaGetLastError());
+  IS(cudaMemcpy(dw, d_dw, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+  IS(cudaMemcpy(acf, d_acf, sizeof(double) * nb * (nlags + 1), cudaMemcpyDeviceToHost));
+#undef IS
+done:
+  cudaFree(d_y); cudaFree(d_v); cudaFree(d_dw); cudaFree(d_acf); cudaFree(d_w);
   return rc;
 }
 

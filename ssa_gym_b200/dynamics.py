@@ -137,3 +137,32 @@ def resolve_operator(role, fn):
         f"env_config['{role}'] = {fn!r} has no device implementation; supported: "
         f"{sorted(n for n in DEVICE_OPERATORS[role] if n)} (the GPU path never calls back into Python, "
         f"there is no CPU fallback)")
+
+
+# the operator combination the kernels implement for each observation type (anything else would silently be a
+# different filter: with mean_z = None filterpy averages the angles with np.dot, with residual_z = np.subtract it does
+# not wrap the azimuth)
+DEVICE_COMBINATIONS = {
+    "aer": {"hx": {"hx_aer_erfa"}, "mean_z": {"mean_z_uvw"}, "residual_z": {"residual_z_aer"}},
+    "xyz": {"hx": {"hx_xyz"}, "mean_z": {"mean_xyz", None}, "residual_z": {"residual_xyz", "subtract", None}},
+}
+
+
+def validate_operators(config, obs_type):
+    """Resolve env_config's operator callables (envs/__init__.py:27-28; SS2:112-116, 211-214) to the device operators
+    and check that the (hx, mean_z, residual_z) triple is the one the kernels run for `obs_type`.  Missing keys take
+    the device combination's own operators.  Returns the canonical names; raises otherwise (no CPU fallback)."""
+    if obs_type not in DEVICE_COMBINATIONS:
+        raise ValueError('Invalid Observation Type: ' + str(obs_type))
+    names = {"fx": resolve_operator("fx", config.get("fx", fx_xyz_farnocchia)),
+             "msqrt": resolve_operator("msqrt", config.get("msqrt", robust_cholesky))}
+    defaults = {"aer": {"hx": hx_aer_erfa, "mean_z": mean_z_uvw, "residual_z": residual_z_aer},
+                "xyz": {"hx": hx_xyz, "mean_z": None, "residual_z": None}}[obs_type]
+    for role in ("hx", "mean_z", "residual_z"):
+        fn = config[role] if role in config and not (role == "hx" and config[role] is None) else defaults[role]
+        name = resolve_operator(role, fn)
+        if name not in DEVICE_COMBINATIONS[obs_type][role]:
+            raise ValueError(f"env_config['{role}'] = {name} does not belong to obs_type '{obs_type}': the device filter for it "
+                             f"uses {sorted(str(n) for n in DEVICE_COMBINATIONS[obs_type][role])}")
+        names[role] = name
+    return names

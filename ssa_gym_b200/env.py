@@ -22,7 +22,7 @@ import numpy as np
 from . import _lib, dynamics
 from .episode import draw_episode, step_reward
 from .gym_shim import Env, seeding, spaces
-from .transformations import arcsec2rad, deg2rad, gcrs2irts_matrix_b, lla2ecef, load_eop_c04, time_table
+from .transformations import arcsec2rad, default_eops, deg2rad, gcrs2irts_matrix_b, lla2ecef, load_eop_c04, time_table
 from .ukf import BatchedUKF, Q_discrete_white_noise_block
 
 F = _lib
@@ -69,13 +69,7 @@ class SSA_Tasker_Env(Env):
         self.msqrt = config.get('msqrt', dynamics.robust_cholesky)
         if self.hx is None:
             self.hx = dynamics.hx_aer_erfa if self.obs_type == 'aer' else dynamics.hx_xyz
-        dynamics.resolve_operator('fx', self.fx)
-        hx_name = dynamics.resolve_operator('hx', self.hx)
-        dynamics.resolve_operator('mean_z', self.mean_z)
-        dynamics.resolve_operator('residual_z', self.residual_z)
-        dynamics.resolve_operator('msqrt', self.msqrt)
-        if (hx_name == 'hx_xyz') != (self.obs_type == 'xyz'):
-            raise ValueError("env_config['hx'] and env_config['obs_type'] disagree")
+        dynamics.validate_operators(config, self.obs_type)
         self.alpha, self.beta, self.kappa = config['alpha'], config['beta'], config['kappa']
 
         x_dim, z_dim = 6, 3
@@ -91,7 +85,7 @@ class SSA_Tasker_Env(Env):
             self.trans_matrix = np.ascontiguousarray(config['trans_matrix'], dtype=np.float64)
             assert self.trans_matrix.shape == (n, 3, 3), "trans_matrix must be [steps, 3, 3]"
         else:
-            self.eops = load_eop_c04(config['eop_file']) if config.get('eop_file') else None
+            self.eops = load_eop_c04(config['eop_file']) if config.get('eop_file') else default_eops()
             self.trans_matrix = np.ascontiguousarray(gcrs2irts_matrix_b(self.time, self.eops))
         self.z_noise = np.empty((n, m, z_dim))
         self.z_true = np.empty((n, m, z_dim))
@@ -265,7 +259,7 @@ class SSA_Tasker_Env(Env):
 
     def aer_obs(self, obs):
         i = self.i
-        aer = dynamics.hx_aer_erfa(self.x_filter[i], self.trans_matrix[i], self.obs_lla, self.obs_itrs)
+        aer = dynamics.hx_aer_erfa(self.x_filter[i], self.trans_matrix[i], self.obs_lla, self.obs_itrs, device=self._device)
         for j in range(self.m):
             obs[4 * j: 4 * j + 3] = aer[j]
             obs[4 * j + 3] = np.trace(self.P_filter[i, j])
@@ -320,6 +314,55 @@ class SSA_Tasker_Env(Env):
         one = np.stack([(f >> a) & 1 for a in range(3)], axis=1)
         two = np.stack([(f >> (3 + a)) & 1 for a in range(3)], axis=1)
         return np.round(np.stack((np.mean(one, axis=0), np.mean(two, axis=0))) * 100, 2)
+
+    # -- innovation whiteness (SS2:644-698, 782-832): Durbin-Watson statistic and autocorrelation, on the device ------
+    def innovation(self):
+        """SS2:644-653: the tasked object's innovation at every step (NaN where no observation was taken) and, per object,
+        the same series with the steps at which ANOTHER object was observed set to NaN."""
+        steps = min(self.i + 1, self.n)
+        innovation = np.array([self.y[i, int(self.actions[i])] for i in range(1, steps)]).reshape(-1, 3)
+        taken = np.asarray(self.obs_taken[1:steps], dtype=bool)
+        innovation[~taken] = np.nan
+        innovations = []
+        for j in range(self.m):
+            inn = innovation.copy()
+            inn[(np.asarray(self.actions[1:steps]) != j) & taken] = np.nan
+            innovations.append(inn)
+        return innovation, innovations
+
+    def _innovation_stats(self, nlags):
+        from .ukf import innovation_stats
+        innovation, innovations = self.innovation()
+        series = np.stack([innovation] + innovations)            # [1 + m, steps - 1, 3]
+        valid = ~np.isnan(series).any(axis=2)
+        nlags = min(nlags, series.shape[1] - 1)
+        return innovation_stats(series, valid, nlags, self._device), valid
+
+    def autocorrelation(self, nlags=40):
+        """SS2:655-668: acf(innovation[:, c], missing='conservative', fft=False) of the overall innovation [3, nlags + 1] and
+        of every object's own series (list of [3, nlags + 1]); nlags = 40 is the statsmodels default of the reference's era."""
+        (_, acf), _ = self._innovation_stats(nlags)
+        return acf[0], [acf[1 + j] for j in range(self.m)]
+
+    def innovation_dw_test(self):
+        """SS2:782-832: Durbin-Watson statistic of the innovation, rows = (all observations, min per object, max per object),
+        columns = measurement components, rounded to 3 decimals.  Steps without an observation are skipped (the reference's
+        sums turn NaN there); objects observed fewer than twice do not enter min / max."""
+        (dw, _), valid = self._innovation_stats(1)
+        per_obj = dw[1:][valid[1:].sum(axis=1) >= 2]
+        lo = np.min(per_obj, axis=0) if len(per_obj) else np.full(3, np.nan)
+        hi = np.max(per_obj, axis=0) if len(per_obj) else np.full(3, np.nan)
+        table = np.round(np.vstack([dw[0], lo, hi]), 3)
+        try:
+            import pandas as pd
+            cols = ['x', 'y', 'z'] if self.obs_type == 'xyz' else ['Azimuth', 'Elevation', 'Range']
+            out = pd.DataFrame(data=table, columns=cols, index=['Durbin-Watson Statistic for All Obs',
+                                                                 'Durbin-Watson Statistic for Min per Obj',
+                                                                 'Durbin-Watson Statistic for Max per Obj'])
+            out.name = 'Durbin-Watson Statistic for Innovation'
+            return out
+        except ImportError:
+            return table
 
     def close(self):
         if getattr(self, "ukf", None) is not None:

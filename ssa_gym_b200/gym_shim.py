@@ -15,7 +15,10 @@ try:  # pragma: no cover - not available offline
     import gym as _gym
     from gym import spaces as _spaces
     from gym.utils import seeding as _seeding
-    HAVE_GYM = hasattr(_seeding, "np_random") and hasattr(_gym, "Env")
+    # only the gym 0.17-0.21 API reproduces the reference: np_random must hand back a numpy RandomState (gym >= 0.22
+    # returns a Generator without randint / the legacy normal stream, and reset / step changed shape)
+    HAVE_GYM = (hasattr(_seeding, "np_random") and hasattr(_gym, "Env")
+                and isinstance(_seeding.np_random(0)[0], np.random.RandomState))
 except Exception:  # noqa: BLE001
     HAVE_GYM = False
 

@@ -7,9 +7,11 @@ call of `ssa_orbit_gen_eval` (two kernels: propagation + altitude + elevation fo
 gap rule per candidate) decides the whole batch.
 
 The acceptance rule is the reference's, decision for decision (tests: against the reference's own functions).  The
-candidate DISTRIBUTION is the reference's (regime mix 1/3 LEO, 1/3 MEO, 1/9 GEO, 1/9 Tundra, 1/9 Molniya; the
-element ranges of dynamics.py:362-397 including the exo-atmospheric rejection loop); the candidate STREAM is not: a
-sequential accept/reject loop on one RandomState cannot be batched, so candidates are drawn vectorised.
+DISTRIBUTION of the accepted catalog is the reference's: the regime of every output slot is drawn first (1/3 LEO, 1/3
+MEO, 1/9 GEO, 1/9 Tundra, 1/9 Molniya) and candidates are retried inside that regime until one is accepted
+(orbit_gen.py:51-54), with the element ranges of dynamics.py:362-397 including the exo-atmospheric rejection loop.
+The candidate STREAM is not the reference's: a sequential accept/reject loop on one RandomState cannot be batched, so
+candidates are drawn vectorised.
 """
 import ctypes
 
@@ -17,15 +19,16 @@ import numpy as np
 
 from . import _lib
 from .catalog import RE_EQ, coe2rv
-from .transformations import deg2rad, gcrs2irts_matrix_b, lla2ecef, load_eop_c04, time_table, trans_uvw_ecef
+from .transformations import default_eops, deg2rad, gcrs2irts_matrix_b, lla2ecef, load_eop_c04, time_table, trans_uvw_ecef
 
 REGIMES = ('LEO', 'MEO', 'GEO', 'Tundra', 'Molniya')
 REGIME_P = (1 / 3, 1 / 3, 1 / 9, 1 / 9, 1 / 9)          # orbit_gen.py:52
 
 
-def sample_candidates(k, rng, p=REGIME_P):
-    """k candidate states [k, 6] (GCRS, m and m/s) with the distributions of dynamics.py:357-399."""
-    reg = rng.choice(len(REGIMES), size=k, p=p)
+def sample_candidates(k, rng, p=REGIME_P, reg=None):
+    """k candidate states [k, 6] (GCRS, m and m/s) with the distributions of dynamics.py:357-399; `reg` fixes the regime
+    of every candidate (indices into REGIMES), else it is drawn with probabilities p."""
+    reg = rng.choice(len(REGIMES), size=k, p=p) if reg is None else np.asarray(reg, dtype=int)
     inc = np.radians(rng.uniform(0, 180, k))
     raan = np.radians(rng.uniform(0, 360, k))
     argp = np.radians(rng.uniform(0, 360, k))
@@ -52,7 +55,9 @@ def sample_candidates(k, rng, p=REGIME_P):
 
 def evaluate(candidates, trans_table, step_s, obs_lla, obs_limit_rad, min_alt=300e3, first_window=18, max_gap=36,
              details=False, device=0):
-    """Acceptance flags (bool [K]) of the candidates; with details=True also elevation and altitude [K, n]."""
+    """Acceptance flags (bool [K]) of the candidates; with details=True also elevation and altitude [K, n].
+    `max_gap` (in samples) may be fractional: the reference compares the integer gap lengths with the float limit
+    (orbit_gen.py:66), which for integers is the comparison with its ceiling."""
     cand = np.ascontiguousarray(candidates, dtype=np.float64).reshape(-1, 6)
     table = np.ascontiguousarray(trans_table, dtype=np.float64).reshape(-1, 9)
     K, n = len(cand), len(table)
@@ -65,7 +70,7 @@ def evaluate(candidates, trans_table, step_s, obs_lla, obs_limit_rad, min_alt=30
     vp = lambda x_: None if x_ is None else x_.ctypes.data_as(ctypes.c_void_p)
     lib = _lib.require_gpu()
     _lib.check(lib.ssa_orbit_gen_eval(vp(cand), K, vp(table), n, float(step_s), vp(obs_itrs), vp(T), float(obs_limit_rad),
-                                      float(min_alt), int(first_window), int(max_gap), vp(acc), vp(el), vp(alt), int(device)),
+                                      float(min_alt), int(first_window), int(np.ceil(max_gap)), vp(acc), vp(el), vp(alt), int(device)),
                "ssa_orbit_gen_eval")
     return (acc.astype(bool), el, alt) if details else acc.astype(bool)
 
@@ -78,16 +83,32 @@ def generate_catalog(samples=20000, seed=0, step_size=60 * 2.5, max_gap_hours=1.
     from datetime import datetime
     n = int(np.ceil(duration_hours * 60 * 60 / step_size))
     if trans_matrix is None:
-        eops = load_eop_c04(eop_file) if eop_file else None
+        eops = load_eop_c04(eop_file) if eop_file else default_eops()
         trans_matrix = gcrs2irts_matrix_b(time_table(t_0 or datetime(2020, 5, 4, 0, 0, 0), step_size, n), eops)
     obs_lla = np.array(observer) * [deg2rad, deg2rad, 1]
     rng = np.random.RandomState(seed)
-    kept, drawn, have = [], 0, 0
-    while have < samples:
-        cand = sample_candidates(batch, rng)
+    # The reference fixes the regime of every OUTPUT slot first and retries inside that regime until a candidate is
+    # accepted (orbit_gen.py:51-54), so the accepted catalog has exactly the drawn mix (1/3, 1/3, 1/9, 1/9, 1/9) whatever
+    # the regimes' acceptance rates are.  Same here: the slots' regimes are drawn once, every batch proposes candidates
+    # for the still-empty slots (cyclically, so that a batch is always full) and a slot takes its first accepted one.
+    slot_regime = rng.choice(len(REGIMES), size=samples, p=REGIME_P)
+    catalog = np.zeros((samples, 6))
+    filled = np.zeros(samples, dtype=bool)
+    drawn = accepted = 0
+    while not filled.all():
+        todo = np.where(~filled)[0]
+        slots = todo[np.arange(batch) % len(todo)]
+        cand = sample_candidates(batch, rng, reg=slot_regime[slots])
         ok = evaluate(cand, trans_matrix, step_size, obs_lla, np.radians(obs_limit_deg), first_window=int(first_window_min * 60 / step_size),
                       max_gap=max_gap_hours * 60 * 60 / step_size, device=device)
-        kept.append(cand[ok])
         drawn += len(cand)
-        have += int(ok.sum())
-    return np.concatenate(kept)[:samples], have / drawn
+        accepted += int(ok.sum())
+        first = {}
+        for k_ in np.where(ok)[0]:
+            first.setdefault(int(slots[k_]), int(k_))
+        idx = np.array(sorted(first), dtype=int)
+        if len(idx):
+            catalog[idx] = cand[[first[i] for i in idx]]
+            filled[idx] = True
+    generate_catalog.last_slot_regime = slot_regime
+    return catalog, accepted / drawn

@@ -63,8 +63,26 @@ def load_eop_c04(path):
     return {int(r[3]): (r[4], r[5], r[6], r[8], r[9]) for r in arr}
 
 
+DEFAULT_EOP_FILE = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "data",
+                                              "eopc04_IAU2000_excerpt.txt")
+_default_eop = {}
+
+
+def default_eops():
+    """The EOP rows shipped with the package: an excerpt of IERS EOP 14 C04 (public IERS data, the table the reference
+    downloads in get_eops, transformations.py:19-31) in the original file format: 2007-03-31 .. 2007-04-10 (the SOFA
+    cookbook date of tests.py:12-30) and 2020-04-01 .. 2020-06-23 (the default t_0 = 2020-05-04 and the end of the
+    reference's cached file).  Dates outside it need `env_config['eop_file']` (a full C04 file) or run without polar
+    motion / UT1-UTC / dX,dY (a 30 m class error at GEO, see the module docstring)."""
+    if "t" not in _default_eop:
+        _default_eop["t"] = load_eop_c04(DEFAULT_EOP_FILE)
+    return _default_eop["t"]
+
+
 def _interp_eop(eop, mjd_day, day_frac):
-    if eop is None:
+    """Linear interpolation between the two daily rows, as transformations.py:156-165 does with the pandas frame.
+    Returns zeros when there is no table or the date is outside it."""
+    if eop is None or int(mjd_day) not in eop or int(mjd_day) + 1 not in eop:
         return 0.0, 0.0, 0.0, 0.0, 0.0
     lo, hi = eop[int(mjd_day)], eop[int(mjd_day) + 1]
     return tuple(l * (1 - day_frac) + h * day_frac for l, h in zip(lo, hi))

@@ -313,3 +313,18 @@ def fp64_peak_tflops(device=0, stream=None):
     v = ctypes.c_double()
     _lib.check(lib.ssa_ukf_fp64_peak(int(device), stream, ctypes.byref(v)), "ssa_ukf_fp64_peak")
     return v.value
+
+
+def innovation_stats(y, valid, nlags=40, device=0):
+    """Whiteness statistics of B innovation series on the device (ssa_innovation_stats): y [B, n, 3], valid [B, n] bool.
+    Returns (dw [B, 3], acf [B, 3, nlags + 1]): Durbin-Watson over the valid entries in order (SS2:782-832) and the
+    autocorrelation with missing='conservative' (SS2:655-668)."""
+    lib = _lib.require_gpu()
+    y = np.ascontiguousarray(np.nan_to_num(np.asarray(y, dtype=np.float64)))
+    valid = np.ascontiguousarray(np.asarray(valid).astype(np.uint8))
+    B, n = valid.shape
+    assert y.shape == (B, n, 3) and 0 <= nlags < n
+    dw = np.empty((B, 3))
+    acf = np.empty((B, 3, nlags + 1))
+    _lib.check(lib.ssa_innovation_stats(_ptr(y), _ptr(valid), B, n, int(nlags), _ptr(dw), _ptr(acf), int(device)), "ssa_innovation_stats")
+    return dw, acf

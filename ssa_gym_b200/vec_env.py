@@ -22,7 +22,7 @@ import numpy as np
 from . import _lib, dynamics
 from .episode import draw_episode
 from .gym_shim import seeding, spaces
-from .transformations import arcsec2rad, deg2rad, gcrs2irts_matrix_b, lla2ecef, load_eop_c04, time_table
+from .transformations import arcsec2rad, default_eops, deg2rad, gcrs2irts_matrix_b, lla2ecef, load_eop_c04, time_table
 from .ukf import BatchedUKF, Q_discrete_white_noise_block
 
 F = _lib
@@ -51,16 +51,14 @@ class VecSSATaskerEnv:
                         else np.asarray(config['z_sigma'], dtype=float))
         self.x_sigma = np.array(config['x_sigma'])
         self.Q = Q_discrete_white_noise_block(self.dt, config['q_sigma'] ** 2, 3)
-        for role in ('fx', 'hx', 'mean_z', 'residual_z', 'msqrt'):
-            if role in config and not (role in ('mean_z', 'residual_z') and config[role] is None):
-                dynamics.resolve_operator(role, config[role])
+        dynamics.validate_operators(config, self.obs_type)
         self.P_0 = np.copy(np.diag(self.x_sigma ** 2)) if config.get('P_0') is None else np.copy(config['P_0'])
         self.R = np.diag(self.z_sigma ** 2) if config.get('R') is None else np.copy(config['R'])
         if config.get('trans_matrix') is not None:
             self.trans_matrix = np.ascontiguousarray(config['trans_matrix'], dtype=np.float64)
         else:
-            eops = load_eop_c04(config['eop_file']) if config.get('eop_file') else None
-            self.trans_matrix = np.ascontiguousarray(gcrs2irts_matrix_b(time_table(config['t_0'], self.dt, self.n), eops))
+            eops = load_eop_c04(config['eop_file']) if config.get('eop_file') else default_eops()
+            self.trans_matrix = np.ascontiguousarray(gcrs2irts_matrix_b(time_table(config.get('t_0'), self.dt, self.n), eops))
         self.ukf = BatchedUKF(n_envs=self.E, m=self.m, dt=self.dt, Q=self.Q, R=self.R, obs_lla=self.obs_lla,
                               obs_limit_rad=self.obs_limit, alpha=config['alpha'], beta=config['beta'], kappa=config['kappa'],
                               obs_type=self.obs_type, reward_type=self.reward_type, n_steps=self.n,

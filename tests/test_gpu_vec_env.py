@@ -78,6 +78,7 @@ def _emu_env_reduce(st, E, m, step_idx, reward_type, n_steps):
             greedy[e, F.TASKER_VISIBLE_GREEDY] = idx[tr[e, idx].argmax()]
             greedy[e, F.TASKER_POS_ERROR_GREEDY] = idx[dpos[e, idx].argmax()]
             greedy[e, F.TASKER_VEL_ERROR_GREEDY] = idx[dvel[e, idx].argmax()]
+            greedy[e, F.TASKER_VISIBLE_GREEDY_AER] = idx[np.nan_to_num(tr[e, idx], nan=0.001, posinf=0.001, neginf=0.001).argmax()]
     return reward, done, greedy
 
 
@@ -121,7 +122,7 @@ def test_device_episodic_mode_equals_twin_emulation(over):
     H.cpu_step("twin", tcfg, st, table[step_idx].reshape(E, 9), F.STEP_EPILOGUE | F.STEP_M_PER_ENV)
     _, _, g_e = _emu_env_reduce(st, E, m, step_idx, cfg["reward_type"], n)
     assert H.bits_equal(vec.obs.reshape(N, 12), st.obs)
-    assert np.array_equal(vec._io["greedy"], g_e)
+    assert np.array_equal(vec._io["greedy"][:, :5], g_e[:, :5])     # (agent_shannon: test_gpu_vs_oracle.py)
     rng = np.random.RandomState(11)
     n_resets = 0
     for t in range(total_steps):
@@ -146,7 +147,10 @@ def test_device_episodic_mode_equals_twin_emulation(over):
             H.cpu_step("twin", tcfg, st, table[step_idx].reshape(E, 9), F.STEP_EPILOGUE | F.STEP_M_PER_ENV)
         _, _, g_e = _emu_env_reduce(st, E, m, step_idx, cfg["reward_type"], n)
         assert H.bits_equal(obs_v.reshape(N, 12), st.obs), t
-        assert np.array_equal(vec._io["greedy"], g_e), t
+        assert np.array_equal(vec._io["greedy"][:, :5], g_e[:, :5]), t
+        sh = vec._io["greedy"][:, F.TASKER_SHANNON]
+        assert np.array_equal(sh >= 0, g_e[:, F.TASKER_VISIBLE_GREEDY] >= 0)
+        assert all(st.visible.reshape(E, m)[e, sh[e]] for e in range(E) if sh[e] >= 0)
         assert np.array_equal(vec.i, step_idx), t
     assert n_resets >= E
     assert H.bits_equal(vec.ukf.download(F.F_X_FILTER), st.x) and H.bits_equal(vec.ukf.download(F.F_X_TRUE), st.x_true)

@@ -102,7 +102,17 @@ def test_env_reduce_and_scores():
         for s in range(3):
             ukf.upload(F.F_ACTIONS, rng.randint(0, m, E).astype(np.int32)); ukf.upload(F.F_Z_NOISE, zn[s])
             ukf.step(H.CEL2TER06AXY, F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ACT | F.STEP_EPILOGUE)
-        ukf.env_reduce(step_index=3)
+        P_prev = ukf.download(F.F_P_FILTER).reshape(E, m, 6, 6)
+        ukf.env_reduce(step_index=3)     # first call: no previous covariance -> every log-determinant ratio is 0
+        g0 = ukf.download(F.F_GREEDY)
+        vis0 = ukf.download(F.F_VISIBLE).reshape(E, m).astype(bool)
+        for e in range(E):
+            v = np.where(vis0[e])[0]
+            assert g0[e, F.TASKER_SHANNON] == (v[0] if np.any(v) else -1)
+        for s in range(3, 5):
+            ukf.upload(F.F_ACTIONS, rng.randint(0, m, E).astype(np.int32)); ukf.upload(F.F_Z_NOISE, zn[s % 3])
+            ukf.step(H.CEL2TER06AXY, F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ACT | F.STEP_EPILOGUE)
+        ukf.env_reduce(step_index=5)
         ukf.sync()
         dpos, dvel, tr = (ukf.download(f).reshape(E, m) for f in (F.F_DELTA_POS, F.F_DELTA_VEL, F.F_TRACE))
         vis = ukf.download(F.F_VISIBLE).reshape(E, m).astype(bool)
@@ -117,6 +127,17 @@ def test_env_reduce_and_scores():
                 assert greedy[e, F.TASKER_VISIBLE_GREEDY] == v[np.argmax([np.trace(Pj) for Pj in P[e][v]])]
                 assert greedy[e, F.TASKER_POS_ERROR_GREEDY] == v[np.argmax(dpos[e, v])]
                 assert greedy[e, F.TASKER_VEL_ERROR_GREEDY] == v[np.argmax(dvel[e, v])]
+                # agent_visible_greedy_aer (agents.py:57-63): the 'aer' observation's trace column after nan_to_num
+                assert greedy[e, F.TASKER_VISIBLE_GREEDY_AER] == v[np.argmax(np.nan_to_num(tr[e, v], nan=0.001, posinf=0.001, neginf=0.001))]
+                # agent_shannon (agents.py:15-26): argmax log(det P_i / det P_{i-1}); the determinants come from an LU with
+                # partial pivoting on both sides but not from the same BLAS: equal up to ties inside 1e-9
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    sc = np.array([np.log(np.linalg.det(P[e, j]) / np.linalg.det(P_prev[e, j])) for j in v])
+                pick = list(v).index(greedy[e, F.TASKER_SHANNON])
+                if np.isnan(sc).any():
+                    assert np.isnan(sc[pick])          # np.argmax: the first NaN wins
+                else:
+                    assert sc[pick] >= np.max(sc) - 1e-9 * max(1.0, abs(np.max(sc))), (e, sc, pick)
             if reward_type == "trinary":
                 assert rew[e] == np.mean(((dpos[e] < 1e4) * 1 + (dpos[e] < 1e7) * 1)) / 2 and done[e] == 0
             else:

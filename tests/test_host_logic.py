@@ -77,6 +77,28 @@ def test_trans_matrix_generator_against_sofa_golden():
     assert abs(ang - 7.292115e-5 * 20.0) < 1e-9
 
 
+def test_eop_table_parsing_interpolation_and_default():
+    """The IERS EOP 14 C04 rows the reference reads (transformations.py:19-31; SURVEY 8c quotes MJD 58973): parsed from the
+    shipped excerpt in the original file format, interpolated linearly between the daily rows like the reference
+    (transformations.py:177-186), used by default, and ignored gracefully outside the excerpt."""
+    eop = T.default_eops()
+    assert eop[58973] == (0.081539, 0.439339, -0.2445748, 0.000098, 0.000039)          # 2020-05-04 0h UTC
+    assert eop[54195] == (0.033194, 0.483144, -0.0714163, 0.000250, -0.000302)         # 2007-04-05 0h UTC
+    assert 59023 in eop and 58940 in eop and 58939 not in eop
+    got = T._interp_eop(eop, 58973, 0.25)
+    want = tuple(0.75 * a + 0.25 * b for a, b in zip(eop[58973], eop[58974]))
+    assert np.allclose(got, want, rtol=1e-15) and T._interp_eop(eop, 58973, 0.0) == eop[58973]
+    assert T._interp_eop(eop, 40000, 0.5) == (0.0,) * 5 and T._interp_eop(None, 58973, 0.5) == (0.0,) * 5
+    assert T.cal2jd(2020, 5, 4)[1] == 58973.0 and T.dat(2020, 5) == 37.0 and T.dat(2016, 12) == 36.0 and T.dat(2017, 1) == 37.0
+    # with the table: polar motion (0.44 arcsec = 2.1e-6 rad) and UT1-UTC (-0.245 s = 1.8e-5 rad of Earth rotation) enter
+    t = datetime(2020, 5, 4, 6, 0, 0)
+    A, B = T.gcrs2irts_matrix_approx(t, eop), T.gcrs2irts_matrix_approx(t, None)
+    ang = np.arccos(min(1.0, (np.trace(A @ B.T) - 1) / 2))
+    assert 1.5e-5 < ang < 2.2e-5
+    # the C04 daily values reproduce the SOFA cookbook matrix of 2007-04-05 12:00 (which used Bulletin-B-era values) to 1e-6
+    assert np.max(np.abs(T.gcrs2irts_matrix_approx(datetime(2007, 4, 5, 12, 0, 0), eop) - H.CEL2TER06AXY)) < 1e-6
+
+
 def test_geometry_constants_match_reference_values():
     lla = np.array([np.radians(38.828198), np.radians(-77.305352), 20.0])
     assert np.allclose(T.lla2ecef(lla), [1093352.569823721, -4853701.926649121, 3977489.550983512], rtol=0, atol=1e-9)

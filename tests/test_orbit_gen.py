@@ -108,3 +108,21 @@ def test_generate_catalog_end_to_end():
     acc, el, alt = _twin_eval(cat, table, 150.0)
     assert acc.all()                                              # every orbit of the catalog passes the rule
     assert (alt > 300e3).all() and ((el >= LIMIT).sum(1) > 0).all()
+    # the ACCEPTED catalog has the reference's regime mix (orbit_gen.py:51-54 fixes the regime per output slot and
+    # retries inside it): classify the orbits back from their elements and compare with the slots' drawn regimes
+    mu = 398600441800000.0
+    r, v = np.linalg.norm(cat[:, :3], axis=1), np.linalg.norm(cat[:, 3:], axis=1)
+    a = 1.0 / (2.0 / r - v * v / mu)
+    h = np.cross(cat[:, :3], cat[:, 3:])
+    ecc = np.sqrt(np.maximum(0.0, 1.0 - np.sum(h * h, 1) / (mu * a)))
+    inc = np.degrees(np.arccos(h[:, 2] / np.linalg.norm(h, axis=1)))
+    geo_a = np.abs(a - 42164e3) < 1.0
+    cls = np.where(np.abs(ecc - 0.737) < 1e-6, 4, np.where(geo_a & (np.abs(inc - 63.4) < 1e-6) & (np.abs(ecc - 0.2) < 1e-6), 3,
+                   np.where(geo_a & (inc < 1e-9), 2, np.where(a < 6378136.6 + 2000e3, 0, 1))))
+    assert np.array_equal(cls, orbit_gen.generate_catalog.last_slot_regime)
+    frac = np.bincount(cls, minlength=5) / len(cls)
+    assert np.all(np.abs(frac - np.array(orbit_gen.REGIME_P)) < 0.03), frac
+    # fractional gap limit: integer gap lengths against a float limit == against its ceiling (orbit_gen.py:66)
+    ok_a = orbit_gen.evaluate(G["candidates"], G["table"], float(G["step"]), G["lla"], LIMIT, max_gap=35.2)
+    ok_b = orbit_gen.evaluate(G["candidates"], G["table"], float(G["step"]), G["lla"], LIMIT, max_gap=36)
+    assert np.array_equal(ok_a, ok_b)
