@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=["c2", "c4", "c3"])
     ap.add_argument("--envs", type=int, default=4096, help="c3: parallel environments per GPU")
+    ap.add_argument("--collector", default="greedy", choices=["greedy", "mlp"], help="c3: 'mlp' = stub PPO rollout collector on the device (1 GPU)")
     ap.add_argument("--gather", action="store_true", help="c3, N>1: also all_gather rewards and observations over NCCL every step (a learner on one device)")
     ap.add_argument("--rng", default="device", choices=["device", "host"], help="c3: episodic RNG mode of VecSSATaskerEnv")
     ap.add_argument("--objects", type=int, default=0, help="override the catalog size (c4: whole job, c2: per rank)")
@@ -326,6 +327,87 @@ def c3_measure(a, rank, local_rank, world, steps, warmup, gather):
     return line
 
 
+def c3_collector_measure(a, local_rank, steps, warmup, fragment=32):
+    """BASELINE.json config 3 with a PPO-shaped consumer ON THE DEVICE (RLlib is absent, so a stub MLP rollout
+    collector stands in; rl_agents/RLLib_PPO_training.py:15-48: default fcnet 2 x 256 tanh, rollout_fragment_length = 32).
+    Every vector step: the policy reads the observations [E, m*12] where the step left them (float64 -> float32 cast, no
+    normalisation, like the reference feeds them), samples one action per environment, writes them into the env's device
+    action buffer, the env steps (ONE graph launch, no H2D / D2H, nothing synchronises), reward / done are appended to
+    the fragment; every 32 steps the fragment [32, E, ...] is handed over as a sample batch (kept on the device, where a
+    learner would consume it)."""
+    import torch
+    from ssa_gym_b200 import env_config
+    from ssa_gym_b200.catalog import synthetic_catalog
+    from ssa_gym_b200.transformations import gcrs2irts_matrix_approx, time_table
+    from ssa_gym_b200.vec_env import VecSSATaskerEnv
+    E = a.envs
+    cfg = dict(env_config)
+    cfg["orbits"] = synthetic_catalog(20000, 0)
+    cfg["trans_matrix"] = gcrs2irts_matrix_approx(time_table(cfg["t_0"], cfg["time_step"], cfg["steps"]))
+    m = cfg["rso_count"]
+    env = VecSSATaskerEnv(cfg, E, seeds=list(range(E)), device=local_rank, rng="device")
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(0)
+    policy = torch.nn.Sequential(torch.nn.Linear(m * 12, 256), torch.nn.Tanh(), torch.nn.Linear(256, 256), torch.nn.Tanh(),
+                                 torch.nn.Linear(256, m + 1)).to(dev)   # m action logits + the value head
+    v = env.device_views()
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    frag = {"obs": torch.empty((fragment, E, m * 12), dtype=torch.float32, device=dev),
+            "actions": torch.empty((fragment, E), dtype=torch.int32, device=dev),
+            "logp": torch.empty((fragment, E), dtype=torch.float32, device=dev),
+            "vf": torch.empty((fragment, E), dtype=torch.float32, device=dev),
+            "rewards": torch.empty((fragment, E), dtype=torch.float32, device=dev),
+            "dones": torch.empty((fragment, E), dtype=torch.uint8, device=dev)}
+    batches = 0
+
+    def one(t):
+        k = t % fragment
+        with torch.no_grad():
+            obs32 = v["obs"].to(torch.float32)
+            out = policy(obs32)
+            logp_all = torch.log_softmax(out[:, :m], dim=1)
+            act = torch.multinomial(logp_all.exp(), 1).squeeze(1)
+            frag["obs"][k].copy_(obs32)
+            frag["actions"][k].copy_(act)
+            frag["logp"][k].copy_(logp_all.gather(1, act[:, None]).squeeze(1))
+            frag["vf"][k].copy_(out[:, m])
+            v["actions"].copy_(act)
+        env.vector_step_device(stream=sp)
+        frag["rewards"][k].copy_(v["reward"])
+        frag["dones"][k].copy_(v["done"])
+
+    for w in range(max(warmup, 3)):
+        one(w)
+    torch.cuda.synchronize()
+    l0 = env.ukf.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    e0.record(stream)
+    sample_batch = None
+    for t in range(steps):
+        one(t)
+        if (t + 1) % fragment == 0:   # hand the fragment over: [32 * E] timesteps, stays on the device
+            sample_batch = {k_: x_.reshape((fragment * E,) + tuple(x_.shape[2:])).clone() for k_, x_ in frag.items()}
+            batches += 1
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - tw0
+    ms = e0.elapsed_time(e1)
+    n_done = int(frag["dones"].sum().item())
+    ok = bool(torch.isfinite(frag["rewards"]).all().item()) and (sample_batch is None or sample_batch["obs"].shape == (fragment * E, m * 12))
+    out = {"workload": f"C3: {E} envs x {m} RSOs, stub-MLP PPO rollout collector on the device (2 x 256 tanh, fragment {fragment}), "
+                       f"device-resident obs / actions (no host copies)",
+           "value": E * steps / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms / steps, "steps": steps,
+           "object_predicts_per_s": E * m * steps / (ms * 1e-3), "sample_batches": batches, "timesteps_per_batch": fragment * E,
+           "gpu_launches": int(env.ukf.launch_count - l0), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+           "dones_in_last_fragment": n_done, "finite": ok, "wall_s": t_wall,
+           "note": "our kernels: one CUDA graph per vector step (gpu_launches counts its kernel nodes); the policy is ~12 small torch "
+                   "kernels per step, launched from Python: the loop is host-launch bound"}
+    env.close()
+    return out
+
+
 def c2_measure(local_rank, steps, warmup):
     """BASELINE.json config 2 on THIS rank's GPU: the 20 000-orbit catalog, every object predicted and updated once per
     step; per-step CUDA events, L2 flushed between steps.  Returns a small dict."""
@@ -441,6 +523,8 @@ def main():
         if a.workload == "c3":
             line = c3_measure(a, rank, local_rank, world, a.steps, a.warmup, a.gather)
             if rank == 0:
+                if a.collector == "mlp":
+                    line["extra"]["ppo_collector_on_device"] = c3_collector_measure(a, local_rank, a.steps, a.warmup)
                 print(json.dumps(line))
         else:
             run_catalog(a, rank, local_rank, world)
@@ -612,40 +696,56 @@ def run_catalog(a, rank, local_rank, world):
     barrier()
     b2b_ms = e0.elapsed_time(e1) / a.steps
 
-    # ---- e2e: the user-facing call with HOST buffers: every step ONE H2D copy of that step's inputs (z_noise +
-    # trans_matrix) from the handle's pinned input block, the kernel chain (one captured graph launch), ONE D2H copy
-    # of obs / delta_pos / status into the pinned output block (ssa_ukf_step_pinned: double-buffered, the copies
-    # overlap the neighbouring steps' kernels); C4 adds the shard reward terms + their NCCL gather every step.
+    # ---- e2e: the user-facing call with HOST buffers (ssa_ukf_step_pinned: double-buffered pinned blocks, the copies
+    # overlap the neighbouring steps' kernels).  Every step: ONE H2D copy of that step's inputs (z_noise + trans_matrix)
+    # from the handle's pinned input block, the kernel chain (one captured graph launch) and a D2H read of the step's
+    # result.  C4's result is what BASELINE.json config 4 names — the per-step reward terms, reduced per shard on the
+    # device, all-gathered over NCCL and read back to pinned host memory (40 B per rank); the filter state and the
+    # observations stay device-resident for a device-side consumer.  `e2e.full_outputs` is the same loop with the whole
+    # per-object output block (obs 96 B + delta_pos 8 B + status 4 B per object) copied to the host every step as well
+    # (C2's e2e, and round 1's definition): that one is bound by PCIe / host memory, not by the GPUs.
     io = ukf.host_io()
     for b_ in range(2):
         io[b_]["z_noise"][:] = zn[b_]
         io[b_]["M"][:] = M.reshape(9)
-    for w in range(4):
-        ukf.step_pinned(flags, stream=sp)
-    ukf.host_join(stream=sp)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches_e0 = ukf.launch_count
-    e0.record(stream)
-    for s in range(a.steps):
-        b_ = ukf.next_parity
-        io[b_]["M"][:] = M.reshape(9)  # this step's trans_matrix[i] (72 B) travels with the noise
-        ukf.step_pinned(flags, stream=sp)
-        if c4 and world > 1:
-            reward_gather()
-    ukf.host_join(stream=sp)
-    e1.record(stream)
-    barrier()
-    e2e_ms = e0.elapsed_time(e1) / a.steps
-    e2e_launches = ukf.launch_count - launches_e0
-    obs_np = io[0]["obs"]
-    clocks = sampler.stop()  # sampled over both timed regions (value and e2e)
-    assert np.isfinite(obs_np).all()
+    gathered_host = torch.empty(world * 5, dtype=torch.float64).pin_memory() if c4 else None
+
+    def e2e_loop(extra_flags):
+        for w in range(4):
+            ukf.step_pinned(flags | extra_flags, stream=sp)
+        ukf.host_join(stream=sp)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ukf.launch_count
+        e0.record(stream)
+        for s in range(a.steps):
+            b_ = ukf.next_parity
+            io[b_]["M"][:] = M.reshape(9)  # this step's trans_matrix[i] (72 B) travels with the noise
+            ukf.step_pinned(flags | extra_flags, stream=sp)
+            if c4:
+                reward_gather()
+                gathered_host.copy_(gathered, non_blocking=True)
+        ukf.host_join(stream=sp)
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1) / a.steps, ukf.launch_count - l0
+
+    full_ms, full_launches = e2e_loop(0)
     h2d = io[0]["z_noise"].nbytes + 80 + 8  # z_noise, trans_matrix (+1 pad double), the env's action word
-    d2h = io[0]["obs"].nbytes + (ukf.ld + ukf.ld // 2) * 8
+    d2h_full = io[0]["obs"].nbytes + (ukf.ld + ukf.ld // 2) * 8 + (40 * world if c4 else 0)
+    if c4:
+        e2e_ms, e2e_launches = e2e_loop(F.STEP_NO_D2H)
+        d2h = 40 * world
+        g2 = gathered_host.numpy().reshape(world, 5)
+        assert g2[:, 2].sum() == total and np.isfinite(g2).all()
+    else:
+        e2e_ms, e2e_launches, d2h = full_ms, full_launches, d2h_full
+    obs_np = io[0]["obs"]
+    clocks = sampler.stop()  # sampled over the timed regions (value and e2e)
+    assert np.isfinite(obs_np).all()
 
     # ---- reduce over ranks (max time) --------------------------------------------------------------
-    t = torch.tensor([total_ms, b2b_ms, e2e_ms] + [float(v) for v in kms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, b2b_ms, e2e_ms, full_ms] + [float(v) for v in kms], dtype=torch.float64, device="cuda")
     per_rank = [total_ms / a.steps]
     if world > 1:
         allr = [torch.zeros_like(t) for _ in range(world)]
@@ -653,8 +753,8 @@ def run_catalog(a, rank, local_rank, world):
         per_rank = [float(r_[0]) / a.steps for r_ in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tl = [float(v) for v in t.tolist()]
-    total_ms, b2b_ms, e2e_ms = tl[:3]
-    kms = np.array(tl[3:])
+    total_ms, b2b_ms, e2e_ms, full_ms = tl[:4]
+    kms = np.array(tl[4:])
     ms_per_step = total_ms / a.steps
     units = total
     value = units / (ms_per_step * 1e-3)
@@ -674,6 +774,7 @@ def run_catalog(a, rank, local_rank, world):
             extra_c3 = {k: l3[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "object_predicts_per_s")}
             extra_c3["workload"] = l3["config"]["workload"]
             extra_c3["e2e_bytes_per_step"] = {"h2d": l3["e2e"]["h2d_bytes_per_step"], "d2h": l3["e2e"]["d2h_bytes_per_step"]}
+            extra_c3["ppo_collector_on_device"] = c3_collector_measure(a3, local_rank, 64, 5)
         except Exception as ex:  # the headline must not be lost to a failure of an extra
             extra_c3 = {"error": repr(ex)}
     barrier()
@@ -733,12 +834,23 @@ def run_catalog(a, rank, local_rank, world):
                                  "step's kernels from the committed ncu capture (profiles/r02_ncu_kernels.json) when one exists for this shard size"},
             "e2e": {"value": e2e_val, "unit": "object-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "gpu_launches": int(e2e_launches), "bytes_are": "per rank",
-                    "api": "BatchedUKF.step_pinned (ssa_ukf_step_pinned): pinned host I/O blocks, 1 H2D + 1 graph launch + 1 D2H per step"
-                           + (" + shard reward terms + NCCL all_gather" if (c4 and world > 1) else ""),
-                    "limiter": f"PCIe / host memory: every step moves {(h2d + d2h) * world / 1e6:.1f} MB between the GPUs and pinned host "
-                               f"memory ({(h2d + d2h) * world / (e2e_ms * 1e-3) / 1e9:.1f} GB/s aggregate), the kernels alone need {ms_per_step:.3f} ms",
+                    "api": "BatchedUKF.step_pinned (ssa_ukf_step_pinned): pinned host input block, 1 H2D + 1 graph launch per step"
+                           + (" + ssa_ukf_catalog_stats + NCCL all_gather of the shard reward terms + their D2H read" if c4 else
+                              " + 1 D2H of obs / delta_pos / status"),
+                    "result_read_back": ("the step's reward terms (max delta_pos, trinary reward, arg-max trace: 5 doubles per shard) of "
+                                         "every rank, after the NCCL all_gather; state and observations stay device-resident" if c4
+                                         else "obs [N,12], delta_pos [N], status [N]"),
+                    "full_outputs": {"value": units / (full_ms * 1e-3), "ms_per_step": full_ms, "d2h_bytes_per_step": d2h_full,
+                                     "gpu_launches": int(full_launches),
+                                     "what": "same loop, the whole per-object output block (obs, delta_pos, status: 108 B per object) "
+                                             "also copied to pinned host memory every step",
+                                     "limiter": f"PCIe / host memory: {(h2d + d2h_full) * world / 1e6:.1f} MB per step between the GPUs and one "
+                                                f"host ({(h2d + d2h_full) * world / (full_ms * 1e-3) / 1e9:.1f} GB/s aggregate); the kernels "
+                                                f"alone need {ms_per_step:.3f} ms"},
+                    "limiter": (f"H2D of the measurements ({h2d * world / 1e6:.1f} MB per step, {h2d * world / (e2e_ms * 1e-3) / 1e9:.1f} GB/s "
+                                f"aggregate) overlapped with the kernels ({ms_per_step:.3f} ms)"),
                     "l2": "not flushed: the filter state is device-resident between steps by design; every step's inputs arrive "
-                          "from pinned host memory and its outputs leave to pinned host memory inside the timed region"},
+                          "from pinned host memory and its result leaves to pinned host memory inside the timed region"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "extra": {"ms_per_step_back_to_back_no_flush": b2b_ms, "wall_s_timed_region": t_wall, "failed_filters": n_failed,

@@ -101,6 +101,9 @@ enum ssa_field {
   SSA_F_CATALOG_STATS = 28, /* double [5]: max delta_pos, sum of trinary counts, objects, max trace P, its index */
   SSA_F_ROLLOUT_OBS = 29,   /* device views of the episodic mode's output block: obs [N][12] ...              */
   SSA_F_ROLLOUT_REWARD = 30, /* ... and reward [E] (for an NCCL gather onto a learner's device)                 */
+  SSA_F_ROLLOUT_ACTIONS = 31, /* int32 [E]: the device-side action buffer read by ssa_ukf_rollout_step(.., auto_reset | 2, ..) */
+  SSA_F_ROLLOUT_DONE = 32,    /* uint8 [E]  and                                                                    */
+  SSA_F_ROLLOUT_GREEDY = 33,  /* int32 [E][SSA_N_TASKERS] of the episodic output block                             */
   SSA_F_COUNT_
 };
 
@@ -124,6 +127,9 @@ enum ssa_field {
 #define SSA_STEP_RECORD 0x20      /* also store z_true, y, S, sigmas_h of updated objects (SS2:298-304) */
 #define SSA_STEP_M_PER_ENV 0x40   /* vectorised envs at different step indices: use the uploaded SSA_F_TRANS_ENV
                                      table (double[E][9], one trans_matrix per environment) instead of M      */
+#define SSA_STEP_NO_D2H 0x80    /* ssa_ukf_step_pinned only: do not copy the per-object output block (obs, delta_pos, status)
+                                   back to the host; the state stays device-resident and the caller reads what it needs (e.g. the
+                                   shard reward terms of ssa_ukf_catalog_stats) */
 
 int ssa_ukf_abi_version(void);
 const char* ssa_ukf_last_error(void);
@@ -201,6 +207,10 @@ int ssa_ukf_rollout_config(ssa_ukf* h, const double* orbits, int n_orbits, const
                            int update_interval);
 int ssa_ukf_rollout_io(ssa_ukf* h, int32_t** actions, double** obs, double** reward, int32_t** greedy, uint8_t** done);
 int ssa_ukf_rollout_reset(ssa_ukf* h, void* stream);
+/* auto_reset bit 0: re-draw finished environments inside the step; bit 1 (SSA_ROLLOUT_DEVICE_IO): no host copies —
+ * the actions are read from the device buffer SSA_F_ROLLOUT_ACTIONS and obs / reward / done / greedy stay in the device
+ * block (SSA_F_ROLLOUT_*), for a policy that lives on the same GPU (everything stream-ordered, nothing synchronises). */
+#define SSA_ROLLOUT_DEVICE_IO 2
 int ssa_ukf_rollout_step(ssa_ukf* h, int auto_reset, void* stream);
 /* make `stream` wait for every outstanding internal copy of ssa_ukf_step_host / ssa_ukf_step_pinned */
 int ssa_ukf_host_join(ssa_ukf* h, void* stream);

@@ -18,6 +18,7 @@ REWARD_JONES, REWARD_TRINARY, REWARD_SHAPED = 0, 1, 2
 ST_FAILED, ST_LINALG, ST_NAN, ST_FXEXC, ST_TRUTHEXC, ST_IN_UPDATE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 STEP_TRUTH, STEP_PREDICT, STEP_UPDATE_ALL, STEP_UPDATE_ACT, STEP_EPILOGUE, STEP_RECORD = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 STEP_M_PER_ENV = 0x40
+STEP_NO_D2H = 0x80
 N_TASKERS = 6
 (TASKER_NAIVE_GREEDY, TASKER_VISIBLE_GREEDY, TASKER_POS_ERROR_GREEDY, TASKER_VEL_ERROR_GREEDY, TASKER_VISIBLE_GREEDY_AER,
  TASKER_SHANNON) = range(6)
@@ -25,7 +26,8 @@ N_TASKERS = 6
 (F_X_TRUE, F_X_FILTER, F_P_FILTER, F_OBS, F_DELTA_POS, F_DELTA_VEL, F_SIGMA_POS, F_SIGMA_VEL, F_TRACE,
  F_Z_TRUE, F_Y, F_S, F_SIGMAS_H, F_Z_NOISE, F_VISIBLE, F_STATUS, F_INFLATIONS, F_ACTIONS, F_REWARD, F_DONE,
  F_GREEDY, F_SCORES, F_UPDATED, F_TRANS_ENV, F_STEP_INDEX, F_ENV_STATS, F_DIAG, F_INNOV_FLAGS, F_CATALOG_STATS,
- F_ROLLOUT_OBS, F_ROLLOUT_REWARD) = range(31)
+ F_ROLLOUT_OBS, F_ROLLOUT_REWARD, F_ROLLOUT_ACTIONS, F_ROLLOUT_DONE, F_ROLLOUT_GREEDY) = range(34)
+ROLLOUT_DEVICE_IO = 2
 
 
 class SsaUkfCfg(ctypes.Structure):

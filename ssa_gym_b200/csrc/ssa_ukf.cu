@@ -1680,6 +1680,8 @@ struct ssa_ukf {
   double* diag;     // [N][2] NEES, NIS of the last ssa_ukf_diagnostics call
   void* snap;       // device block of ssa_ukf_snapshot (allocated on first use)
   void* cat_part; double* cat_stats;  // ssa_ukf_catalog_stats: per-block partials, result [5]
+  const double *last_dpos, *last_trace;  // where the most recent step left delta_pos / trace (the handle's arrays, or a
+                                         // block of the double-buffered host pipeline)
   size_t stage_bytes;
 };
 
@@ -1916,6 +1918,15 @@ static int field_info(ssa_ukf* h, int field, void** p, size_t* bytes, int* soa_c
     case SSA_F_ROLLOUT_REWARD:
       if (!h->ro.init) { snprintf(g_err, sizeof(g_err), "episodic mode not configured"); return SSA_EINVAL; }
       *p = h->ro.dout + 12 * N; *bytes = E * 8; break;
+    case SSA_F_ROLLOUT_ACTIONS:
+      if (!h->ro.init) { snprintf(g_err, sizeof(g_err), "episodic mode not configured"); return SSA_EINVAL; }
+      *p = h->ro.act_in; *bytes = E * 4; break;
+    case SSA_F_ROLLOUT_GREEDY:
+      if (!h->ro.init) { snprintf(g_err, sizeof(g_err), "episodic mode not configured"); return SSA_EINVAL; }
+      *p = (int32_t*)(h->ro.dout + 12 * N + E); *bytes = E * SSA_N_TASKERS * 4; break;
+    case SSA_F_ROLLOUT_DONE:
+      if (!h->ro.init) { snprintf(g_err, sizeof(g_err), "episodic mode not configured"); return SSA_EINVAL; }
+      *p = (uint8_t*)((int32_t*)(h->ro.dout + 12 * N + E) + SSA_N_TASKERS * E); *bytes = E; break;
     case SSA_F_INNOV_FLAGS: *p = h->innov_flags; *bytes = N; break;
     default: snprintf(g_err, sizeof(g_err), "unknown field %d", field); return SSA_EINVAL;
   }
@@ -2100,8 +2111,17 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
   return SSA_OK;
 }
 
+static void set_last_outputs(ssa_ukf* h, int hostbuf) {
+  if (hostbuf < 0) { h->last_dpos = h->dpos; h->last_trace = h->trace; return; }
+  const long N_ = h->cfg.n_objects, ld_ = h->ld;
+  const double* dpos = h->hp.block[hostbuf] + 12 * N_;
+  h->last_dpos = dpos;
+  h->last_trace = dpos + ld_ + ld_ / 2 + 3 * ld_;   // [dpos ld][status ld/2][dvel ld][spos ld][svel ld][trace ld]
+}
+
 int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
   if (!h) return SSA_EINVAL;
+  set_last_outputs(h, -1);
   if (!h->sg.on || h->use_team || (flags & SSA_STEP_M_PER_ENV) || !M || h->chunk < h->cfg.n_objects)
     return step_impl(h, M, flags, stream, nullptr);
   CK(cudaSetDevice(h->device));
@@ -2213,6 +2233,7 @@ int ssa_ukf_step_host(ssa_ukf* h, const double M[9], int flags, const int32_t* a
   if (h->hp.calls >= 2) CK(cudaStreamWaitEvent(st, h->hp.e_dn[b], 0));
   rc = step_impl(h, M, flags, stream, nullptr, b);
   if (rc) return rc;
+  set_last_outputs(h, b);
   CK(cudaEventRecord(h->hp.e_c[b], st));
   // download stream
   CK(cudaStreamWaitEvent(h->hp.dn, h->hp.e_c[b], 0));
@@ -2254,6 +2275,8 @@ int ssa_ukf_host_io(ssa_ukf* h, int parity, double** z_noise, double** M, int32_
 
 int ssa_ukf_step_pinned(ssa_ukf* h, int flags, void* stream, int* parity_used) {
   if (!h) return SSA_EINVAL;
+  const bool no_d2h = (flags & SSA_STEP_NO_D2H) != 0;
+  flags &= ~SSA_STEP_NO_D2H;
   if (flags & SSA_STEP_M_PER_ENV) { snprintf(g_err, sizeof(g_err), "ssa_ukf_step_pinned: one trans_matrix per call"); return SSA_EINVAL; }
   CK(cudaSetDevice(h->device));
   int rc = hostpipe_init(h);
@@ -2294,10 +2317,11 @@ int ssa_ukf_step_pinned(ssa_ukf* h, int flags, void* stream, int* parity_used) {
     rc = step_impl(h, nullptr, flags, stream, nullptr, b);
     if (rc) return rc;
   }
+  set_last_outputs(h, b);
   CK(cudaEventRecord(h->hp.e_c[b], st));
   // download stream
   CK(cudaStreamWaitEvent(h->hp.dn, h->hp.e_c[b], 0));
-  CK(cudaMemcpyAsync(h->hp.hout[b], blk, sizeof(double) * h->hp.out_doubles, cudaMemcpyDeviceToHost, h->hp.dn));
+  if (!no_d2h) CK(cudaMemcpyAsync(h->hp.hout[b], blk, sizeof(double) * h->hp.out_doubles, cudaMemcpyDeviceToHost, h->hp.dn));
   CK(cudaEventRecord(h->hp.e_dn[b], h->hp.dn));
   if (parity_used) *parity_used = b;
   h->hp.parity ^= 1;
@@ -2442,8 +2466,9 @@ int ssa_ukf_rollout_step(ssa_ukf* h, int auto_reset, void* stream) {
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t E = h->cfg.n_envs;
-  const int a = auto_reset ? 1 : 0;
-  CK(cudaMemcpyAsync(h->ro.act_in, h->ro.hin, sizeof(int32_t) * E, cudaMemcpyHostToDevice, st));
+  const int a = (auto_reset & 1) ? 1 : 0;
+  const bool device_io = (auto_reset & SSA_ROLLOUT_DEVICE_IO) != 0;
+  if (!device_io) CK(cudaMemcpyAsync(h->ro.act_in, h->ro.hin, sizeof(int32_t) * E, cudaMemcpyHostToDevice, st));
   const char* gv = getenv("SSA_UKF_GRAPH");
   if (!(gv && strcmp(gv, "0") == 0) && !h->use_team) {
     if (!h->ro.gexec[a]) {
@@ -2469,7 +2494,7 @@ int ssa_ukf_rollout_step(ssa_ukf* h, int auto_reset, void* stream) {
     const int rc = rollout_chain(h, st, a);
     if (rc) return rc;
   }
-  CK(cudaMemcpyAsync(h->ro.hout, h->ro.dout, h->ro.out_bytes, cudaMemcpyDeviceToHost, st));
+  if (!device_io) CK(cudaMemcpyAsync(h->ro.hout, h->ro.dout, h->ro.out_bytes, cudaMemcpyDeviceToHost, st));
   return SSA_OK;
 }
 
@@ -2552,7 +2577,10 @@ int ssa_ukf_catalog_stats(ssa_ukf* h, long index_offset, void* stream) {
   const long N = h->cfg.n_objects;
   int nb = (int)((N + 255) / 256);
   nb = nb > kStatBlocks ? kStatBlocks : nb;
-  ssa_cat_stats_stage1<<<nb, 256, 0, st>>>(h->dpos, h->trace, N, (CatPart*)h->cat_part);
+  // the reward terms of the MOST RECENT step: its delta_pos / trace live in the handle's arrays or, after a pinned /
+  // host-pipelined step, in that call's output block
+  ssa_cat_stats_stage1<<<nb, 256, 0, st>>>(h->last_dpos ? h->last_dpos : h->dpos, h->last_trace ? h->last_trace : h->trace, N,
+                                          (CatPart*)h->cat_part);
   ssa_cat_stats_stage2<<<1, 256, 0, st>>>((const CatPart*)h->cat_part, nb, N, index_offset, h->cat_stats);
   h->launches += 2;
   CK(cudaGetLastError());

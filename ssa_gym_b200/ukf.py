@@ -103,7 +103,8 @@ class BatchedUKF:
             _lib.F_STEP_INDEX: ((self.n_envs,), np.int32), _lib.F_ENV_STATS: ((self.n_envs, 4), np.float64),
             _lib.F_DIAG: ((self.N, 2), np.float64), _lib.F_INNOV_FLAGS: ((self.N,), np.uint8),
             _lib.F_CATALOG_STATS: ((5,), np.float64), _lib.F_ROLLOUT_OBS: ((self.N, 12), np.float64),
-            _lib.F_ROLLOUT_REWARD: ((self.n_envs,), np.float64),
+            _lib.F_ROLLOUT_REWARD: ((self.n_envs,), np.float64), _lib.F_ROLLOUT_ACTIONS: ((self.n_envs,), np.int32),
+            _lib.F_ROLLOUT_DONE: ((self.n_envs,), np.uint8), _lib.F_ROLLOUT_GREEDY: ((self.n_envs, _lib.N_TASKERS), np.int32),
         }
 
     # -- lifetime ---------------------------------------------------------------------------------
@@ -249,8 +250,9 @@ class BatchedUKF:
     def rollout_reset(self, stream=None):
         _lib.check(self.lib.ssa_ukf_rollout_reset(self.h, stream), "ssa_ukf_rollout_reset")
 
-    def rollout_step(self, auto_reset=True, stream=None):
-        _lib.check(self.lib.ssa_ukf_rollout_step(self.h, 1 if auto_reset else 0, stream), "ssa_ukf_rollout_step")
+    def rollout_step(self, auto_reset=True, stream=None, device_io=False):
+        mode = (1 if auto_reset else 0) | (_lib.ROLLOUT_DEVICE_IO if device_io else 0)
+        _lib.check(self.lib.ssa_ukf_rollout_step(self.h, mode, stream), "ssa_ukf_rollout_step")
 
     @property
     def next_parity(self):

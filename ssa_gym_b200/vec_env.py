@@ -211,6 +211,28 @@ class VecSSATaskerEnv:
         self.obs = io["obs"].reshape(self.E, self.m * 12)
         return self.obs, rewards, dones, self._infos  # E empty dicts, allocated once (4096 dict constructions cost 100 us)
 
+    # -- device-resident consumer (a policy on the same GPU): no host copies, nothing synchronises -------------------
+    def device_views(self):
+        """Zero-copy torch tensors over the episodic mode's device buffers: 'actions' int32 [E] (INPUT of
+        vector_step_device), 'obs' float64 [E, m*12], 'reward' float64 [E], 'done' uint8 [E], 'greedy' int32 [E, taskers].
+        The outputs are overwritten by every step; they are valid in stream order on the stream the step runs on."""
+        assert self.rng == 'device', "device views exist in the device-resident episodic mode (rng='device')"
+        if getattr(self, "_views", None) is None:
+            u = self.ukf
+            self._views = {"actions": u.torch_view(F.F_ROLLOUT_ACTIONS), "obs": u.torch_view(F.F_ROLLOUT_OBS).view(self.E, self.m * 12),
+                           "reward": u.torch_view(F.F_ROLLOUT_REWARD), "done": u.torch_view(F.F_ROLLOUT_DONE),
+                           "greedy": u.torch_view(F.F_ROLLOUT_GREEDY)}
+        return self._views
+
+    def vector_step_device(self, stream=None):
+        """One vectorised env step whose actions are ALREADY in device_views()['actions'] (written by a device-side
+        policy on the same stream) and whose obs / reward / done stay on the device: one CUDA-graph launch, no H2D, no D2H,
+        no synchronisation (the reference hands every observation to the learner process through the host).
+        The host mirrors (self.i, self.episodes) are not maintained in this mode."""
+        assert self.rng == 'device'
+        self.ukf.rollout_step(self.auto_reset, stream=stream, device_io=True)
+        return self.device_views()
+
     # -- device taskers --------------------------------------------------------------------------------------
     def greedy_actions(self, tasker=F.TASKER_VISIBLE_GREEDY):
         """agents.py argmax rules evaluated on the device for every env (valid after a step / reset); where the

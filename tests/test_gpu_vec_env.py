@@ -155,3 +155,31 @@ def test_device_episodic_mode_equals_twin_emulation(over):
     assert n_resets >= E
     assert H.bits_equal(vec.ukf.download(F.F_X_FILTER), st.x) and H.bits_equal(vec.ukf.download(F.F_X_TRUE), st.x_true)
     vec.close()
+
+
+def test_device_resident_step_equals_host_io_step():
+    """vector_step_device (actions read from the device buffer, obs / reward / done / greedy left on the device, no copies,
+    no synchronisation) is the same step as vector_step: every output bit-equal over auto-resets."""
+    import torch
+    E = 64
+    cfg = dict(ssa_gym_b200.env_config, steps=12)
+    cfg["trans_matrix"] = gcrs2irts_matrix_approx(time_table(cfg["t_0"], cfg["time_step"], cfg["steps"]))
+    seeds = list(range(900, 900 + E))
+    a_env = VecSSATaskerEnv(cfg, E, seeds=seeds, rng="device")
+    b_env = VecSSATaskerEnv(cfg, E, seeds=seeds, rng="device")
+    v = b_env.device_views()
+    assert np.array_equal(v["obs"].cpu().numpy(), a_env.obs)
+    rng = np.random.RandomState(4)
+    n_done = 0
+    for t in range(30):
+        act = rng.randint(0, cfg["rso_count"], size=E).astype(np.int32)
+        obs, rew, done, _ = a_env.vector_step(act)
+        v["actions"].copy_(torch.from_numpy(act).to(v["actions"].device))
+        b_env.vector_step_device()
+        torch.cuda.synchronize()
+        assert H.bits_equal(v["obs"].cpu().numpy(), obs) and H.bits_equal(v["reward"].cpu().numpy(), rew)
+        assert np.array_equal(v["done"].cpu().numpy().astype(bool), done)
+        assert np.array_equal(v["greedy"].cpu().numpy(), a_env._io["greedy"])
+        n_done += int(done.sum())
+    assert n_done > E
+    a_env.close(); b_env.close()
