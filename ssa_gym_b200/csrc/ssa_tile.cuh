@@ -35,7 +35,7 @@
 #define SSA_LB_PT 4  // resident CTAs per SM the predict tile kernel is compiled for (224 threads: 4 -> 72 registers)
 #endif
 #ifndef SSA_LB_UTILE
-#define SSA_LB_UTILE 5
+#define SSA_LB_UTILE 4  // (5 CTAs at 56 registers spill in the measurement phase: 0.654 vs 0.639 ms at 1 M objects)
 #endif
 constexpr int kTileThreads = 14 * SSA_TILE / SSA_TILE_ROUNDS;
 static_assert((14 * SSA_TILE) % SSA_TILE_ROUNDS == 0 && kTileThreads % SSA_TILE == 0 && kTileThreads % 32 == 0, "tile shape");
