@@ -764,8 +764,7 @@ def run_catalog(a, rank, local_rank, world):
     # ---- short C2 / C3 sub-measurements on rank 0 (the other ranks wait) ---------------------------------------
     extra_c2 = extra_c3 = None
     tile = os.environ.get("SSA_UKF_KERNEL", "tile") not in ("split", "team")
-    if rank == 0 and not a.no_extra:
-        ukf_mem_free = None
+    if rank == 0 and not a.no_extra and world == 1:   # (N > 1: the other ranks would idle; the N = 1 line carries them)
         try:
             if a.workload != "c2":
                 extra_c2 = c2_measure(local_rank, 50, 5)
@@ -859,7 +858,7 @@ def run_catalog(a, rank, local_rank, world):
                       "step_ms_min": float(np.min(step_ms)), "step_ms_max": float(np.max(step_ms)),
                       "c2": extra_c2, "c3": extra_c3},
         }
-        if not a.no_cpu_baseline and world >= 1:
+        if not a.no_cpu_baseline and world == 1:   # the CPU baseline is timed on rank 0 at N = 1 only
             n_s = min(n_obj, 200_000)
             if c4:
                 catc, xc, P0c, znc = workload_inputs(total, 0, 4, 0, n_s)
