@@ -621,8 +621,9 @@ def run_catalog(a, rank, local_rank, world):
         ukf.catalog_stats(index_offset=lo, stream=sp)
         stats_view = ukf.torch_view(F.F_CATALOG_STATS)
 
+    step_flags = flags | (F.STEP_CATALOG_STATS if c4 else 0)   # C4: the reward reduction rides in the step's own graph
+
     def reward_gather():
-        ukf.catalog_stats(index_offset=lo, stream=sp)
         if world > 1:
             dist.all_gather_into_tensor(gathered, stats_view)
         else:
@@ -631,7 +632,7 @@ def run_catalog(a, rank, local_rank, world):
     # ---- warm-up -----------------------------------------------------------------------------------
     for w in range(max(a.warmup, 3)):
         load_noise(w)
-        ukf.step(M, flags, stream=sp)
+        ukf.step(M, step_flags, stream=sp)
         if c4:
             reward_gather()
     torch.cuda.synchronize()
@@ -649,7 +650,7 @@ def run_catalog(a, rank, local_rank, world):
         flush.fill_(s & 0xFF)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        ukf.step(M, flags, stream=sp)
+        ukf.step(M, step_flags, stream=sp)
         if c4:
             reward_gather()
         e1.record(stream)
@@ -689,7 +690,7 @@ def run_catalog(a, rank, local_rank, world):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for s in range(a.steps):
-        ukf.step(M, flags, stream=sp)
+        ukf.step(M, step_flags, stream=sp)
         if c4:
             reward_gather()
     e1.record(stream)
@@ -710,32 +711,36 @@ def run_catalog(a, rank, local_rank, world):
         io[b_]["M"][:] = M.reshape(9)
     gathered_host = torch.empty(world * 5, dtype=torch.float64).pin_memory() if c4 else None
 
-    def e2e_loop(extra_flags, read_reward):
+    host_issue = {}
+
+    def e2e_loop(extra_flags, read_reward, tag):
         for w in range(4):
-            ukf.step_pinned(flags | extra_flags, stream=sp)
+            ukf.step_pinned(step_flags | extra_flags, stream=sp)
         ukf.host_join(stream=sp)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ukf.launch_count
         e0.record(stream)
+        th0 = time.perf_counter()
         for s in range(a.steps):
             b_ = ukf.next_parity
             io[b_]["M"][:] = M.reshape(9)  # this step's trans_matrix[i] (72 B) travels with the noise
-            ukf.step_pinned(flags | extra_flags, stream=sp)
+            ukf.step_pinned(step_flags | extra_flags, stream=sp)
             if c4:
                 reward_gather()
                 if read_reward:
                     gathered_host.copy_(gathered, non_blocking=True)
+        host_issue[tag] = (time.perf_counter() - th0) / a.steps * 1e3   # host time to ISSUE one step (Python + driver + NCCL enqueue)
         ukf.host_join(stream=sp)
         e1.record(stream)
         barrier()
         return e0.elapsed_time(e1) / a.steps, ukf.launch_count - l0
 
-    full_ms, full_launches = e2e_loop(0, False)   # (the reward terms follow from the downloaded outputs)
+    full_ms, full_launches = e2e_loop(0, False, "full")   # (the reward terms follow from the downloaded outputs)
     h2d = io[0]["z_noise"].nbytes + 80 + 8  # z_noise, trans_matrix (+1 pad double), the env's action word
     d2h_full = io[0]["obs"].nbytes + (ukf.ld + ukf.ld // 2) * 8
     if c4:
-        e2e_ms, e2e_launches = e2e_loop(F.STEP_NO_D2H, True)
+        e2e_ms, e2e_launches = e2e_loop(F.STEP_NO_D2H, True, "reward")
         d2h = 40 * world
         g2 = gathered_host.numpy().reshape(world, 5)
         assert g2[:, 2].sum() == total and np.isfinite(g2).all()
@@ -847,8 +852,10 @@ def run_catalog(a, rank, local_rank, world):
                                      "limiter": f"PCIe / host memory: {(h2d + d2h_full) * world / 1e6:.1f} MB per step between the GPUs and one "
                                                 f"host ({(h2d + d2h_full) * world / (full_ms * 1e-3) / 1e9:.1f} GB/s aggregate); the kernels "
                                                 f"alone need {ms_per_step:.3f} ms"},
-                    "limiter": (f"H2D of the measurements ({h2d * world / 1e6:.1f} MB per step, {h2d * world / (e2e_ms * 1e-3) / 1e9:.1f} GB/s "
-                                f"aggregate) overlapped with the kernels ({ms_per_step:.3f} ms)"),
+                    "host_issue_ms_per_step": host_issue.get("reward", host_issue.get("full")),
+                    "limiter": (f"the kernels need {ms_per_step:.3f} ms per step, the host needs {host_issue.get('reward', host_issue.get('full')):.3f} ms to "
+                                f"issue one (Python + 1 H2D + 1 graph launch + NCCL enqueue + 1 D2H on rank 0's process); H2D of the measurements "
+                                f"({h2d * world / 1e6:.1f} MB per step, {h2d * world / (e2e_ms * 1e-3) / 1e9:.1f} GB/s aggregate) overlaps the kernels"),
                     "l2": "not flushed: the filter state is device-resident between steps by design; every step's inputs arrive "
                           "from pinned host memory and its result leaves to pinned host memory inside the timed region"},
             "gpu_launches": int(launches),

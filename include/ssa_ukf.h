@@ -127,6 +127,9 @@ enum ssa_field {
 #define SSA_STEP_RECORD 0x20      /* also store z_true, y, S, sigmas_h of updated objects (SS2:298-304) */
 #define SSA_STEP_M_PER_ENV 0x40   /* vectorised envs at different step indices: use the uploaded SSA_F_TRANS_ENV
                                      table (double[E][9], one trans_matrix per environment) instead of M      */
+#define SSA_STEP_CATALOG_STATS 0x100 /* ssa_ukf_step / ssa_ukf_step_pinned: append the shard reward reduction of
+                                   ssa_ukf_catalog_stats (index offset of its last explicit call) to the step's kernel chain,
+                                   inside the same captured graph */
 #define SSA_STEP_NO_D2H 0x80    /* ssa_ukf_step_pinned only: do not copy the per-object output block (obs, delta_pos, status)
                                    back to the host; the state stays device-resident and the caller reads what it needs (e.g. the
                                    shard reward terms of ssa_ukf_catalog_stats) */

@@ -19,6 +19,7 @@ ST_FAILED, ST_LINALG, ST_NAN, ST_FXEXC, ST_TRUTHEXC, ST_IN_UPDATE = 0x1, 0x2, 0x
 STEP_TRUTH, STEP_PREDICT, STEP_UPDATE_ALL, STEP_UPDATE_ACT, STEP_EPILOGUE, STEP_RECORD = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 STEP_M_PER_ENV = 0x40
 STEP_NO_D2H = 0x80
+STEP_CATALOG_STATS = 0x100
 N_TASKERS = 6
 (TASKER_NAIVE_GREEDY, TASKER_VISIBLE_GREEDY, TASKER_POS_ERROR_GREEDY, TASKER_VEL_ERROR_GREEDY, TASKER_VISIBLE_GREEDY_AER,
  TASKER_SHANNON) = range(6)

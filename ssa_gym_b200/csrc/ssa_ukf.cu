@@ -1683,6 +1683,7 @@ struct ssa_ukf {
   double* diag;     // [N][2] NEES, NIS of the last ssa_ukf_diagnostics call
   void* snap;       // device block of ssa_ukf_snapshot (allocated on first use)
   void* cat_part; double* cat_stats;  // ssa_ukf_catalog_stats: per-block partials, result [5]
+  long cat_index_offset;
   const double *last_dpos, *last_trace;  // where the most recent step left delta_pos / trace (the handle's arrays, or a
                                          // block of the double-buffered host pipeline)
   size_t stage_bytes;
@@ -2010,6 +2011,8 @@ struct StepOverride {  // episodic mode: redirect the step's inputs / outputs
   double* obs; const int32_t* actions; const double* table; const int32_t* step_idx; int bias, rows;
 };
 
+static int cat_stats_launch(ssa_ukf* h, const double* dpos, const double* trace, long index_offset, cudaStream_t st);
+
 static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cudaEvent_t* ev, int hostbuf = -1,
                      const StepOverride* ov = nullptr, KParams* p_out = nullptr) {
   if (!h) return SSA_EINVAL;
@@ -2109,6 +2112,10 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
       h->launches++;
     }
     if (evc) CK(cudaEventRecord(evc[5], st));
+  }
+  if (flags & SSA_STEP_CATALOG_STATS) {  // the shard's reward terms of THIS step, same chain / same graph
+    const int rc = cat_stats_launch(h, p.dpos, p.trace, h->cat_index_offset, st);
+    if (rc) return rc;
   }
   CK(cudaGetLastError());
   return SSA_OK;
@@ -2569,6 +2576,20 @@ int ssa_ukf_snapshot(ssa_ukf* h, void* host, size_t bytes, void* stream) {
   return SSA_OK;
 }
 
+static int cat_stats_launch(ssa_ukf* h, const double* dpos, const double* trace, long index_offset, cudaStream_t st) {
+  if (!h->cat_part) {
+    snprintf(g_err, sizeof(g_err), "SSA_STEP_CATALOG_STATS: call ssa_ukf_catalog_stats once first (it sets the index offset)");
+    return SSA_EINVAL;
+  }
+  const long N = h->cfg.n_objects;
+  int nb = (int)((N + 255) / 256);
+  nb = nb > kStatBlocks ? kStatBlocks : nb;
+  ssa_cat_stats_stage1<<<nb, 256, 0, st>>>(dpos, trace, N, (CatPart*)h->cat_part);
+  ssa_cat_stats_stage2<<<1, 256, 0, st>>>((const CatPart*)h->cat_part, nb, N, index_offset, h->cat_stats);
+  h->launches += 2;
+  return SSA_OK;
+}
+
 int ssa_ukf_catalog_stats(ssa_ukf* h, long index_offset, void* stream) {
   if (!h) return SSA_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
@@ -2577,15 +2598,11 @@ int ssa_ukf_catalog_stats(ssa_ukf* h, long index_offset, void* stream) {
     CK(cudaMalloc(&h->cat_part, sizeof(CatPart) * kStatBlocks + 8 * sizeof(double)));
     h->cat_stats = (double*)((CatPart*)h->cat_part + kStatBlocks);
   }
-  const long N = h->cfg.n_objects;
-  int nb = (int)((N + 255) / 256);
-  nb = nb > kStatBlocks ? kStatBlocks : nb;
+  h->cat_index_offset = index_offset;
   // the reward terms of the MOST RECENT step: its delta_pos / trace live in the handle's arrays or, after a pinned /
   // host-pipelined step, in that call's output block
-  ssa_cat_stats_stage1<<<nb, 256, 0, st>>>(h->last_dpos ? h->last_dpos : h->dpos, h->last_trace ? h->last_trace : h->trace, N,
-                                          (CatPart*)h->cat_part);
-  ssa_cat_stats_stage2<<<1, 256, 0, st>>>((const CatPart*)h->cat_part, nb, N, index_offset, h->cat_stats);
-  h->launches += 2;
+  const int rc = cat_stats_launch(h, h->last_dpos ? h->last_dpos : h->dpos, h->last_trace ? h->last_trace : h->trace, index_offset, st);
+  if (rc) return rc;
   CK(cudaGetLastError());
   return SSA_OK;
 }

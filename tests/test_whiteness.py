@@ -58,7 +58,7 @@ def test_device_innovation_stats_against_restatement():
 def test_env_durbin_watson_and_autocorrelation():
     import ssa_gym_b200
     from ssa_gym_b200 import agents, env as envmod
-    cfg = dict(ssa_gym_b200.env_config, steps=120, rso_count=6, reward_type="trinary", obs_limit=10)
+    cfg = dict(ssa_gym_b200.env_config, steps=120, rso_count=6, reward_type="trinary", obs_limit=-90)
     env = envmod.SSA_Tasker_Env(cfg)
     env.seed(3)
     obs, done = env.reset(), False
