@@ -32,103 +32,88 @@ class SSA_Tasker_Env(Env):
     metadata = {"render.modes": ["live", "none"]}
     visualization = None
 
+    # timers of the reference's `runtime` table that still mean something here (the plot_* entries have no counterpart)
+    RUNTIME_KEYS = ('__init__', 'reset', 'step', 'perform predictions', 'Observations and Reward', 'filter_error',
+                    'visible_objects')
+    # per-step history arrays of the reference (SS2:132-161): name -> trailing shape
+    HISTORIES = {'x_true': (6,), 'x_filter': (6,), 'P_filter': (6, 6), 'obs': (12,), 'z_noise': (3,), 'z_true': (3,), 'y': (3,),
+                 'S': (3, 3), 'delta_pos': (), 'delta_vel': (), 'sigma_pos': (), 'sigma_vel': (), 'scores': (), 'nees': ()}
+
     def __init__(self, config=None):
-        s = time.time()
+        t_start = time.time()
         if config is None:
             from . import env_config
             config = env_config
-        self.runtime = {'__init__': 0, 'reset': 0, 'step': 0, 'step prep': 0, 'propagate next true state': 0,
-                        'perform predictions': 0, 'update with observation': 0, 'Observations and Reward': 0,
-                        'filter_error': 0, 'visible_objects': 0, 'object_visibility': 0, 'anees': 0,
-                        'failed_filters': 0, 'plot_sigma_delta': 0, 'plot_rewards': 0, 'plot_anees': 0,
-                        'plot_actions': 0, 'all_true_obs': 0, 'plot_visibility': 0, 'predict method': 0}
-        self.t_0 = config.get('t_0', datetime(2020, 5, 4, 0, 0, 0))
-        self.dt = config['time_step']
-        self.n = config['steps']
-        self.m = config['rso_count']
-        self.obs_limit = np.radians(config['obs_limit'])
-        self.obs_returned = config['obs_returned']
-        self.reward_type = config['reward_type']
-        self.orbits = np.asarray(config['orbits'] if config.get('orbits') is not None else _default_orbits())
-        self.obs_lla = np.array(config['observer']) * [deg2rad, deg2rad, 1]
-        self.obs_itrs = lla2ecef(self.obs_lla)
-        self.update_interval = config['update_interval']
-        self.i = 0
-        self.obs_type = config['obs_type']
-        if self.obs_type == 'aer':
-            self.z_sigma = config['z_sigma'] * np.array([arcsec2rad, arcsec2rad, 1])
-        elif self.obs_type == 'xyz':
-            self.z_sigma = np.asarray(config['z_sigma'])
-        else:
-            raise ValueError('Invalid Observation Type: ' + str(config['obs_type']))
-        self.x_sigma = np.array(config['x_sigma'])
-        self.Q = Q_discrete_white_noise_block(self.dt, config['q_sigma'] ** 2, 3)
-        # operator plug points: resolved to device implementations, never called from the hot path
-        self.fx, self.hx = config.get('fx', dynamics.fx_xyz_farnocchia), config.get('hx')
-        self.mean_z, self.residual_z = config.get('mean_z'), config.get('residual_z')
-        self.msqrt = config.get('msqrt', dynamics.robust_cholesky)
-        if self.hx is None:
-            self.hx = dynamics.hx_aer_erfa if self.obs_type == 'aer' else dynamics.hx_xyz
-        dynamics.validate_operators(config, self.obs_type)
-        self.alpha, self.beta, self.kappa = config['alpha'], config['beta'], config['kappa']
-
-        x_dim, z_dim = 6, 3
-        self.P_0 = np.copy(np.diag(self.x_sigma ** 2)) if config.get('P_0') is None else np.copy(config['P_0'])
-        self.R = np.diag(self.z_sigma ** 2) if config.get('R') is None else np.copy(config['R'])
-        n, m = self.n, self.m
-        self.x_true = np.empty((n, m, x_dim))
-        self.x_filter = np.empty((n, m, x_dim))
-        self.P_filter = np.empty((n, m, x_dim, x_dim))
-        self.obs = np.empty((n, m, x_dim * 2))
-        self.time = time_table(self.t_0, self.dt, n)
-        if config.get('trans_matrix') is not None:
-            self.trans_matrix = np.ascontiguousarray(config['trans_matrix'], dtype=np.float64)
-            assert self.trans_matrix.shape == (n, 3, 3), "trans_matrix must be [steps, 3, 3]"
-        else:
-            self.eops = load_eop_c04(config['eop_file']) if config.get('eop_file') else default_eops()
-            self.trans_matrix = np.ascontiguousarray(gcrs2irts_matrix_b(self.time, self.eops))
-        self.z_noise = np.empty((n, m, z_dim))
-        self.z_true = np.empty((n, m, z_dim))
-        self.y = np.empty((n, m, z_dim))
-        self.S = np.empty((n, m, z_dim, z_dim))
-        self.x_noise = np.empty((m, x_dim))
-        self.delta_pos = np.empty((n, m))
-        self.delta_vel = np.empty((n, m))
-        self.sigma_pos = np.empty((n, m))
-        self.sigma_vel = np.empty((n, m))
-        self.scores = np.empty((n, m))
-        self.rewards = np.empty(n)
-        self.failed_filters_id = []
-        self.failed_filters_msg = ["None"] * m
-        self.actions = np.empty(n, dtype=int)
-        self.obs_taken = np.empty(n, dtype=bool)
-        self.x_failed = np.array([1e20, 1e20, 1e20, 1e12, 1e12, 1e12])
-        self.P_failed = np.diag([1e20, 1e20, 1e20, 1e12, 1e12, 1e12])
-        self.nees = np.empty((n, m))
-        self.visibility = []
-        self.sigmas_h = np.empty((n, x_dim * 2 + 1, z_dim))
-        self._visible_now = np.zeros(m, dtype=bool)
-
-        self.action_space = spaces.Discrete(m)
-        if self.obs_returned == 'flatten':
-            self.observation_space = spaces.Box(low=np.tile(-np.inf, (m * 12)), high=np.tile(np.inf, (m * 12)), dtype=np.float64)
-        elif self.obs_returned == 'aer':
-            self.observation_space = spaces.Box(low=np.tile(-np.inf, (m * 4)), high=np.tile(np.inf, (m * 4)), dtype=np.float64)
-            self.observation = np.zeros(m * 4)
-        else:
-            self.observation_space = spaces.Box(low=np.tile(-np.inf, (m, 12)), high=np.tile(np.inf, (m, 12)), dtype=np.float64)
-
+        self.runtime = dict.fromkeys(self.RUNTIME_KEYS, 0)
+        self._read_config(config)
+        self._allocate_histories()
+        self._make_spaces()
         # the device-resident filters: one handle for the m RSOs of this environment
-        self.ukf = BatchedUKF(n_envs=1, m=m, dt=self.dt, Q=self.Q, R=self.R, obs_lla=self.obs_lla,
-                              obs_limit_rad=self.obs_limit, alpha=self.alpha, beta=self.beta, kappa=self.kappa,
-                              obs_type=self.obs_type, reward_type=self.reward_type, n_steps=n,
-                              resample_after_predict=config.get('resample_after_predict', True),
-                              device=config.get('device', 0))
         self._device = config.get('device', 0)
+        self.ukf = BatchedUKF(n_envs=1, m=self.m, dt=self.dt, Q=self.Q, R=self.R, obs_lla=self.obs_lla,
+                              obs_limit_rad=self.obs_limit, alpha=self.alpha, beta=self.beta, kappa=self.kappa,
+                              obs_type=self.obs_type, reward_type=self.reward_type, n_steps=self.n,
+                              resample_after_predict=config.get('resample_after_predict', True), device=self._device)
         self.np_random = None
         self.init_seed = self.seed()
         self.reset()
-        self.runtime['__init__'] += time.time() - s
+        self.runtime['__init__'] += time.time() - t_start
+
+    def _read_config(self, config):
+        """env_config (envs/__init__.py:23-28) -> scalars, noise models, operators, trans_matrix table (SS2:81-137)."""
+        g = config.get
+        self.t_0, self.dt, self.n, self.m = g('t_0', datetime(2020, 5, 4, 0, 0, 0)), config['time_step'], config['steps'], config['rso_count']
+        self.obs_limit = np.radians(config['obs_limit'])
+        self.obs_returned, self.reward_type = config['obs_returned'], config['reward_type']
+        self.obs_type, self.update_interval = config['obs_type'], config['update_interval']
+        self.alpha, self.beta, self.kappa = config['alpha'], config['beta'], config['kappa']
+        self.orbits = np.asarray(g('orbits') if g('orbits') is not None else _default_orbits())
+        self.obs_lla = np.array(config['observer']) * [deg2rad, deg2rad, 1]
+        self.obs_itrs = lla2ecef(self.obs_lla)
+        # operator plug points: resolved to the device implementations, never called from the hot path
+        dynamics.validate_operators(config, self.obs_type)
+        self.fx, self.msqrt = g('fx', dynamics.fx_xyz_farnocchia), g('msqrt', dynamics.robust_cholesky)
+        self.hx = g('hx') or (dynamics.hx_aer_erfa if self.obs_type == 'aer' else dynamics.hx_xyz)
+        self.mean_z, self.residual_z = g('mean_z'), g('residual_z')
+        # noise models: measurement sigmas in (arcsec, arcsec, m) for 'aer' (SS2:100-104)
+        z_unit = np.array([arcsec2rad, arcsec2rad, 1]) if self.obs_type == 'aer' else 1.0
+        self.z_sigma = np.asarray(config['z_sigma']) * z_unit
+        self.x_sigma = np.array(config['x_sigma'])
+        self.Q = Q_discrete_white_noise_block(self.dt, config['q_sigma'] ** 2, 3)
+        self.P_0 = np.copy(np.diag(self.x_sigma ** 2)) if g('P_0') is None else np.copy(config['P_0'])
+        self.R = np.diag(self.z_sigma ** 2) if g('R') is None else np.copy(config['R'])
+        # GCRS -> ITRS rotation of every step: an INPUT of the path (SS2:136-137)
+        self.time = time_table(self.t_0, self.dt, self.n)
+        if g('trans_matrix') is not None:
+            self.trans_matrix = np.ascontiguousarray(config['trans_matrix'], dtype=np.float64)
+            assert self.trans_matrix.shape == (self.n, 3, 3), "trans_matrix must be [steps, 3, 3]"
+        else:
+            self.eops = load_eop_c04(config['eop_file']) if g('eop_file') else default_eops()
+            self.trans_matrix = np.ascontiguousarray(gcrs2irts_matrix_b(self.time, self.eops))
+
+    def _allocate_histories(self):
+        n, m = self.n, self.m
+        for name, tail in self.HISTORIES.items():
+            setattr(self, name, np.empty((n, m) + tail))
+        self.sigmas_h = np.empty((n, 13, 3))          # of the tasked object only (SS2:304)
+        self.x_noise = np.empty((m, 6))
+        self.rewards = np.empty(n)
+        self.actions = np.empty(n, dtype=int)
+        self.obs_taken = np.empty(n, dtype=bool)
+        self.i = 0
+        self.failed_filters_id, self.failed_filters_msg, self.visibility = [], ["None"] * m, []
+        self.x_failed = np.array([1e20] * 3 + [1e12] * 3)   # sentinels of a failed filter (SS2:157-158)
+        self.P_failed = np.diag(self.x_failed)
+        self._visible_now = np.zeros(m, dtype=bool)
+
+    def _make_spaces(self):
+        """SS2:164-177: Discrete(m) actions; observations 'flatten' [m*12], 'aer' [m*4] or [m, 12]."""
+        m = self.m
+        self.action_space = spaces.Discrete(m)
+        shape = {'flatten': (m * 12,), 'aer': (m * 4,)}.get(self.obs_returned, (m, 12))
+        self.observation_space = spaces.Box(low=np.full(shape, -np.inf), high=np.full(shape, np.inf), dtype=np.float64)
+        if self.obs_returned == 'aer':
+            self.observation = np.zeros(m * 4)
 
     # ------------------------------------------------------------------------------------------------
     def seed(self, seed=None):
