@@ -1013,32 +1013,11 @@ struct EnvParams {
   int increment;    // episodic mode: step_idx[e] += 1 before it is used (the device owns the counters)
   int greedy_only;  // refresh greedy / env_stats only (after an auto-reset); reward and done stay
   const double* P; long ld;   // packed covariances (agent_shannon: determinants)
+  const double* det_cur;      // [N] det P of the current covariances (ssa_det_kernel, thread per object)
   double* det_prev;           // [N] det P of the previous call (P_filter[i-1] of agents.py:24)
   const uint8_t* reset_mask;  // episodic refresh after an auto-reset: only these environments restart their det history
 };
 
-// det of a packed symmetric 6x6 by LU with partial pivoting (numpy.linalg.det = LAPACK getrf + product of the pivots)
-__device__ double ssa_det6_packed(const double* P, long ld, long n) {
-  double a[6][6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = i; j < 6; ++j) { a[i][j] = P[ssa_pidx(i, j) * ld + n]; a[j][i] = a[i][j]; }
-  double det = 1.0;
-  for (int c = 0; c < 6; ++c) {
-    int pv = c;
-    for (int i = c + 1; i < 6; ++i) if (fabs(a[i][c]) > fabs(a[pv][c])) pv = i;
-    if (pv != c) { for (int j = 0; j < 6; ++j) { const double t = a[c][j]; a[c][j] = a[pv][j]; a[pv][j] = t; } det = -det; }
-    det = ssa_mul(det, a[c][c]);
-    if (a[c][c] == 0.0) break;
-    const double rp = ssa_div(1.0, a[c][c]);
-    for (int i = c + 1; i < 6; ++i) {
-      const double l = ssa_mul(a[i][c], rp);
-      for (int j = c + 1; j < 6; ++j) a[i][j] = a[i][j] - ssa_mul(l, a[c][j]);
-    }
-  }
-  return det;
-}
 
 struct ArgMax { double v; int i; };
 __device__ __forceinline__ ArgMax am_better(ArgMax a, ArgMax b) {
@@ -1059,8 +1038,15 @@ __device__ __forceinline__ ArgMax am_warp(ArgMax a) {
   return a;
 }
 
+// det P of every object (agent_shannon), one thread per object: a chain of 6 divisions that would hold the per-environment
+// reduction below at 4 CTAs per SM if it ran there on m of 128 threads (measured: 50 us per launch at E = 4096)
+__global__ void __launch_bounds__(128) ssa_det_kernel(const double* __restrict__ P, long ld, int N, double* __restrict__ det_cur) {
+  const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) det_cur[n] = ssa_det6_sym(P + n, ld);
+}
+
 // One CTA per environment; threads stride over the m objects of the env.
-__global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) {
+__global__ void __launch_bounds__(128, 12) ssa_env_reduce_kernel(const EnvParams p) {
   const int e = blockIdx.x;
   const long base = (long)e * p.m;
   ArgMax a_trace{0.0, -1}, a_vtrace{0.0, -1}, a_vdpos{0.0, -1}, a_vdvel{0.0, -1}, a_spos{0.0, -1}, a_dpos{0.0, -1};
@@ -1074,7 +1060,7 @@ __global__ void __launch_bounds__(128) ssa_env_reduce_kernel(const EnvParams p) 
     // reference reads row -1 of its history array there): the ratio is taken as 1
     double shan = 0.0;
     if (p.det_prev && !(p.greedy_only && !restart)) {
-      const double det = ssa_det6_packed(p.P, p.ld, base + j);
+      const double det = p.det_cur[base + j];
       double prev = p.det_prev[base + j];
       if (restart || prev != prev) prev = det;  // (NaN = never set: ssa_ukf_reset)
       shan = ssa_log(ssa_div(det, prev));
@@ -1618,7 +1604,7 @@ struct ssa_ukf {
   long launches;
   // one slab for all fp64 SoA state
   double* slab;
-  double *xt, *x, *P, *dpos, *dvel, *spos, *svel, *trace, *det_prev;
+  double *xt, *x, *P, *dpos, *dvel, *spos, *svel, *trace, *det_prev, *det_cur;
   double *obs, *z_noise, *z_true, *y, *S, *sigmas_h, *scores, *reward, *env_stats;
   double* stage;  // staging for AoS<->SoA conversion ([N][39] doubles)
   double* qr;     // packed Q (21) + R (9)
@@ -1724,7 +1710,7 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
   h->ld = (N + 31) / 32 * 32;
   const long ld = h->ld;
   // fp64 slab: xt 6, x 6, P 21, dpos dvel spos svel trace 5 (SoA rows of ld) + AoS outputs
-  const size_t n_soa = (size_t)(6 + 6 + 21 + 5 + 1) * ld;
+  const size_t n_soa = (size_t)(6 + 6 + 21 + 5 + 2) * ld;
   const size_t n_aos = (size_t)N * (12 + 3 + 3 + 3 + 9 + 39 + 6 + 2) + (size_t)E * (1 + 4 + 9) + 32;
   cudaError_t e = cudaMalloc(&h->slab, (n_soa + n_aos) * sizeof(double));
   if (e != cudaSuccess) { delete h; return set_err("cudaMalloc(slab)", e); }
@@ -1735,6 +1721,7 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
   h->P = q; q += 21 * ld;
   h->dpos = q; q += ld; h->dvel = q; q += ld; h->spos = q; q += ld; h->svel = q; q += ld; h->trace = q; q += ld;
   h->det_prev = q; q += ld;
+  h->det_cur = q; q += ld;
   h->obs = q; q += N * 12;
   h->z_noise = q; q += N * 3;
   h->z_true = q; q += N * 3;
@@ -2361,8 +2348,15 @@ static void rollout_env_params(ssa_ukf* h, EnvParams* p, int increment, int gree
   p->env_stats = h->env_stats;
   p->E = h->cfg.n_envs; p->m = h->cfg.m; p->reward_type = h->cfg.reward_type; p->n_steps = h->cfg.n_steps;
   p->step_index = -1; p->step_idx = h->step_idx; p->increment = increment; p->greedy_only = greedy_only;
-  p->P = h->P; p->ld = h->ld; p->det_prev = h->det_prev;
+  p->P = h->P; p->ld = h->ld; p->det_prev = h->det_prev; p->det_cur = h->det_cur;
   p->reset_mask = nullptr;
+}
+
+static void launch_env_reduce(ssa_ukf* h, const EnvParams& ep, cudaStream_t st) {
+  const int N = h->cfg.n_objects;
+  ssa_det_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(h->P, h->ld, N, h->det_cur);
+  ssa_env_reduce_kernel<<<(unsigned)ep.E, 128, 0, st>>>(ep);
+  h->launches += 2;
 }
 
 // obs / errors / visibility of the current states + greedy taskers (after a reset)
@@ -2373,8 +2367,7 @@ static int rollout_refresh(ssa_ukf* h, cudaStream_t st, int only_done) {
   EnvParams ep;
   rollout_env_params(h, &ep, 0, 1);
   if (only_done) ep.reset_mask = ep.done;  // the environments k_env_reset has just re-drawn
-  ssa_env_reduce_kernel<<<(unsigned)ep.E, 128, 0, st>>>(ep);
-  h->launches++;
+  launch_env_reduce(h, ep, st);
   return SSA_OK;
 }
 
@@ -2460,8 +2453,7 @@ static int rollout_chain(ssa_ukf* h, cudaStream_t st, int auto_reset) {
   if (rc) return rc;
   EnvParams ep;
   rollout_env_params(h, &ep, 1, 0);
-  ssa_env_reduce_kernel<<<(unsigned)ep.E, 128, 0, st>>>(ep);
-  h->launches++;
+  launch_env_reduce(h, ep, st);
   if (auto_reset) {
     k_env_reset<<<(unsigned)rp.E, 128, 0, st>>>(rp);
     h->launches++;
@@ -2545,9 +2537,8 @@ int ssa_ukf_env_reduce(ssa_ukf* h, const double M[9], int step_index, void* stre
   p.step_index = step_index;
   p.step_idx = h->step_idx;
   p.increment = 0; p.greedy_only = 0;
-  p.P = h->P; p.ld = h->ld; p.det_prev = h->det_prev; p.reset_mask = nullptr;
-  ssa_env_reduce_kernel<<<(unsigned)p.E, 128, 0, st>>>(p);
-  h->launches++;
+  p.P = h->P; p.ld = h->ld; p.det_prev = h->det_prev; p.det_cur = h->det_cur; p.reset_mask = nullptr;
+  launch_env_reduce(h, p, st);
   CK(cudaGetLastError());
   return SSA_OK;
 }

@@ -236,6 +236,33 @@ SSA_HD double ssa_nis3(const double* S, const double* y, int* flags) {
   return acc;
 }
 
+// Determinant of a packed symmetric 6x6 (agent_shannon, agents.py:24: np.linalg.det(P)).  numpy factors with a pivoted
+// LU; for the symmetric (normally positive definite) covariances of the path the unpivoted symmetric elimination
+// P = L D L^T is just as stable, needs half the arithmetic and keeps its 21 entries in registers with static indices:
+// det = prod d_j.  The value agrees with LAPACK's to rounding (the tasker's argmax is compared with numpy up to ties
+// inside 1e-9 in tests/test_gpu_vs_oracle.py).  A zero pivot returns 0.
+SSA_HD double ssa_det6_sym(const double* P, long stride) {
+  double a[SSA_NP];
+#pragma unroll
+  for (int e = 0; e < SSA_NP; ++e) a[e] = P[e * stride];
+  double det = 1.0;
+  int zero = 0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const double d = a[ssa_pidx(j, j)];
+    det = ssa_mul(det, d);
+    zero |= (d == 0.0);
+    const double inv = ssa_div(1.0, d);
+#pragma unroll
+    for (int r = j + 1; r < 6; ++r) {
+      const double l = ssa_mul(a[ssa_pidx(j, r)], inv);
+#pragma unroll
+      for (int c = r; c < 6; ++c) a[ssa_pidx(r, c)] = ssa_fma(-l, a[ssa_pidx(j, c)], a[ssa_pidx(r, c)]);
+    }
+  }
+  return zero ? 0.0 : det;
+}
+
 // np.trace(P) over the packed diagonal, numpy's left-to-right order (agents.py:8,40)
 SSA_HD double ssa_trace6(const double* P, long stride) {
   double t = P[0];
