@@ -25,8 +25,12 @@ typedef struct {
 } ssa_obs;
 
 // hx for the 'aer' observation type.  out = [az, el, range].  INL: inlined math (k_hx), same arithmetic.
+// `enz` (optional): the topocentric vector e = T^T (x_itrs - obs_itrs) itself.  It IS the Cartesian image the update's
+// mean_z needs: aer2uvw(ecef2aer(.)) = (r cos el cos az, r cos el sin az, r sin el) with az = atan2(e1, e0),
+// el = asin(e2 / r), r = |e| is e again (transformations.py:283-297 after :329-352), so the two sincos of the round trip
+// are not evaluated for the 13 measurement sigma points (the identity holds to the rounding of that round trip, 1e-16).
 template <bool INL>
-SSA_HD void ssa_hx_aer_m(const double* x, const double* M, const double* obs_itrs, const double* T, double* out) {
+SSA_HD void ssa_hx_aer_m(const double* x, const double* M, const double* obs_itrs, const double* T, double* out, double* enz = nullptr) {
   // x_itrs = M @ x[:3]
   double xi[3], d[3], e[3];
   for (int i = 0; i < 3; ++i)
@@ -41,10 +45,11 @@ SSA_HD void ssa_hx_aer_m(const double* x, const double* M, const double* obs_itr
   out[0] = az;
   out[1] = INL ? ssa_asin_t<true>(ssa_div_i(e[2], r)) : ssa_asin(ssa_div(e[2], r));
   out[2] = r;
+  if (enz) { enz[0] = e[0]; enz[1] = e[1]; enz[2] = e[2]; }
 }
 template <bool INL>
-SSA_HD void ssa_hx_aer_t(const double* x, const ssa_obs* o, double* out) { ssa_hx_aer_m<INL>(x, o->M, o->obs_itrs, o->T, out); }
-SSA_HD void ssa_hx_aer(const double* x, const ssa_obs* o, double* out) { ssa_hx_aer_t<false>(x, o, out); }
+SSA_HD void ssa_hx_aer_t(const double* x, const ssa_obs* o, double* out, double* enz = nullptr) { ssa_hx_aer_m<INL>(x, o->M, o->obs_itrs, o->T, out, enz); }
+SSA_HD void ssa_hx_aer(const double* x, const ssa_obs* o, double* out, double* enz = nullptr) { ssa_hx_aer_t<false>(x, o, out, enz); }
 
 // Geodetic altitude of an ECEF position (transformations.py:239-279 `ecef2lla`, the closed form of You (2000);
 // only the altitude is needed by the catalog generator's 300 km rule, envs/orbit_gen.py:62).  WGS-84.

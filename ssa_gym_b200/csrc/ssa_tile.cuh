@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(NT, SSA_LB_UTILE) k_update_tile(const KParams 
     const bool live = !(sm.st[o] & SSA_ST_FAILED) && !sm.code[o];
     if (loc < p.Nc && (is_truth || live)) {
       const long obj = p.obj0 + loc;
-      double s[6], z[3];
+      double s[6], z[3], uvw[3];
       tile_sigma<T>(sm.S + US_X, sm.S + US_U, o, is_truth ? 0 : k, s);
       if (is_truth) {
 #pragma unroll
@@ -340,9 +340,9 @@ __global__ void __launch_bounds__(NT, SSA_LB_UTILE) k_update_tile(const KParams 
           const double* Mg = env_M(p, obj / p.m);
 #pragma unroll
           for (int i = 0; i < 9; ++i) M[i] = Mg[i];
-          ssa_hx_aer_m<true>(s, M, p.ob.obs_itrs, p.ob.T, z);
+          ssa_hx_aer_m<true>(s, M, p.ob.obs_itrs, p.ob.T, z, uvw);
         } else {
-          ssa_hx_aer_m<true>(s, p.ob.M, p.ob.obs_itrs, p.ob.T, z);
+          ssa_hx_aer_m<true>(s, p.ob.M, p.ob.obs_itrs, p.ob.T, z, uvw);
         }
       }
       if (is_truth) {
@@ -351,9 +351,7 @@ __global__ void __launch_bounds__(NT, SSA_LB_UTILE) k_update_tile(const KParams 
         sm.vis[o] = visible;
 #pragma unroll
         for (int a = 0; a < 3; ++a) sm.zt[a][o] = aer ? z[a] : s[a];
-      } else if (aer) {
-        double uvw[3];
-        ssa_aer2uvw_t<true>(z, uvw);
+      } else if (aer) {  // the Cartesian image of the measurement is the topocentric vector itself (ssa_meas.h)
 #pragma unroll
         for (int a = 0; a < 3; ++a) { sm.ZS[k * 3 + a][o] = z[a]; sm.UVW[k * 3 + a][o] = uvw[a]; }
       } else {

@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) 
 #pragma unroll
       for (int i = 0; i < 9; ++i) ob.M[i] = env_M(p, obj / p.m)[i];
     }
-    ssa_hx_aer(hin, &ob, zk);
+    double enz[3];
+    ssa_hx_aer(hin, &ob, zk, enz);
     // broadcast the truth measurement of lane 13
     double zt[3];
 #pragma unroll
@@ -287,10 +288,8 @@ __global__ void __launch_bounds__(kCtaThreads) ssa_step_kernel(const KParams p) 
         for (int a = 0; a < 3; ++a) z[a] = zt[a] + (p.z_noise ? p.z_noise[obj * 3 + a] : 0.0);
         if (p.obs_type == SSA_OBS_AER) {
           if (lane < 13) {
-            double uvw[3];
-            ssa_aer2uvw(zk, uvw);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) ws[WS_ZZ + lane * 3 + a] = uvw[a];
+            for (int a = 0; a < 3; ++a) ws[WS_ZZ + lane * 3 + a] = enz[a];
           }
           team_sync(tmask);
           if (lane < 3) ws[WS_ZM + lane] = ssa_wmean13(ws + WS_ZZ, 3, lane, p.Wm);
@@ -747,8 +746,7 @@ __global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx
 #pragma unroll
       for (int i = 0; i < 9; ++i) ob.M[i] = env_M(p, obj / p.m)[i];
     }
-    ssa_hx_aer_t<SSA_HX_INLINE>(s, &ob, z);
-    ssa_aer2uvw_t<SSA_HX_INLINE>(z, uvw);
+    ssa_hx_aer_t<SSA_HX_INLINE>(s, &ob, z, uvw);
 #pragma unroll
     for (int a = 0; a < 3; ++a) p.UVW[(k * 3 + a) * lds + loc] = uvw[a];
   } else {

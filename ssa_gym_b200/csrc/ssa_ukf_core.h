@@ -50,31 +50,40 @@ SSA_HD double ssa_pow10_infl(int t) {  // t = 0..15  <->  i = -6..9
   }
 }
 
-// Upper Cholesky A = U^T U of a packed 6x6 in registers (LAPACK dpotf2 'U' order: dot, sqrt,
-// row update scaled by the reciprocal of the pivot).  Returns 1 on success, 0 if a pivot is <= 0
-// or NaN (dpotrf info > 0 -> scipy LinAlgError) or if any entry is non-finite (scipy check_finite
-// -> ValueError); both are swallowed by robust_cholesky's bare except.
+// Upper Cholesky A = U^T U of a packed 6x6 in registers.  Returns 1 on success, 0 if a pivot is <= 0 or NaN (dpotrf
+// info > 0 -> scipy LinAlgError) or if any entry is non-finite (scipy check_finite -> ValueError); both are swallowed by
+// robust_cholesky's bare except.
+// Evaluated as the root-free factorisation A = L D L^T followed by U = sqrt(D) L^T: the pivots d_j are the same
+// quantities as LAPACK dpotf2's (a_jj minus the squares above it), so the success / failure decision is the same
+// condition, but the dependent chain of a column is ONE division instead of a square root AND a division — the kernels
+// that run this are nothing but that chain (k_factor / k_refactor: 6 columns per object at low occupancy), and the six
+// square roots at the end are independent of each other.  U agrees with dpotf2's to rounding (U^T U = A to 1e-15).
 template <bool INL>
 SSA_HD int ssa_chol6_t(double* a /* 21, in: A, out: U */) {
   int ok = 1;
 #pragma unroll
   for (int e = 0; e < SSA_NP; ++e) ok &= (ssa_fabs(a[e]) <= 1.79769313486231570815e+308);
+  double d[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double d = a[ssa_pidx(j, j)];
+    d[j] = a[ssa_pidx(j, j)];
+    ok &= (d[j] > 0.0);
+    const double inv = ssa_div_t<INL>(1.0, d[j]);
 #pragma unroll
-    for (int k = 0; k < j; ++k) d = ssa_fma(-a[ssa_pidx(k, j)], a[ssa_pidx(k, j)], d);
-    ok &= (d > 0.0);
-    const double ujj = ssa_sqrt_t<INL>(d);
-    a[ssa_pidx(j, j)] = ujj;
-    const double inv = ssa_div_t<INL>(1.0, ujj);
+    for (int r = j + 1; r < 6; ++r) {
+      const double l = ssa_mul(a[ssa_pidx(j, r)], inv);   // L[r][j]
 #pragma unroll
-    for (int c = j + 1; c < 6; ++c) {
-      double s = a[ssa_pidx(j, c)];
-#pragma unroll
-      for (int k = 0; k < j; ++k) s = ssa_fma(-a[ssa_pidx(k, j)], a[ssa_pidx(k, c)], s);
-      a[ssa_pidx(j, c)] = ssa_mul(s, inv);
+      for (int c = r; c < 6; ++c) a[ssa_pidx(r, c)] = ssa_fma(-l, a[ssa_pidx(j, c)], a[ssa_pidx(r, c)]);
     }
+#pragma unroll
+    for (int c = j + 1; c < 6; ++c) a[ssa_pidx(j, c)] = ssa_mul(a[ssa_pidx(j, c)], inv);   // row j of L^T
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const double sj = ssa_sqrt_t<INL>(d[j]);
+    a[ssa_pidx(j, j)] = sj;
+#pragma unroll
+    for (int c = j + 1; c < 6; ++c) a[ssa_pidx(j, c)] = ssa_mul(a[ssa_pidx(j, c)], sj);
   }
   return ok;
 }

@@ -130,7 +130,7 @@ void object_step(const ssa_ukf_cfg& cfg, const ssa_obs& ob, int flags, bool task
       double zs[SSA_NSIG][3], rz[SSA_NSIG][3], dx[SSA_NSIG][6], zp[3], Sm[9];
       if (cfg.obs_type == SSA_OBS_AER) {
         double uvw[SSA_NSIG][3], zm[3];
-        for (int k = 0; k < SSA_NSIG; ++k) { ssa_hx_aer(sig[k], &ob, zs[k]); ssa_aer2uvw(zs[k], uvw[k]); }
+        for (int k = 0; k < SSA_NSIG; ++k) ssa_hx_aer(sig[k], &ob, zs[k], uvw[k]);  // uvw = the topocentric vector (ssa_meas.h)
         for (int a = 0; a < 3; ++a) zm[a] = ssa_wmean13(&uvw[0][0], 3, a, cfg.Wm);
         ssa_uvw2aer(zm, zp);
         for (int k = 0; k < SSA_NSIG; ++k) ssa_residual_aer(zs[k], zp, rz[k]);
