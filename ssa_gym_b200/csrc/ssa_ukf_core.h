@@ -162,6 +162,7 @@ SSA_HD int ssa_inv3_t(const double* S /* row-major 3x3 */, double* SI) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) { a[i][j] = S[3 * i + j]; b[i][j] = (i == j) ? 1.0 : 0.0; }
   int ok = 1;
+  double rpiv[3];  // reciprocals of the three pivots: the back substitutions multiply by them (3 divisions instead of 12)
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     // pivot search (first maximum of |a[i][c]|, i >= c) and row swap, written with selects so the
@@ -179,6 +180,7 @@ SSA_HD int ssa_inv3_t(const double* S /* row-major 3x3 */, double* SI) {
     }
     ok &= (a[c][c] != 0.0);
     const double rp = ssa_div_t<INL>(1.0, a[c][c]);
+    rpiv[c] = rp;
 #pragma unroll
     for (int i = c + 1; i < 3; ++i) {
       a[i][c] = ssa_mul(a[i][c], rp);
@@ -192,9 +194,9 @@ SSA_HD int ssa_inv3_t(const double* S /* row-major 3x3 */, double* SI) {
     double y0 = b[0][col];
     double y1 = ssa_fma(-a[1][0], y0, b[1][col]);
     double y2 = ssa_fma(-a[2][1], y1, ssa_fma(-a[2][0], y0, b[2][col]));
-    const double x2 = ssa_div_t<INL>(y2, a[2][2]);
-    const double x1 = ssa_div_t<INL>(ssa_fma(-a[1][2], x2, y1), a[1][1]);
-    const double x0 = ssa_div_t<INL>(ssa_fma(-a[0][1], x1, ssa_fma(-a[0][2], x2, y0)), a[0][0]);
+    const double x2 = ssa_mul(y2, rpiv[2]);
+    const double x1 = ssa_mul(ssa_fma(-a[1][2], x2, y1), rpiv[1]);
+    const double x0 = ssa_mul(ssa_fma(-a[0][1], x1, ssa_fma(-a[0][2], x2, y0)), rpiv[0]);
     SI[col] = x0; SI[3 + col] = x1; SI[6 + col] = x2;
   }
   return ok;
