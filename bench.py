@@ -779,7 +779,7 @@ def run_catalog(a, rank, local_rank, world):
             extra_c3 = {k: l3[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "object_predicts_per_s")}
             extra_c3["workload"] = l3["config"]["workload"]
             extra_c3["e2e_bytes_per_step"] = {"h2d": l3["e2e"]["h2d_bytes_per_step"], "d2h": l3["e2e"]["d2h_bytes_per_step"]}
-            extra_c3["ppo_collector_on_device"] = c3_collector_measure(a3, local_rank, 64, 5)
+            extra_c3["ppo_collector_on_device"] = c3_collector_measure(a3, local_rank, 128, 10)
         except Exception as ex:  # the headline must not be lost to a failure of an extra
             extra_c3 = {"error": repr(ex)}
     barrier()
