@@ -1,29 +1,31 @@
 // ssa_ukf.cu — sm_100a kernels and the C ABI (include/ssa_ukf.h) of the UKF hot path.
 //
-// Two device implementations of the step live here, both bit-identical to the host twin
+// Three device implementations of the step live here, all bit-identical to the host twin
 // (tests/twin/twin.cpp):
-//  * the SPLIT PIPELINE (default): five kernels per step — k_factor, k_fx, k_ut, k_hx, k_update(_staged) — one
-//    thread per object for the small linear algebra, one thread per (sigma point, object) for the propagation `fx`
-//    and the measurement `hx` (>85 % of the fp64 work), objects fastest-varying so every access is coalesced; the
-//    update stages its operand tile with 2-D TMA loads (cp.async.bulk.tensor + mbarrier), the chain is linked by
-//    programmatic dependent launch (griddepcontrol) and replayed as a CUDA graph (ssa_ukf_step, _step_pinned,
-//    _rollout_step);
-//  * the TEAM KERNEL ssa_step_kernel (SSA_UKF_KERNEL=team): one launch, one object per 16-lane team (lanes 0..12
-//    own the sigma points, lane 13 the TRUE state), sigma set staged in a 1.7 KB shared-memory workspace per
-//    team, Cholesky / 3x3 inverse evaluated redundantly per lane.
-// Reductions over the 13 sigma points are sequential k = 0..12 FMAs in a FIXED order everywhere.
+//  * the TILE PIPELINE (default; ssa_tile.cuh): k_factor -> k_predict_tile -> k_refactor -> k_update_tile.  A CTA owns 32
+//    consecutive objects; the propagated sigma set and the measurement sigma set live in its shared memory only, the
+//    state tile arrives by one 2-D TMA load (cp.async.bulk.tensor + mbarrier), propagation / measurement tasks are mapped
+//    (object, sigma index) so that a warp holds the sigma points of at most four objects, the per-object linear algebra
+//    is spread over the tile's threads with every sum over the 13 sigma points in a fixed sequential order;
+//  * the SPLIT PIPELINE (SSA_UKF_KERNEL=split, and always for the RL-mode update of one tasked object per environment and
+//    for the book-version filter): k_factor, k_fx, k_ut, k_hx, k_update(_staged) — one thread per object for the small
+//    linear algebra, one thread per (sigma point, object) for fx / hx, intermediates in global scratch;
+//  * the TEAM KERNEL ssa_step_kernel (SSA_UKF_KERNEL=team): one launch, one object per 16-lane team.
+// The chain of a step is linked by programmatic dependent launch (griddepcontrol) and replayed as a CUDA graph
+// (ssa_ukf_step, _step_pinned, _rollout_step).
 //
 // HBM layout: struct-of-arrays fp64, leading dimension ld = N rounded up to 32:
-//   xt[6][ld]  x[6][ld]  P[21][ld] (packed upper triangle)  + per-object scalars [ld]
+//   xt[6][ld]  x[6][ld]  P[21][ld] (packed upper triangle; one [33][ld] tensor)  + per-object scalars [ld]
 // AoS only where the reference's own array layout is the interface (obs[N][12], z_noise[N][3], ...).
 //
 // Also here: the device-resident episodic mode (k_env_reset / k_env_begin: vectorised reset and on-the-fly noise with
-// the counter-based generator of ssa_rng.h), the per-env and per-shard reward reductions, consistency diagnostics,
-// the single-copy snapshot of the drop-in env's histories and the catalog generator's acceptance kernels.
+// the counter-based generator of ssa_rng.h), the per-env and per-shard reward reductions and heuristic taskers,
+// consistency diagnostics (NEES / NIS / innovation bounds, Durbin-Watson / autocorrelation), the single-copy snapshot of
+// the drop-in env's histories and the catalog generator's acceptance kernels.
 //
 // No tensor cores: nothing here is a dense contraction (13-term sums of 6x6 outer products).
-// No libdevice transcendental, no implicit FMA contraction (compiled with -fmad=false, every FMA is
-// explicit in the shared headers).
+// No libdevice transcendental, no implicit FMA contraction (compiled with -fmad=false, every FMA is explicit in the
+// shared headers).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
