@@ -709,15 +709,27 @@ def run_catalog(a, rank, local_rank, world):
     for b_ in range(2):
         io[b_]["z_noise"][:] = zn[b_]
         io[b_]["M"][:] = M.reshape(9)
-    gathered_host = torch.empty(world * 5, dtype=torch.float64).pin_memory() if c4 else None
+    # The step's result is read back OFF the compute stream: with SSA_STEP_CATALOG_STATS a pinned step reduces the shard's
+    # reward terms into the device slot of its parity and the library's download stream copies them to pinned host memory
+    # (N = 1: that is the read-back).  N > 1: a side stream all-gathers the slot over NCCL and copies the gathered rows
+    # to pinned host memory; the compute stream only waits — two steps later, before the slot is rewritten — for that
+    # gather to have finished.  (Measured, tools/e2e_probe.py: the same copies issued on the compute stream cost 40 us
+    # per step of serialisation between consecutive graph launches — 0.244 vs 0.204 ms per step at 125 000 objects.)
+    side = torch.cuda.Stream()
+    stats_host = [ukf.host_stats(b_)[0] for b_ in range(2)] if c4 else None
+    stats_dev = [ukf.host_stats_torch(b_) for b_ in range(2)] if c4 else None
+    gathered2 = [torch.zeros(world * 5, dtype=torch.float64, device="cuda") for _ in range(2)] if c4 else None
+    gathered_host2 = [torch.zeros(world * 5, dtype=torch.float64).pin_memory() for _ in range(2)] if c4 else None
 
     host_issue = {}
+    last_parity = {}
 
     def e2e_loop(extra_flags, read_reward, tag):
         for w in range(4):
             ukf.step_pinned(step_flags | extra_flags, stream=sp)
         ukf.host_join(stream=sp)
         barrier()
+        side_done = [None, None]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ukf.launch_count
         e0.record(stream)
@@ -725,13 +737,22 @@ def run_catalog(a, rank, local_rank, world):
         for s in range(a.steps):
             b_ = ukf.next_parity
             io[b_]["M"][:] = M.reshape(9)  # this step's trans_matrix[i] (72 B) travels with the noise
+            if side_done[b_] is not None:
+                stream.wait_event(side_done[b_])   # the gather of two steps ago has read this parity's slot
             ukf.step_pinned(step_flags | extra_flags, stream=sp)
-            if c4:
-                reward_gather()
-                if read_reward:
-                    gathered_host.copy_(gathered, non_blocking=True)
+            if c4 and read_reward and world > 1:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    dist.all_gather_into_tensor(gathered2[b_], stats_dev[b_])
+                    gathered_host2[b_].copy_(gathered2[b_], non_blocking=True)
+                    side_done[b_] = torch.cuda.Event()
+                    side_done[b_].record(side)
+            last_parity[tag] = b_
         host_issue[tag] = (time.perf_counter() - th0) / a.steps * 1e3   # host time to ISSUE one step (Python + driver + NCCL enqueue)
         ukf.host_join(stream=sp)
+        stream.wait_stream(side)
         e1.record(stream)
         barrier()
         return e0.elapsed_time(e1) / a.steps, ukf.launch_count - l0
@@ -742,8 +763,10 @@ def run_catalog(a, rank, local_rank, world):
     if c4:
         e2e_ms, e2e_launches = e2e_loop(F.STEP_NO_D2H, True, "reward")
         d2h = 40 * world
-        g2 = gathered_host.numpy().reshape(world, 5)
+        lp = last_parity["reward"]
+        g2 = (gathered_host2[lp].numpy() if world > 1 else np.array(stats_host[lp])).reshape(world, 5)
         assert g2[:, 2].sum() == total and np.isfinite(g2).all()
+        assert g2[rank if world > 1 else 0, 2] == n_obj
     else:
         e2e_ms, e2e_launches, d2h = full_ms, full_launches, d2h_full
     obs_np = io[0]["obs"]
@@ -840,7 +863,8 @@ def run_catalog(a, rank, local_rank, world):
             "e2e": {"value": e2e_val, "unit": "object-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "gpu_launches": int(e2e_launches), "bytes_are": "per rank",
                     "api": "BatchedUKF.step_pinned (ssa_ukf_step_pinned): pinned host input block, 1 H2D + 1 graph launch per step"
-                           + (" + ssa_ukf_catalog_stats + NCCL all_gather of the shard reward terms + their D2H read" if c4 else
+                           + (" (shard reward terms reduced in the same graph) + their D2H read on the download stream"
+                              + (" after an NCCL all_gather on a side stream" if world > 1 else "") if c4 else
                               " + 1 D2H of obs / delta_pos / status"),
                     "result_read_back": ("the step's reward terms (max delta_pos, trinary reward, arg-max trace: 5 doubles per shard) of "
                                          "every rank, after the NCCL all_gather; state and observations stay device-resident" if c4

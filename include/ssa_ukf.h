@@ -188,6 +188,12 @@ int ssa_ukf_step_host(ssa_ukf* h, const double M[9], int flags, const int32_t* a
 int ssa_ukf_host_io(ssa_ukf* h, int parity, double** z_noise, double** M, int32_t** actions, double** obs,
                     double** delta_pos, int32_t** status);
 int ssa_ukf_step_pinned(ssa_ukf* h, int flags, void* stream, int* parity_used);
+/* With SSA_STEP_CATALOG_STATS a pinned step also reduces the shard's reward terms (reward.py / SS2:324-354 over the
+ * whole shard: the 5 doubles of SSA_F_CATALOG_STATS) into the device slot of ITS parity and copies them to the pinned
+ * host block of that parity on the internal download stream - the caller's stream never waits for a read-back, and a
+ * consumer (host, or an NCCL gather on a side stream) may still read step s while step s + 1 runs.  Returns the two
+ * addresses of `parity`: host (valid after ssa_ukf_host_join + synchronize) and device.                         */
+int ssa_ukf_host_stats(ssa_ukf* h, int parity, double** stats_host, double** stats_device);
 /* ---- device-resident episodic mode (vectorised reset) ---------------------------------------------
  * Replaces, for E parallel environments, the whole host side of an RL step: reset() with its catalog sampling and
  * noise draws (SS2:193-241), the per-step bookkeeping of step() (SS2:243-367: step counter, trans_matrix[i],

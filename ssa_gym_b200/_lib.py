@@ -63,6 +63,7 @@ PROTOTYPES = {
     "ssa_ukf_step_host": (_I, [c_void_p, c_void_p, _I, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ssa_ukf_host_join": (_I, [c_void_p, c_void_p]),
     "ssa_ukf_host_io": (_I, [c_void_p, _I] + [c_void_p] * 6),
+    "ssa_ukf_host_stats": (_I, [c_void_p, _I, c_void_p, c_void_p]),
     "ssa_ukf_step_pinned": (_I, [c_void_p, _I, c_void_p, c_void_p]),
     "ssa_ukf_rollout_config": (_I, [c_void_p, c_void_p, _I, c_void_p, _I, c_void_p, c_void_p, c_void_p, c_void_p, _I]),
     "ssa_ukf_rollout_io": (_I, [c_void_p] + [c_void_p] * 5),

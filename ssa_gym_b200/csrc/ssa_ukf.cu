@@ -1618,6 +1618,8 @@ struct ssa_ukf {
   int pdl;  // programmatic dependent launch of the step's kernel chain (SSA_UKF_PDL=0 turns it off)
   int use_tile;   // tile kernels (default); SSA_UKF_KERNEL=split selects the five-kernel split pipeline
   int use_team;   // SSA_UKF_KERNEL=team selects the fused 16-lane team kernel instead of the split pipeline
+  int use_fused;  // one launch per full catalog step (k_step_tile) instead of the four tile kernels
+  int fold_factor;  // tile2: the two factorisations inside the tile kernels instead of k_factor / k_refactor
   // double-buffered host pipeline (ssa_ukf_step_host)
   struct {
     int init, parity;
@@ -1779,7 +1781,11 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
     const char* kv = getenv("SSA_UKF_KERNEL");
     h->use_team = (kv && strcmp(kv, "team") == 0) ? 1 : 0;
     h->use_tile = (kv && strcmp(kv, "split") == 0) ? 0 : 1;
-    cudaFuncSetAttribute(k_update_tile<SSA_TILE, kTileThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateTile<SSA_TILE>));
+    h->use_fused = (kv && strcmp(kv, "fused") == 0) ? 1 : 0;
+    h->fold_factor = (kv && strcmp(kv, "tile2") == 0) ? 1 : 0;
+    cudaFuncSetAttribute(k_update_tile<SSA_TILE, kTileThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateTile<SSA_TILE>));
+    cudaFuncSetAttribute(k_update_tile<SSA_TILE, kTileThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateTile<SSA_TILE>));
+    cudaFuncSetAttribute(k_step_tile<SSA_TILE, kTileThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateTile<SSA_TILE>));
     const char* gv = getenv("SSA_UKF_STEP_GRAPH");
     h->sg.on = (gv && strcmp(gv, "0") == 0) ? 0 : 1;
     const char* pv = getenv("SSA_UKF_PDL");
@@ -1998,7 +2004,7 @@ struct StepOverride {  // episodic mode: redirect the step's inputs / outputs
   double* obs; const int32_t* actions; const double* table; const int32_t* step_idx; int bias, rows;
 };
 
-static int cat_stats_launch(ssa_ukf* h, const double* dpos, const double* trace, long index_offset, cudaStream_t st);
+static int cat_stats_launch(ssa_ukf* h, const double* dpos, const double* trace, long index_offset, cudaStream_t st, double* out);
 
 static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cudaEvent_t* ev, int hostbuf = -1,
                      const StepOverride* ov = nullptr, KParams* p_out = nullptr) {
@@ -2073,26 +2079,37 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
     // the tile kernels keep the sigma sets in shared memory; the book-version filter (sigmas_f kept across calls)
     // and the RL-mode update of one tasked object per environment use the split kernels
     const bool tile = h->use_tile && p.resample;
-    if (predict || update) { launch_chain(pdl, k_factor, gobj2, kObjThreads, 0, st, p); h->launches++; }
+    if (tile && h->use_fused && predict && (flags & SSA_STEP_UPDATE_ALL)) {  // the whole step of the chunk in one launch
+      launch_chain(pdl, k_step_tile<SSA_TILE, kTileThreads>, gtile, kTileThreads, sizeof(UpdateTile<SSA_TILE>), st, p, h->tm_s, h->tm_u);
+      h->launches++;
+      if (evc) for (int i = 1; i <= 5; ++i) CK(cudaEventRecord(evc[i], st));
+      continue;
+    }
+    // SSA_UKF_KERNEL=tile2: the factorisations ride inside the tile kernels (two launches per catalog step, the factor
+    // never in HBM) instead of running as k_factor / k_refactor (default: four launches, measured faster — DESIGN.md)
+    const bool fold = tile && h->fold_factor && predict;
+    const bool tile_upd = tile && (flags & SSA_STEP_UPDATE_ALL);
+    if ((predict || update) && !fold) { launch_chain(pdl, k_factor, gobj2, kObjThreads, 0, st, p); h->launches++; }
     if (evc) CK(cudaEventRecord(evc[1], st));
     if (predict || truth) {
-      if (tile) launch_chain(pdl, k_predict_tile<SSA_TILE, kTileThreads>, gtile, kTileThreads, 0, st, p, h->tm_x, h->tm_u);
+      if (fold) launch_chain(pdl, k_predict_tile<SSA_TILE, kTileThreads, true>, gtile, kTileThreads, 0, st, p, h->tm_s, h->tm_u);
+      else if (tile) launch_chain(pdl, k_predict_tile<SSA_TILE, kTileThreads, false>, gtile, kTileThreads, 0, st, p, h->tm_x, h->tm_u);
       else launch_chain(pdl, k_fx, dim3(gfx, 14), kFxThreads, 0, st, p);
       h->launches++;
     }
     if (evc) CK(cudaEventRecord(evc[2], st));
     const bool staged = p.Nc <= h->staged_max;
-    if (predict) {
+    if (predict && !(fold && tile_upd)) {
       if (tile) launch_chain(pdl, k_refactor, gobj2, kObjThreads, 0, st, p);
       else launch_chain(pdl, k_ut, gobj2, kObjThreads, 0, st, p);
       h->launches++;
     }
     if (evc) CK(cudaEventRecord(evc[3], st));
-    const bool tile_upd = tile && (flags & SSA_STEP_UPDATE_ALL);
     if ((update || epi) && !tile_upd) { launch_chain(pdl, k_hx, dim3(gfx, 14), kFxThreads, 0, st, p); h->launches++; }
     if (evc) CK(cudaEventRecord(evc[4], st));
     if (update || epi) {
-      if (tile_upd) launch_chain(pdl, k_update_tile<SSA_TILE, kTileThreads>, gtile, kTileThreads, sizeof(UpdateTile<SSA_TILE>), st, p, h->tm_s, h->tm_u);
+      if (tile_upd && fold) launch_chain(pdl, k_update_tile<SSA_TILE, kTileThreads, true>, gtile, kTileThreads, sizeof(UpdateTile<SSA_TILE>), st, p, h->tm_s, h->tm_u);
+      else if (tile_upd) launch_chain(pdl, k_update_tile<SSA_TILE, kTileThreads, false>, gtile, kTileThreads, sizeof(UpdateTile<SSA_TILE>), st, p, h->tm_s, h->tm_u);
       else if (staged && p.resample && (flags & SSA_STEP_UPDATE_ALL))
         launch_chain(pdl, k_update_staged, (unsigned)((p.Nc + 31) / 32), 32, kUpdStagedSmem, st, p, h->tm_z, h->tm_u, h->tm_s);
       else launch_chain(pdl, k_update, gobj, kSplitThreads, 0, st, p);
@@ -2101,7 +2118,8 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
     if (evc) CK(cudaEventRecord(evc[5], st));
   }
   if (flags & SSA_STEP_CATALOG_STATS) {  // the shard's reward terms of THIS step, same chain / same graph
-    const int rc = cat_stats_launch(h, p.dpos, p.trace, h->cat_index_offset, st);
+    // (a pinned step writes the slot of its parity: the consumer of step i may still be reading while step i + 1 runs)
+    const int rc = cat_stats_launch(h, p.dpos, p.trace, h->cat_index_offset, st, hostbuf >= 0 ? h->cat_stats + 5 * (1 + hostbuf) : h->cat_stats);
     if (rc) return rc;
   }
   CK(cudaGetLastError());
@@ -2151,7 +2169,9 @@ int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
       cudaKernelNodeParams kp;
       if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel &&
           cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess &&
-          (kp.func == (void*)k_hx || kp.func == (void*)k_update_tile<SSA_TILE, kTileThreads>)) {
+          (kp.func == (void*)k_hx || kp.func == (void*)k_update_tile<SSA_TILE, kTileThreads, false> ||
+           kp.func == (void*)k_update_tile<SSA_TILE, kTileThreads, true> ||
+           kp.func == (void*)k_step_tile<SSA_TILE, kTileThreads>)) {
         h->sg.hx_node[gi] = nodes[i];
         h->sg.hx_params[gi] = kp;
       }
@@ -2164,7 +2184,7 @@ int ssa_ukf_step(ssa_ukf* h, const double M[9], int flags, void* stream) {
   }
   if (h->sg.hx_node[gi]) {  // this step's trans_matrix
     memcpy(h->sg.p[gi].ob.M, M, 9 * sizeof(double));
-    void* args[3] = {&h->sg.p[gi], &h->tm_s, &h->tm_u};  // k_hx takes the first, k_update_tile all three
+    void* args[3] = {&h->sg.p[gi], &h->tm_s, &h->tm_u};  // k_hx takes the first, k_update_tile / k_step_tile all three
     cudaKernelNodeParams kp = h->sg.hx_params[gi];
     kp.kernelParams = args;
     kp.extra = nullptr;
@@ -2192,9 +2212,9 @@ static int hostpipe_init(ssa_ukf* h) {
     CK(cudaMalloc(&h->hp.block[b], sizeof(double) * tot));
     CK(cudaMemset(h->hp.block[b], 0, sizeof(double) * tot));
     CK(cudaHostAlloc(&h->hp.hin[b], sizeof(double) * h->hp.in_doubles, cudaHostAllocDefault));
-    CK(cudaHostAlloc(&h->hp.hout[b], sizeof(double) * h->hp.out_doubles, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&h->hp.hout[b], sizeof(double) * (h->hp.out_doubles + 8), cudaHostAllocDefault));  // + the step's reward terms
     memset(h->hp.hin[b], 0, sizeof(double) * h->hp.in_doubles);
-    memset(h->hp.hout[b], 0, sizeof(double) * h->hp.out_doubles);
+    memset(h->hp.hout[b], 0, sizeof(double) * (h->hp.out_doubles + 8));
     h->hp.gexec[b] = nullptr;
     h->hp.gflags[b] = -1;
     CK(cudaEventCreateWithFlags(&h->hp.e_up[b], cudaEventDisableTiming));
@@ -2270,6 +2290,17 @@ int ssa_ukf_host_io(ssa_ukf* h, int parity, double** z_noise, double** M, int32_
   return SSA_OK;
 }
 
+int ssa_ukf_host_stats(ssa_ukf* h, int parity, double** stats_host, double** stats_device) {
+  if (!h || parity < 0 || parity > 1) return SSA_EINVAL;
+  if (!h->cat_stats) { snprintf(g_err, sizeof(g_err), "call ssa_ukf_catalog_stats first"); return SSA_EINVAL; }
+  CK(cudaSetDevice(h->device));
+  int rc = hostpipe_init(h);
+  if (rc) return rc;
+  if (stats_host) *stats_host = h->hp.hout[parity] + h->hp.out_doubles;
+  if (stats_device) *stats_device = h->cat_stats + 5 * (1 + parity);
+  return SSA_OK;
+}
+
 int ssa_ukf_step_pinned(ssa_ukf* h, int flags, void* stream, int* parity_used) {
   if (!h) return SSA_EINVAL;
   const bool no_d2h = (flags & SSA_STEP_NO_D2H) != 0;
@@ -2319,6 +2350,8 @@ int ssa_ukf_step_pinned(ssa_ukf* h, int flags, void* stream, int* parity_used) {
   // download stream
   CK(cudaStreamWaitEvent(h->hp.dn, h->hp.e_c[b], 0));
   if (!no_d2h) CK(cudaMemcpyAsync(h->hp.hout[b], blk, sizeof(double) * h->hp.out_doubles, cudaMemcpyDeviceToHost, h->hp.dn));
+  if ((flags & SSA_STEP_CATALOG_STATS) && h->cat_stats)  // the step's reward terms follow on the download stream (40 B)
+    CK(cudaMemcpyAsync(h->hp.hout[b] + h->hp.out_doubles, h->cat_stats + 5 * (1 + b), 5 * sizeof(double), cudaMemcpyDeviceToHost, h->hp.dn));
   CK(cudaEventRecord(h->hp.e_dn[b], h->hp.dn));
   if (parity_used) *parity_used = b;
   h->hp.parity ^= 1;
@@ -2567,7 +2600,7 @@ int ssa_ukf_snapshot(ssa_ukf* h, void* host, size_t bytes, void* stream) {
   return SSA_OK;
 }
 
-static int cat_stats_launch(ssa_ukf* h, const double* dpos, const double* trace, long index_offset, cudaStream_t st) {
+static int cat_stats_launch(ssa_ukf* h, const double* dpos, const double* trace, long index_offset, cudaStream_t st, double* out) {
   if (!h->cat_part) {
     snprintf(g_err, sizeof(g_err), "SSA_STEP_CATALOG_STATS: call ssa_ukf_catalog_stats once first (it sets the index offset)");
     return SSA_EINVAL;
@@ -2576,7 +2609,7 @@ static int cat_stats_launch(ssa_ukf* h, const double* dpos, const double* trace,
   int nb = (int)((N + 255) / 256);
   nb = nb > kStatBlocks ? kStatBlocks : nb;
   ssa_cat_stats_stage1<<<nb, 256, 0, st>>>(dpos, trace, N, (CatPart*)h->cat_part);
-  ssa_cat_stats_stage2<<<1, 256, 0, st>>>((const CatPart*)h->cat_part, nb, N, index_offset, h->cat_stats);
+  ssa_cat_stats_stage2<<<1, 256, 0, st>>>((const CatPart*)h->cat_part, nb, N, index_offset, out);
   h->launches += 2;
   return SSA_OK;
 }
@@ -2586,13 +2619,14 @@ int ssa_ukf_catalog_stats(ssa_ukf* h, long index_offset, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(h->device));
   if (!h->cat_part) {
-    CK(cudaMalloc(&h->cat_part, sizeof(CatPart) * kStatBlocks + 8 * sizeof(double)));
-    h->cat_stats = (double*)((CatPart*)h->cat_part + kStatBlocks);
+    CK(cudaMalloc(&h->cat_part, sizeof(CatPart) * kStatBlocks + 16 * sizeof(double)));
+    h->cat_stats = (double*)((CatPart*)h->cat_part + kStatBlocks);  // [3][5]: plain steps | pinned parity 0 | pinned parity 1
+    CK(cudaMemsetAsync(h->cat_stats, 0, 16 * sizeof(double), st));
   }
   h->cat_index_offset = index_offset;
   // the reward terms of the MOST RECENT step: its delta_pos / trace live in the handle's arrays or, after a pinned /
   // host-pipelined step, in that call's output block
-  const int rc = cat_stats_launch(h, h->last_dpos ? h->last_dpos : h->dpos, h->last_trace ? h->last_trace : h->trace, index_offset, st);
+  const int rc = cat_stats_launch(h, h->last_dpos ? h->last_dpos : h->dpos, h->last_trace ? h->last_trace : h->trace, index_offset, st, h->cat_stats);
   if (rc) return rc;
   CK(cudaGetLastError());
   return SSA_OK;

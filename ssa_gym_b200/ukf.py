@@ -214,6 +214,25 @@ class BatchedUKF:
             self._parity_out = ctypes.c_int(0)
         return self._io
 
+    def host_stats(self, parity):
+        """Reward terms (SSA_F_CATALOG_STATS layout, 5 doubles) of the pinned steps of `parity`: (numpy view of the
+        pinned host copy - valid after host_join() + sync -, device pointer of the slot).  Needs catalog_stats() once."""
+        hp, dp = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(self.lib.ssa_ukf_host_stats(self.h, int(parity), ctypes.byref(hp), ctypes.byref(dp)), "ssa_ukf_host_stats")
+        host = np.ctypeslib.as_array(ctypes.cast(hp, ctypes.POINTER(ctypes.c_double)), shape=(5,))
+        return host, dp.value
+
+    def host_stats_torch(self, parity):
+        """Zero-copy torch view [5] of the device slot of host_stats(parity) (input of an NCCL gather)."""
+        import torch
+        _, dp = self.host_stats(parity)
+
+        class _CAI:
+            pass
+        o = _CAI()
+        o.__cuda_array_interface__ = {"shape": (5,), "typestr": "<f8", "data": (dp, False), "version": 2}
+        return torch.as_tensor(o, device=torch.device("cuda", self.device))
+
     def step_pinned(self, flags, stream=None):
         """Pipelined step on the pinned blocks of host_io(): fill host_io()[b] of the parity this call will use
         (0, 1, 0, ... from the first call; `next_parity`), call, read host_io()[b] outputs after host_join()+sync.

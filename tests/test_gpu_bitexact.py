@@ -14,7 +14,7 @@ from ssa_gym_b200.ukf import BatchedUKF
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tile", "split", "team"], autouse=False)
+@pytest.fixture(params=["tile", "tile2", "fused", "split", "team"], autouse=False)
 def kernel(request, monkeypatch):
     """Every device implementation of the step: the tile kernels (default: sigma sets in shared memory), the split
     five-kernel pipeline (SSA_UKF_KERNEL=split) and the fused 16-lane team kernel (SSA_UKF_KERNEL=team).  The handle
@@ -268,7 +268,7 @@ def _rotz(a):
     return np.array([[c, s_, 0.0], [-s_, c, 0.0], [0.0, 0.0, 1.0]])
 
 
-@pytest.mark.parametrize("impl", ["tile", "split"])
+@pytest.mark.parametrize("impl", ["tile", "tile2", "fused", "split"])
 @pytest.mark.parametrize("chunk", ["640", "4000"])
 def test_chunked_execution_bitexact(chunk, impl, monkeypatch):
     """Large batches run in L2-sized chunks (SSA_UKF_CHUNK objects per chunk, env-aligned in RL mode).  Forcing
@@ -337,6 +337,43 @@ def test_catalog_stats_reduction_exact():
     tv[123] = tv[60000] = float(tr.max()) * 2
     ukf.catalog_stats(index_offset=0)
     assert ukf.download(F.F_CATALOG_STATS)[4] == 123
+    ukf.close()
+
+
+def test_pinned_step_reward_terms_per_parity():
+    """ssa_ukf_step_pinned with SSA_STEP_CATALOG_STATS: each call leaves its shard reward terms in the device slot and the
+    pinned host mirror of ITS parity (ssa_ukf_host_stats), copied on the download stream — equal to numpy on the same
+    call's downloaded outputs; the slot of the other parity still holds the previous step's terms."""
+    N, steps = 9001, 5
+    cat, x, P0, zn = H.c2_inputs(N, steps)
+    cfg = H.make_cfg(N)
+    ukf = BatchedUKF(n_envs=1, m=N, dt=20.0, Q=np.array(cfg.Q).reshape(6, 6), R=np.array(cfg.R).reshape(3, 3),
+                     obs_lla=[np.radians(H.OBSERVER_DEG[0]), np.radians(H.OBSERVER_DEG[1]), H.OBSERVER_DEG[2]],
+                     obs_limit_rad=np.radians(-90.0))
+    ukf.reset(cat, x, P0)
+    ukf.catalog_stats(index_offset=700)
+    io = ukf.host_io()
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE | F.STEP_CATALOG_STATS
+    prev = {}
+    for s in range(steps):
+        b = ukf.next_parity
+        io[b]["z_noise"][:] = zn[s]
+        io[b]["M"][:] = np.asarray(H.CEL2TER06AXY).reshape(9)
+        assert ukf.step_pinned(flags) == b
+        ukf.host_join()
+        ukf.sync()
+        host, _ = ukf.host_stats(b)
+        dpos = io[b]["delta_pos"]
+        assert host[0] == dpos.max() and host[2] == N
+        assert host[1] == float(((dpos < 1e4).astype(int) + (dpos < 1e7).astype(int)).sum())
+        obs = io[b]["obs"]
+        trace = ((((obs[:, 6] + obs[:, 7]) + obs[:, 8]) + obs[:, 9]) + obs[:, 10]) + obs[:, 11]
+        assert host[3] == trace.max() and host[4] == 700 + int(np.argmax(trace))
+        dev = ukf.host_stats_torch(b).cpu().numpy()
+        assert np.array_equal(dev, host)
+        if (b ^ 1) in prev:
+            assert np.array_equal(ukf.host_stats(b ^ 1)[0], prev[b ^ 1])
+        prev[b] = np.array(host)
     ukf.close()
 
 

@@ -134,7 +134,7 @@ def test_gpu_bitexact_on_stress_inputs():
     zn = np.random.RandomState(4).normal(size=(4, n, 3)) * np.array([H.arcsec2rad, H.arcsec2rad, 1e3])
     flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE | F.STEP_RECORD
     import os
-    for kernel in ("tile", "split", "team"):
+    for kernel in ("tile", "tile2", "fused", "split", "team"):
         os.environ["SSA_UKF_KERNEL"] = kernel
         for dt in (20.0, 6000.0):
             cfg = H.make_cfg(n, dt=dt)
