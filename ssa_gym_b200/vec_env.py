@@ -38,6 +38,7 @@ class VecSSATaskerEnv:
         self.obs_limit = np.radians(config['obs_limit'])
         self.reward_type = config['reward_type']
         self.obs_type = config['obs_type']
+        self.obs_returned = config.get('obs_returned', 'flatten')
         self.update_interval = config['update_interval']
         self.auto_reset = auto_reset
         if config.get('orbits') is not None:
@@ -64,7 +65,11 @@ class VecSSATaskerEnv:
                               obs_type=self.obs_type, reward_type=self.reward_type, n_steps=self.n,
                               resample_after_predict=config.get('resample_after_predict', True), device=device)
         self.action_spaces = [spaces.Discrete(self.m) for _ in range(self.E)]
-        self.observation_space = spaces.Box(low=np.tile(-np.inf, (self.m * 12)), high=np.tile(np.inf, (self.m * 12)), dtype=np.float64)
+        # SS2:164-177: 'flatten' [m*12] (x and diag P per RSO), 'aer' [m*4] (az, el, range of the filter mean and trace P),
+        # anything else the 2-d [m, 12] array
+        oshape = {'flatten': (self.m * 12,), 'aer': (self.m * 4,)}.get(self.obs_returned, (self.m, 12))
+        self.observation_space = spaces.Box(low=np.full(oshape, -np.inf), high=np.full(oshape, np.inf), dtype=np.float64)
+        self._device = device
         self.np_randoms = [None] * self.E
         self.i = np.zeros(self.E, dtype=np.int32)
         self.z_noise = np.empty((self.E, self.n, self.m, 3)) if rng == 'host' else None
@@ -107,6 +112,31 @@ class VecSSATaskerEnv:
         self.rewards_hist[e] = 0.0
         self.prev_spos_argmax[e] = 0  # argmax of the (all equal) sigma_pos[0]
 
+    def _format_obs(self, obs12, idx=None):
+        """The per-env observation in the layout config['obs_returned'] asks for (SS2:355-361).  obs12 = [E', m*12] rows
+        (x [6], diag P [6] per RSO) of the environments `idx` (default: all); 'aer' evaluates az / el / range of every
+        filter mean on the device with the env's own trans_matrix[i] (SS2:834-840) — environments at the same step index
+        share one launch — and replaces NaN / inf by 0.001 as the reference does."""
+        if self.obs_returned == 'flatten':
+            return obs12
+        o = np.asarray(obs12).reshape(-1, self.m, 12)
+        if self.obs_returned != 'aer':
+            return o
+        idx = np.arange(self.E) if idx is None else np.asarray(idx)
+        steps = np.minimum(self.i[idx], len(self.trans_matrix) - 1)
+        out = np.empty((len(o), self.m, 4))
+        for i in np.unique(steps):
+            sel = np.where(steps == i)[0]
+            out[sel, :, :3] = dynamics.hx_aer_erfa(o[sel, :, :6], self.trans_matrix[i], self.obs_lla, self.obs_itrs,
+                                                   device=self._device)
+        d = o[:, :, 6:]
+        out[:, :, 3] = ((((d[:, :, 0] + d[:, :, 1]) + d[:, :, 2]) + d[:, :, 3]) + d[:, :, 4]) + d[:, :, 5]  # np.trace order
+        return np.nan_to_num(out.reshape(len(o), self.m * 4), copy=False, nan=0.001, posinf=0.001, neginf=0.001)
+
+    def _format_reward(self, rewards):
+        # SS2:358-361: every layout but 'flatten' returns nan_to_num(reward, nan = +-inf = 0.5)
+        return rewards if self.obs_returned == 'flatten' else np.nan_to_num(rewards, copy=False, nan=0.5, posinf=0.5, neginf=0.5)
+
     def _dev_views(self):
         if self._views is None:
             tv = self.ukf.torch_view
@@ -119,12 +149,12 @@ class VecSSATaskerEnv:
             self.ukf.rollout_reset()
             self.ukf.sync()
             self.i[:] = 0
-            return self._io["obs"].reshape(self.E, self.m * 12)
+            return self._format_obs(self._io["obs"].reshape(self.E, self.m * 12))
         for e in range(self.E):
             self._draw(e)
         self.ukf.reset(self.x_true0.reshape(self.N, 6), self.x_filter0.reshape(self.N, 6), self.P_0)
         self._epilogue_only()
-        return self.ukf.download(F.F_OBS).reshape(self.E, self.m * 12)
+        return self._format_obs(self.ukf.download(F.F_OBS).reshape(self.E, self.m * 12))
 
     def _epilogue_only(self):
         self.ukf.upload(F.F_TRANS_ENV, self.trans_matrix[self.i])
@@ -185,14 +215,16 @@ class VecSSATaskerEnv:
             self.prev_spos_argmax = stats[:, 2].astype(np.int64)
         infos = [{} for _ in range(self.E)]
         if self.auto_reset and dones.any():
-            for e in np.where(dones)[0]:
-                infos[e]["terminal_observation"] = obs[e].copy()
+            de = np.where(dones)[0]
+            term = self._format_obs(obs[de], de)   # in the layout the caller sees, at the step index the episode ended on
+            for k, e in enumerate(de):
+                infos[e]["terminal_observation"] = np.array(term[k], copy=True)
                 self.reset_at(int(e))
             self._epilogue_only()
             fresh = self.ukf.download(F.F_OBS).reshape(self.E, self.m * 12)
             obs[dones] = fresh[dones]
-        self.obs = obs
-        return obs, rewards, dones, infos
+        self.obs = self._format_obs(obs)
+        return self.obs, self._format_reward(rewards), dones, infos
 
     def _device_step(self, actions):
         """rng='device': the whole step (noise, UKF, reward / done, auto-reset, fresh obs, greedy taskers) is one
@@ -208,8 +240,8 @@ class VecSSATaskerEnv:
         if self.auto_reset:
             self.i[dones] = 0
             self.episodes[dones] += 1
-        self.obs = io["obs"].reshape(self.E, self.m * 12)
-        return self.obs, rewards, dones, self._infos  # E empty dicts, allocated once (4096 dict constructions cost 100 us)
+        self.obs = self._format_obs(io["obs"].reshape(self.E, self.m * 12))
+        return self.obs, self._format_reward(rewards), dones, self._infos  # E empty dicts, allocated once (4096 dict constructions cost 100 us)
 
     # -- device-resident consumer (a policy on the same GPU): no host copies, nothing synchronises -------------------
     def device_views(self):

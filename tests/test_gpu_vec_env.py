@@ -19,6 +19,9 @@ pytestmark = pytest.mark.gpu
     ({"steps": 40, "reward_type": "jones"}, F.TASKER_VISIBLE_GREEDY, agents.agent_visible_greedy),
     ({"steps": 30, "reward_type": "trinary", "obs_limit": 15}, F.TASKER_POS_ERROR_GREEDY, agents.agent_pos_error_greedy),
     ({"steps": 25, "reward_type": "shaped", "rso_count": 6}, F.TASKER_NAIVE_GREEDY, agents.agent_naive_greedy),
+    # the other two observation layouts of SS2:164-177 / 355-361
+    ({"steps": 20, "reward_type": "jones", "rso_count": 7, "obs_returned": "aer"}, F.TASKER_VISIBLE_GREEDY, agents.agent_visible_greedy),
+    ({"steps": 20, "reward_type": "trinary", "rso_count": 5, "obs_returned": "2d"}, F.TASKER_NAIVE_GREEDY, agents.agent_naive_greedy),
 ])
 def test_vec_env_equals_independent_envs(over, tasker, agent):
     E, total_steps = 24, 55
