@@ -109,6 +109,7 @@ struct KParams {
   double dt, lam, obs_limit;
   double Wm[13], Wc[13];
   const double* qr;  // device constants: packed Q (21, upper triangle) then R (9, row-major)
+  const uint8_t* env_gate;  // episodic refresh after an auto-reset: [E] mask, only the objects of these environments are touched
   ssa_obs ob;
 };
 
@@ -711,6 +712,7 @@ __global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx
   if (k == 13) {  // truth measurement of every object: visibility (SS2:418-425) and z_true
     if (lidx >= p.Nc) return;
     const long idx = p.obj0 + lidx;
+    if (p.env_gate && !p.env_gate[idx / p.m]) return;
     const long loc = lidx;
     double xt[3], zt[3];
 #pragma unroll
@@ -973,6 +975,7 @@ __global__ void __launch_bounds__(kSplitThreads, SSA_LB_UPD) k_update(const KPar
   pdl_prologue();
   const long loc = (long)blockIdx.x * blockDim.x + threadIdx.x;  // index inside the chunk
   if (loc >= p.Nc) return;
+  if (p.env_gate && !p.env_gate[(p.obj0 + loc) / p.m]) return;
   update_body<false>(p, loc, p.obj0 + loc, nullptr, 0);
 }
 
@@ -1040,9 +1043,11 @@ __device__ __forceinline__ ArgMax am_warp(ArgMax a) {
 
 // det P of every object (agent_shannon), one thread per object: a chain of 6 divisions that would hold the per-environment
 // reduction below at 4 CTAs per SM if it ran there on m of 128 threads (measured: 50 us per launch at E = 4096)
-__global__ void __launch_bounds__(128) ssa_det_kernel(const double* __restrict__ P, long ld, int N, double* __restrict__ det_cur) {
+__global__ void __launch_bounds__(128) ssa_det_kernel(const double* __restrict__ P, long ld, int N, double* __restrict__ det_cur,
+                                                      const uint8_t* __restrict__ env_gate, int m) {
   const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < N) det_cur[n] = ssa_det6_sym(P + n, ld);
+  if (n >= N || (env_gate && !env_gate[n / m])) return;
+  det_cur[n] = ssa_det6_sym(P + n, ld);
 }
 
 // WARP = false: one CTA per environment, threads stride over the m objects of the env (catalog-sized environments).
@@ -1053,6 +1058,8 @@ template <bool WARP>
 __global__ void __launch_bounds__(128, 12) ssa_env_reduce_kernel(const EnvParams p) {
   const int e = WARP ? (int)(blockIdx.x * 4 + (threadIdx.x >> 5)) : (int)blockIdx.x;
   if (WARP && e >= p.E) return;
+  // the refresh after an auto-reset concerns the re-drawn environments only: the others keep this step's results
+  if (p.greedy_only && p.reset_mask && !p.reset_mask[e]) return;
   const int j0 = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x, jstep = WARP ? 32 : (int)blockDim.x;
   const long base = (long)e * p.m;
   ArgMax a_trace{0.0, -1}, a_vtrace{0.0, -1}, a_vdpos{0.0, -1}, a_vdvel{0.0, -1}, a_spos{0.0, -1}, a_dpos{0.0, -1};
@@ -2017,6 +2024,7 @@ int ssa_ukf_download(ssa_ukf* h, int field, void* host, size_t bytes, void* stre
 
 struct StepOverride {  // episodic mode: redirect the step's inputs / outputs
   double* obs; const int32_t* actions; const double* table; const int32_t* step_idx; int bias, rows;
+  const uint8_t* env_gate;  // refresh of the re-drawn environments only (null: every environment)
 };
 
 static int cat_stats_launch(ssa_ukf* h, const double* dpos, const double* trace, long index_offset, cudaStream_t st, double* out);
@@ -2064,6 +2072,7 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
   if (ov) {
     p.obs = ov->obs; p.actions = ov->actions;
     p.Menv = ov->table; p.Mstep = ov->step_idx; p.Mbias = ov->bias; p.Mrows = ov->rows;
+    p.env_gate = ov->env_gate;
   }
   if (M) memcpy(p.ob.M, M, sizeof(p.ob.M));
   memcpy(p.ob.obs_itrs, c.obs_itrs, sizeof(p.ob.obs_itrs));
@@ -2402,7 +2411,7 @@ static void rollout_env_params(ssa_ukf* h, EnvParams* p, int increment, int gree
 
 static void launch_env_reduce(ssa_ukf* h, const EnvParams& ep, cudaStream_t st) {
   const int N = h->cfg.n_objects;
-  ssa_det_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(h->P, h->ld, N, h->det_cur);
+  ssa_det_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(h->P, h->ld, N, h->det_cur, ep.greedy_only ? ep.reset_mask : nullptr, ep.m);
   if (ep.m <= 64) ssa_env_reduce_kernel<true><<<(unsigned)((ep.E + 3) / 4), 128, 0, st>>>(ep);
   else ssa_env_reduce_kernel<false><<<(unsigned)ep.E, 128, 0, st>>>(ep);
   h->launches += 2;
@@ -2410,12 +2419,13 @@ static void launch_env_reduce(ssa_ukf* h, const EnvParams& ep, cudaStream_t st) 
 
 // obs / errors / visibility of the current states + greedy taskers (after a reset)
 static int rollout_refresh(ssa_ukf* h, cudaStream_t st, int only_done) {
-  StepOverride ov{h->ro.dout, h->ro.act_eff, h->ro.table, h->step_idx, 0, h->ro.n_table};
-  int rc = step_impl(h, nullptr, SSA_STEP_EPILOGUE, st, nullptr, -1, &ov);
-  if (rc) return rc;
   EnvParams ep;
   rollout_env_params(h, &ep, 0, 1);
   if (only_done) ep.reset_mask = ep.done;  // the environments k_env_reset has just re-drawn
+  // (observations, visibility, determinants and greedy actions of the other environments are this step's already)
+  StepOverride ov{h->ro.dout, h->ro.act_eff, h->ro.table, h->step_idx, 0, h->ro.n_table, only_done ? ep.done : nullptr};
+  int rc = step_impl(h, nullptr, SSA_STEP_EPILOGUE, st, nullptr, -1, &ov);
+  if (rc) return rc;
   launch_env_reduce(h, ep, st);
   return SSA_OK;
 }
@@ -2497,7 +2507,7 @@ static int rollout_chain(ssa_ukf* h, cudaStream_t st, int auto_reset) {
   const long N = h->cfg.n_objects;
   k_env_begin<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(rp);
   h->launches++;
-  StepOverride ov{h->ro.dout, h->ro.act_eff, h->ro.table, h->step_idx, 1, h->ro.n_table};
+  StepOverride ov{h->ro.dout, h->ro.act_eff, h->ro.table, h->step_idx, 1, h->ro.n_table, nullptr};
   int rc = step_impl(h, nullptr, SSA_STEP_TRUTH | SSA_STEP_PREDICT | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE, st, nullptr, -1, &ov);
   if (rc) return rc;
   EnvParams ep;
