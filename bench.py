@@ -878,7 +878,7 @@ def run_catalog(a, rank, local_rank, world):
                                                 f"alone need {ms_per_step:.3f} ms"},
                     "host_issue_ms_per_step": host_issue.get("reward", host_issue.get("full")),
                     "limiter": (f"the kernels need {ms_per_step:.3f} ms per step, the host needs {host_issue.get('reward', host_issue.get('full')):.3f} ms to "
-                                f"issue one (Python + 1 H2D + 1 graph launch + NCCL enqueue + 1 D2H on rank 0's process); H2D of the measurements "
+                                f"issue one (Python + 1 H2D + 1 graph launch" + (" + NCCL all_gather and D2H enqueued on a side stream" if world > 1 else "") + "; the reward read-back is off the compute stream); H2D of the measurements "
                                 f"({h2d * world / 1e6:.1f} MB per step, {h2d * world / (e2e_ms * 1e-3) / 1e9:.1f} GB/s aggregate) overlaps the kernels"),
                     "l2": "not flushed: the filter state is device-resident between steps by design; every step's inputs arrive "
                           "from pinned host memory and its result leaves to pinned host memory inside the timed region"},
