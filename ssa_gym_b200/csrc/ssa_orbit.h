@@ -515,7 +515,15 @@ SSA_HD int ssa_fx(const double* x, double tof, double* out) {
     // [0.99, 1.01], degenerate and non-finite states keep the literal restatement with its exact failure semantics)
     const bool hyper = (rn > 0.0) && (hn > 0.0) && (hxy2 > 0.0 || h[2] > 0.0) && (ecc > SSA_C(HYP101)) && (ecc < 1e12) &&
                        (planar || ci < 1.0);
-    return hyper ? ssa_fx_hyperbolic(x, tof, out) : ssa_fx_general(x, tof, out);
+    // (through copies: handing x / out themselves to the out-of-line functions would make the caller's arrays escape and
+    // pin them to local memory on the fast path too — measured in k_predict_tile: 25 local loads / stores per propagation)
+    double xs[6], fo[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) xs[j] = x[j];
+    const int e = hyper ? ssa_fx_hyperbolic(xs, tof, fo) : ssa_fx_general(xs, tof, fo);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) out[j] = fo[j];
+    return e;
   }
 
   const double p = ssa_mul(hh, kinv);

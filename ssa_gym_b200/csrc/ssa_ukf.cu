@@ -1055,7 +1055,7 @@ __global__ void __launch_bounds__(128) ssa_det_kernel(const double* __restrict__
 // shared memory and no barrier — with one CTA per 10-object environment 118 of 128 threads only took part in the
 // shuffles (measured at E = 4096: 30 us per launch, two launches per episodic step).
 template <bool WARP>
-__global__ void __launch_bounds__(128, 12) ssa_env_reduce_kernel(const EnvParams p) {
+__global__ void __launch_bounds__(128, 6) ssa_env_reduce_kernel(const EnvParams p) {
   const int e = WARP ? (int)(blockIdx.x * 4 + (threadIdx.x >> 5)) : (int)blockIdx.x;
   if (WARP && e >= p.E) return;
   // the refresh after an auto-reset concerns the re-drawn environments only: the others keep this step's results
