@@ -9,6 +9,10 @@
 //   k_update_tile    (x', P', U', xt', z_noise) -> 14 T measurements hx into shared ZS/UVW[39][T] -> mean_z, residuals,
 //                    S, Pxz (one thread per row / element, k = 0..12 in order), 3x3 inverse, gain, state and
 //                    covariance update, observation / error epilogue
+//   k_step_tile      (SSA_UKF_KERNEL=fused) the whole catalog step in one launch: factor -> propagate -> transform ->
+//                    factor -> the update body of k_update_tile; tile_robust_chol is the factorisation spread over the
+//                    tile's threads, also used by the FACTOR / REFACTOR variants of the two kernels above (tile2).
+//                    Bit-identical and measured slower than the four-kernel chain.
 // They replace k_fx + k_ut and k_hx + k_update(_staged): the propagated sigma set (624 B / object), the measurement
 // sigma set and its Cartesian image (648 B / object) never travel through L2 / HBM, and the per-object linear
 // algebra that used to be one ~2 700-instruction chain per thread is spread over the tile's threads.

@@ -6,7 +6,10 @@
 //    consecutive objects; the propagated sigma set and the measurement sigma set live in its shared memory only, the
 //    state tile arrives by one 2-D TMA load (cp.async.bulk.tensor + mbarrier), propagation / measurement tasks are mapped
 //    (object, sigma index) so that a warp holds the sigma points of at most four objects, the per-object linear algebra
-//    is spread over the tile's threads with every sum over the 13 sigma points in a fixed sequential order;
+//    is spread over the tile's threads with every sum over the 13 sigma points in a fixed sequential order.  Two measured
+//    alternates of the same arithmetic (both slower): SSA_UKF_KERNEL=tile2 folds the two factorisations
+//    into the tile kernels (two launches, the factor never in HBM), SSA_UKF_KERNEL=fused runs the whole catalog step as
+//    ONE launch (k_step_tile: 0.73 KB of DRAM traffic per object-step);
 //  * the SPLIT PIPELINE (SSA_UKF_KERNEL=split, and always for the RL-mode update of one tasked object per environment and
 //    for the book-version filter): k_factor, k_fx, k_ut, k_hx, k_update(_staged) — one thread per object for the small
 //    linear algebra, one thread per (sigma point, object) for fx / hx, intermediates in global scratch;
