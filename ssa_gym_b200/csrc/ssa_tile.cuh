@@ -39,8 +39,8 @@
 #define SSA_LB_PT 4  // resident CTAs per SM the predict tile kernel is compiled for (224 threads: 4 -> 72 registers)
 #endif
 #ifndef SSA_LB_UTILE
-#define SSA_LB_UTILE 4  // (5 CTAs at 56 registers spill in the measurement phase: 0.654 vs 0.639 ms at 1 M objects)
-#endif
+#define SSA_LB_UTILE 5  // 56 registers, 28 bytes of spills: 0.530 vs 0.531 ms at 1 M objects, 73.5 vs 76.2 us at 125 000, 21.0 vs 24.6 us at
+#endif                  // 20 000 (625 tiles: one wave of 740 CTA slots instead of 592 + 33).  k_step_tile keeps 4 (its propagation phase).
 constexpr int kTileThreads = 14 * SSA_TILE / SSA_TILE_ROUNDS;
 static_assert((14 * SSA_TILE) % SSA_TILE_ROUNDS == 0 && kTileThreads % SSA_TILE == 0 && kTileThreads % 32 == 0, "tile shape");
 
@@ -99,8 +99,11 @@ __device__ __forceinline__ void tile_cov_rows(const double (*F)[T + 1], int o, c
 // FACTOR = false: the factor U comes from k_factor (tm_x = box of xt | x, tm_u = box of U).  FACTOR = true: the kernel
 // stages xt | x | P (tm_x = box of all 33 state rows) and factors (lambda + n) P across the tile's threads first —
 // k_factor folded in, the factor never travels through HBM.
-template <int T, int NT, bool FACTOR>
-__global__ void __launch_bounds__(NT, SSA_LB_PT) k_predict_tile(const KParams p, const __grid_constant__ CUtensorMap tm_x,
+// MINB = resident CTAs per SM the kernel is compiled for: 4 (72 registers) everywhere except for catalogs whose tiles fill
+// one wave only at 5 CTAs per SM (56 registers, spills in the propagation: 0.689 vs 0.677 ms at 1 M objects, but 27.6 vs
+// 29.3 us at 20 000 objects = 625 tiles).
+template <int T, int NT, bool FACTOR, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_predict_tile(const KParams p, const __grid_constant__ CUtensorMap tm_x,
                                                                 const __grid_constant__ CUtensorMap tm_u) {
   constexpr int NR = NT / T;  // rows of the algebra mapping
   static_assert(NR >= 7, "the algebra phases use up to 7 thread rows");
@@ -710,7 +713,7 @@ __device__ __forceinline__ void tile_robust_chol(const double (*A)[T], double (*
 // the predicted mean / covariance and the propagated truth never travel through HBM (1.89 KB -> ~0.7 KB per object-step).
 // The propagated sigma tile F[78][T + 1] lives in the storage of ZS | UVW (dead until the measurement phase).
 template <int T, int NT>
-__global__ void __launch_bounds__(NT, SSA_LB_UTILE) k_step_tile(const KParams p, const __grid_constant__ CUtensorMap tm_s,
+__global__ void __launch_bounds__(NT, 4) k_step_tile(const KParams p, const __grid_constant__ CUtensorMap tm_s,
                                                                 const __grid_constant__ CUtensorMap tm_u) {
   constexpr int NR = NT / T;
   static_assert(NR >= 7 && T == 32, "the algebra phases use 7 thread rows; the tile is staged by one TMA load");

@@ -1645,6 +1645,7 @@ struct ssa_ukf {
   int use_team;   // SSA_UKF_KERNEL=team selects the fused 16-lane team kernel instead of the split pipeline
   int use_fused;  // one launch per full catalog step (k_step_tile) instead of the four tile kernels
   int fold_factor;  // tile2: the two factorisations inside the tile kernels instead of k_factor / k_refactor
+  int sm_count;
   // double-buffered host pipeline (ssa_ukf_step_host)
   struct {
     int init, parity;
@@ -1808,6 +1809,8 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
     h->use_tile = (kv && strcmp(kv, "split") == 0) ? 0 : 1;
     h->use_fused = (kv && strcmp(kv, "fused") == 0) ? 1 : 0;
     h->fold_factor = (kv && strcmp(kv, "tile2") == 0) ? 1 : 0;
+    h->sm_count = 148;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
     cudaFuncSetAttribute(k_update_tile<SSA_TILE, kTileThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateTile<SSA_TILE>));
     cudaFuncSetAttribute(k_update_tile<SSA_TILE, kTileThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateTile<SSA_TILE>));
     cudaFuncSetAttribute(k_step_tile<SSA_TILE, kTileThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UpdateTile<SSA_TILE>));
@@ -2119,8 +2122,11 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
     if ((predict || update) && !fold) { launch_chain(pdl, k_factor, gobj2, kObjThreads, 0, st, p); h->launches++; }
     if (evc) CK(cudaEventRecord(evc[1], st));
     if (predict || truth) {
-      if (fold) launch_chain(pdl, k_predict_tile<SSA_TILE, kTileThreads, true>, gtile, kTileThreads, 0, st, p, h->tm_s, h->tm_u);
-      else if (tile) launch_chain(pdl, k_predict_tile<SSA_TILE, kTileThreads, false>, gtile, kTileThreads, 0, st, p, h->tm_x, h->tm_u);
+      // (one wave of tiles only at 5 CTAs per SM: the 56-register build of the kernel)
+      const bool one_wave5 = gtile > (unsigned)h->sm_count * SSA_LB_PT && gtile <= (unsigned)h->sm_count * 5;
+      if (fold) launch_chain(pdl, k_predict_tile<SSA_TILE, kTileThreads, true, SSA_LB_PT>, gtile, kTileThreads, 0, st, p, h->tm_s, h->tm_u);
+      else if (tile && one_wave5) launch_chain(pdl, k_predict_tile<SSA_TILE, kTileThreads, false, 5>, gtile, kTileThreads, 0, st, p, h->tm_x, h->tm_u);
+      else if (tile) launch_chain(pdl, k_predict_tile<SSA_TILE, kTileThreads, false, SSA_LB_PT>, gtile, kTileThreads, 0, st, p, h->tm_x, h->tm_u);
       else launch_chain(pdl, k_fx, dim3(gfx, 14), kFxThreads, 0, st, p);
       h->launches++;
     }
