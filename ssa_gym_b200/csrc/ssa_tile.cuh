@@ -42,7 +42,7 @@
 #define SSA_LB_UTILE 5  // 56 registers, 28 bytes of spills: 0.530 vs 0.531 ms at 1 M objects, 73.5 vs 76.2 us at 125 000, 21.0 vs 24.6 us at
 #endif                  // 20 000 (625 tiles: one wave of 740 CTA slots instead of 592 + 33).  k_step_tile keeps 4 (its propagation phase).
 constexpr int kTileThreads = 14 * SSA_TILE / SSA_TILE_ROUNDS;
-static_assert((14 * SSA_TILE) % SSA_TILE_ROUNDS == 0 && kTileThreads % SSA_TILE == 0 && kTileThreads % 32 == 0, "tile shape");
+static_assert((14 * SSA_TILE) % SSA_TILE_ROUNDS == 0 && kTileThreads % SSA_TILE == 0 && kTileThreads % 32 == 0 && kTileThreads % 14 == 0, "tile shape");
 
 // FACTOR: the kernel factors (lambda + n) P itself (k_factor folded in): rows xt 0..5 | x 6..11 | P 12..32 | U 33..53
 template <int T, bool FACTOR>
@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(NT, MINB) k_predict_tile(const KParams p, cons
 
   // ---- 14 T propagations: task = (object, sigma index), 13 = the TRUE state; ONE call site of fx ----
 #pragma unroll 1
-  for (int task = tid; task < 14 * T; task += NT) {
-    const int o = task / 14, k = task - 14 * o;
+  for (int o = tid / 14; o < T; o += NT / 14) {  // NT is a multiple of 14: a thread keeps its sigma index in every round
+    const int k = tid % 14;
     const bool is_truth = (k == 13);
     const bool run = (loc0 + o < p.Nc) && (is_truth ? truth : (sm.live[o] != 0));
     if (run) {
@@ -321,8 +321,8 @@ __device__ __forceinline__ void tile_update_body(const KParams& p, UpdateTile<T>
 
   // ---- 14 T measurements: task = (object, sigma index); 13 = the TRUE state (visibility, z_true) ----
 #pragma unroll 1
-  for (int task = tid; task < 14 * T; task += NT) {
-    const int o = task / 14, k = task - 14 * o;
+  for (int o = tid / 14; o < T; o += NT / 14) {  // NT is a multiple of 14: a thread keeps its sigma index in every round
+    const int k = tid % 14;
     const long loc = loc0 + o;
     const bool is_truth = (k == 13);
     const bool live = !(sm.st[o] & SSA_ST_FAILED) && !sm.code[o];
@@ -768,8 +768,8 @@ __global__ void __launch_bounds__(NT, 4) k_step_tile(const KParams p, const __gr
 
   // ---- 14 T propagations: task = (object, sigma index), 13 = the TRUE state; ONE call site of fx ----
 #pragma unroll 1
-  for (int task = tid; task < 14 * T; task += NT) {
-    const int o = task / 14, k = task - 14 * o;
+  for (int o = tid / 14; o < T; o += NT / 14) {  // NT is a multiple of 14: a thread keeps its sigma index in every round
+    const int k = tid % 14;
     const bool is_truth = (k == 13);
     const bool run = (loc0 + o < p.Nc) && (is_truth ? truth : (sm.live[o] != 0));
     if (run) {
