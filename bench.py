@@ -823,13 +823,27 @@ def run_catalog(a, rank, local_rank, world):
         dom_flop_impl = (FLOP_PER_UNIT if team else (14 * FLOP_FX + (0.9e3 if tile else 0.0))) * n_obj
         dom_tf = dom_flop_ref / (dom_ms * 1e-3) / 1e12
         # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at this shard size
-        traffic = traffic_step = None
+        traffic = traffic_step = hw = None
         try:
             cap = json.load(open(os.path.join(ROOT, "profiles", "r03_ncu_kernels.json")))
             ent = cap.get(str(n_obj))
             if ent and tile and not team:
                 traffic = ent["k_predict_tile"]["dram_bytes_per_launch"]
                 traffic_step = sum(v["dram_bytes_per_launch"] for v in ent.values() if isinstance(v, dict) and "dram_bytes_per_launch" in v)
+                # FP64 arithmetic counted by the hardware in that capture (DADD + DMUL + 2 DFMA thread instructions per launch),
+                # over THIS run's CUDA-event durations
+                kf = ent["k_predict_tile"].get("fp64_flop_per_launch_hw")
+                sf = sum(v.get("fp64_flop_per_launch_hw", 0.0) for v in ent.values() if isinstance(v, dict))
+                if kf:
+                    hw = {"flop_per_launch": kf, "achieved": kf / (dom_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                          "frac": kf / (dom_ms * 1e-3) / 1e12 / peak_tf,
+                          "fp64_pipe_pct_ncu": ent["k_predict_tile"].get("fp64_pipe_pct"),
+                          "whole_step": {"flop_per_object": sf / n_obj, "achieved": sf / (kern_ms * 1e-3) / 1e12,
+                                         "frac": sf / (kern_ms * 1e-3) / 1e12 / peak_tf},
+                          "what": "sm__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on of the committed ncu capture "
+                                  "(profiles/r03_ncu_kernels.json): flops the threads actually executed, divisions / square roots / "
+                                  "transcendentals expanded into their FMA sequences; the FP64 pipe is busier than this fraction "
+                                  "because DADD / DMUL / DSETP occupy it like an FMA"}
         except Exception:
             pass
         step_tf = FLOP_PER_UNIT_REF * n_obj / (kern_ms * 1e-3) / 1e12
@@ -844,6 +858,7 @@ def run_catalog(a, rank, local_rank, world):
                          "algorithmic_flop_per_launch": dom_flop_ref, "algorithmic_bytes_per_launch": BYTES_PREDICT_TILE * n_obj if tile else None,
                          "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / float(np.sum(kms)),
                          "frac_as_implemented": dom_flop_impl / (dom_ms * 1e-3) / 1e12 / peak_tf,
+                         "hw_counted": hw,
                          "step_kernels_ms": ({"k_factor": float(kms[0]), "k_predict_tile": float(kms[1]), "k_refactor": float(kms[2]),
                                               "k_update_tile": float(kms[4])} if tile and not team else
                                              {"factor": float(kms[0]), "fx": float(kms[1]), "ut": float(kms[2]), "hx": float(kms[3]),

@@ -24,6 +24,12 @@ KEYS = {
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard",
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio": "stall_math_pipe_throttle",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio": "stall_not_selected",
+    # hardware-counted FP64 arithmetic: thread instructions per elapsed cycle, summed over the sub-partitions
+    "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed": "dadd_per_cycle",
+    "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed": "dmul_per_cycle",
+    "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed": "dfma_per_cycle",
+    "smsp__cycles_elapsed.avg": "sm_cycles",
+    "smsp__cycles_elapsed.avg.per_second": "sm_ghz",
 }
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e3, "us": 1.0, "ns": 1e-3, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3}
 
@@ -49,6 +55,9 @@ def summarise(path):
             d[k] = d[k] / n
         d["launches_averaged"] = n
         d["dram_bytes_per_launch"] = d.get("dram_read", 0.0) + d.get("dram_write", 0.0)
+        if "dfma_per_cycle" in d and "sm_cycles" in d:  # DADD + DMUL + 2 DFMA executed by the threads of one launch
+            d["fp64_flop_per_launch_hw"] = (d["dadd_per_cycle"] + d["dmul_per_cycle"] + 2.0 * d["dfma_per_cycle"]) * d["sm_cycles"]
+            d["fp64_tflops_hw"] = d["fp64_flop_per_launch_hw"] / (d["duration_us"] * 1e-6) / 1e12
     return out
 
 
