@@ -17,7 +17,7 @@ def main(path, top=40):
     for r in data:
         if len(r) <= iE or not r[iE].isdigit():
             continue
-        n, s = int(r[iE]), int(r[iSamp] or 0)
+        n, s = int(r[iE]), int(r[iSamp]) if r[iSamp].isdigit() else 0
         m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[iS].strip())
         op = (m.group(2) if m else r[iS].strip()).split(".")[0]
         byop[op] += n
