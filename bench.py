@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--collector", default="greedy", choices=["greedy", "mlp"], help="c3: 'mlp' = stub PPO rollout collector on the device (1 GPU)")
     ap.add_argument("--gather", action="store_true", help="c3, N>1: also all_gather rewards and observations over NCCL every step (a learner on one device)")
     ap.add_argument("--rng", default="device", choices=["device", "host"], help="c3: episodic RNG mode of VecSSATaskerEnv")
+    ap.add_argument("--obs-dtype", default="float64", choices=["float64", "float32"],
+                    help="c3 (device rng): dtype of the observations handed to the host (float32: SSA_ROLLOUT_OBS_F32, half the D2H bytes)")
     ap.add_argument("--objects", type=int, default=0, help="override the catalog size (c4: whole job, c2: per rank)")
     ap.add_argument("--no-extra", action="store_true", help="skip the short C2 / C3 measurements reported under `extra`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -249,6 +251,9 @@ def c3_measure(a, rank, local_rank, world, steps, warmup, gather):
     cfg["orbits"] = synthetic_catalog(20000, 0)
     cfg["trans_matrix"] = gcrs2irts_matrix_approx(time_table(cfg["t_0"], cfg["time_step"], cfg["steps"]))
     m = cfg["rso_count"]
+    obs_dtype = getattr(a, "obs_dtype", "float64")
+    obs_bytes = 4 if obs_dtype == "float32" else 8
+    cfg["obs_dtype"] = obs_dtype
     t0 = time.perf_counter()
     env = VecSSATaskerEnv(cfg, E, seeds=[rank * E + e for e in range(E)], device=local_rank, rng=a.rng)
     t_construct = time.perf_counter() - t0
@@ -306,12 +311,12 @@ def c3_measure(a, rank, local_rank, world, steps, warmup, gather):
         line = {"metric": "env-steps per second (vectorised ssa_tasker_simple_2, RL mode)", "value": val, "unit": "env-steps/s",
                 "n_gpus": nw, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms / steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"C3: {E} parallel envs x {m} RSOs per GPU, vector_step + device greedy tasker, obs to host",
-                           "envs_per_gpu": E, "rso_count": m, "episode_steps": cfg["steps"], "rng": a.rng, "reward_type": cfg["reward_type"],
-                           "l2": f"inputs/outputs larger than nothing to flush: every step moves {E * m * 12 * 8} B of fresh obs over PCIe"},
+                "config": {"workload": f"C3: {E} parallel envs x {m} RSOs per GPU, vector_step + device greedy tasker, {obs_dtype} obs to host",
+                           "obs_dtype": obs_dtype, "envs_per_gpu": E, "rso_count": m, "episode_steps": cfg["steps"], "rng": a.rng, "reward_type": cfg["reward_type"],
+                           "l2": f"inputs/outputs larger than nothing to flush: every step moves {E * m * 12 * obs_bytes} B of fresh obs over PCIe"},
                 "object_predicts_per_s": val * m,
                 "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * E,
-                        "d2h_bytes_per_step": E * m * 12 * 8 + E * 8 + E * 16 + E, "ms_per_step": ms / steps,
+                        "d2h_bytes_per_step": E * m * 12 * obs_bytes + E * 8 + E * 16 + E, "ms_per_step": ms / steps,
                         "api": "VecSSATaskerEnv.vector_step (ssa_ukf_rollout_step)" if a.rng == "device" else "VecSSATaskerEnv.vector_step"},
                 "roofline": {"bound": "fp64", "kernel": "whole env step", "achieved": val / nw * flop_env_step / 1e12, "peak": peak_tf,
                              "unit": "TFLOP/s", "frac": val / nw * flop_env_step / 1e12 / peak_tf, "traffic": None,
@@ -802,6 +807,12 @@ def run_catalog(a, rank, local_rank, world):
             extra_c3 = {k: l3[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "object_predicts_per_s")}
             extra_c3["workload"] = l3["config"]["workload"]
             extra_c3["e2e_bytes_per_step"] = {"h2d": l3["e2e"]["h2d_bytes_per_step"], "d2h": l3["e2e"]["d2h_bytes_per_step"]}
+            if a3.rng == "device":  # the same loop with float32 observations (what an RLlib preprocessor makes of them anyway)
+                a32 = copy.copy(a3)
+                a32.obs_dtype = "float32"
+                l32 = c3_measure(a32, 0, local_rank, 1, 30, 5, None)
+                extra_c3["obs_float32"] = {"value": l32["value"], "unit": l32["unit"], "ms_per_step": l32["ms_per_step"],
+                                           "d2h_bytes_per_step": l32["e2e"]["d2h_bytes_per_step"]}
             extra_c3["ppo_collector_on_device"] = c3_collector_measure(a3, local_rank, 128, 10)
         except Exception as ex:  # the headline must not be lost to a failure of an extra
             extra_c3 = {"error": repr(ex)}

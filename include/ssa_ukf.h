@@ -220,7 +220,14 @@ int ssa_ukf_rollout_reset(ssa_ukf* h, void* stream);
  * the actions are read from the device buffer SSA_F_ROLLOUT_ACTIONS and obs / reward / done / greedy stay in the device
  * block (SSA_F_ROLLOUT_*), for a policy that lives on the same GPU (everything stream-ordered, nothing synchronises). */
 #define SSA_ROLLOUT_DEVICE_IO 2
+/* bit 2 (SSA_ROLLOUT_OBS_F32): the observations leave the device as float32 (rounded to nearest, numpy's
+ * astype(float32)): the last kernel of the step's graph writes obs [N][12] as floats and the D2H copy moves those
+ * 48 N bytes (+ the reward / greedy / done tail) instead of 96 N — for a learner that casts its observations to float32
+ * anyway (RLlib's preprocessors do, rl_agents/RLLib_PPO_training.py).  The float64 rows stay valid on the device.    */
+#define SSA_ROLLOUT_OBS_F32 4
 int ssa_ukf_rollout_step(ssa_ukf* h, int auto_reset, void* stream);
+/* the float32 observation blocks of SSA_ROLLOUT_OBS_F32: pinned host mirror and device block, [N][12] floats          */
+int ssa_ukf_rollout_obs_f32(ssa_ukf* h, float** host, float** device);
 /* make `stream` wait for every outstanding internal copy of ssa_ukf_step_host / ssa_ukf_step_pinned */
 int ssa_ukf_host_join(ssa_ukf* h, void* stream);
 /* Convenience wrappers with the reference's call structure */

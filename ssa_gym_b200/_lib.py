@@ -29,6 +29,7 @@ N_TASKERS = 6
  F_GREEDY, F_SCORES, F_UPDATED, F_TRANS_ENV, F_STEP_INDEX, F_ENV_STATS, F_DIAG, F_INNOV_FLAGS, F_CATALOG_STATS,
  F_ROLLOUT_OBS, F_ROLLOUT_REWARD, F_ROLLOUT_ACTIONS, F_ROLLOUT_DONE, F_ROLLOUT_GREEDY) = range(34)
 ROLLOUT_DEVICE_IO = 2
+ROLLOUT_OBS_F32 = 4
 
 
 class SsaUkfCfg(ctypes.Structure):
@@ -69,6 +70,7 @@ PROTOTYPES = {
     "ssa_ukf_rollout_io": (_I, [c_void_p] + [c_void_p] * 5),
     "ssa_ukf_rollout_reset": (_I, [c_void_p, c_void_p]),
     "ssa_ukf_rollout_step": (_I, [c_void_p, _I, c_void_p]),
+    "ssa_ukf_rollout_obs_f32": (_I, [c_void_p, c_void_p, c_void_p]),
     "ssa_ukf_predict": (_I, [c_void_p, c_void_p]),
     "ssa_ukf_update": (_I, [c_void_p, c_void_p, _I, c_void_p]),
     "ssa_ukf_env_reduce": (_I, [c_void_p, c_void_p, _I, c_void_p]),

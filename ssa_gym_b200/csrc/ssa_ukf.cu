@@ -1689,8 +1689,9 @@ struct ssa_ukf {
     double* hout;        // pinned host mirror
     int32_t* hin;        // pinned host actions [E]
     size_t out_bytes;
-    cudaGraphExec_t gexec[2];  // [auto_reset]
-    int gkernels[2];
+    float *dobs32, *hobs32;    // SSA_ROLLOUT_OBS_F32: obs [N][12] as floats (device block, pinned host mirror)
+    cudaGraphExec_t gexec[4];  // [auto_reset + 2 * obs_f32]
+    int gkernels[4];
   } ro;
   int32_t *status, *infl, *actions, *greedy;
   uint8_t *visible, *updated, *innov_flags, *done;
@@ -1852,9 +1853,9 @@ int ssa_ukf_destroy(ssa_ukf* h) {
   }
   for (int i = 0; i < h->sg.n; ++i) { cudaGraphExecDestroy(h->sg.gexec[i]); cudaGraphDestroy(h->sg.graph[i]); }
   if (h->ro.init) {
-    cudaFree(h->ro.dbuf); cudaFree(h->ro.ibuf); cudaFree(h->ro.dout);
-    cudaFreeHost(h->ro.hout); cudaFreeHost(h->ro.hin);
-    for (int i = 0; i < 2; ++i) if (h->ro.gexec[i]) cudaGraphExecDestroy(h->ro.gexec[i]);
+    cudaFree(h->ro.dbuf); cudaFree(h->ro.ibuf); cudaFree(h->ro.dout); cudaFree(h->ro.dobs32);
+    cudaFreeHost(h->ro.hout); cudaFreeHost(h->ro.hin); cudaFreeHost(h->ro.hobs32);
+    for (int i = 0; i < 4; ++i) if (h->ro.gexec[i]) cudaGraphExecDestroy(h->ro.gexec[i]);
   }
   cudaFree(h->snap);
   cudaFree(h->cat_part);
@@ -2453,7 +2454,8 @@ int ssa_ukf_rollout_config(ssa_ukf* h, const double* orbits, int n_orbits, const
   // (the cached graphs of ssa_ukf_step stay valid: every pointer they captured belongs to the handle)
   if (h->ro.init) {
     cudaFree(h->ro.dbuf); cudaFree(h->ro.ibuf); cudaFree(h->ro.dout); cudaFreeHost(h->ro.hout); cudaFreeHost(h->ro.hin);
-    for (int i = 0; i < 2; ++i) if (h->ro.gexec[i]) { cudaGraphExecDestroy(h->ro.gexec[i]); h->ro.gexec[i] = nullptr; }
+    cudaFree(h->ro.dobs32); cudaFreeHost(h->ro.hobs32);
+    for (int i = 0; i < 4; ++i) if (h->ro.gexec[i]) { cudaGraphExecDestroy(h->ro.gexec[i]); h->ro.gexec[i] = nullptr; }
     h->ro.init = 0;
   }
   h->ro.n_orbits = n_orbits; h->ro.n_table = n_table; h->ro.update_interval = update_interval;
@@ -2478,7 +2480,11 @@ int ssa_ukf_rollout_config(ssa_ukf* h, const double* orbits, int n_orbits, const
   CK(cudaHostAlloc(&h->ro.hin, sizeof(int32_t) * E, cudaHostAllocDefault));
   memset(h->ro.hout, 0, h->ro.out_bytes);
   memset(h->ro.hin, 0, sizeof(int32_t) * E);
-  h->ro.gexec[0] = h->ro.gexec[1] = nullptr;
+  CK(cudaMalloc(&h->ro.dobs32, sizeof(float) * 12 * N));
+  CK(cudaMemset(h->ro.dobs32, 0, sizeof(float) * 12 * N));
+  CK(cudaHostAlloc(&h->ro.hobs32, sizeof(float) * 12 * N, cudaHostAllocDefault));
+  memset(h->ro.hobs32, 0, sizeof(float) * 12 * N);
+  for (int i = 0; i < 4; ++i) h->ro.gexec[i] = nullptr;
   h->ro.init = 1;
   return SSA_OK;
 }
@@ -2510,7 +2516,16 @@ int ssa_ukf_rollout_reset(ssa_ukf* h, void* stream) {
 }
 
 // the kernels of one episodic step (captured into a graph by ssa_ukf_rollout_step)
-static int rollout_chain(ssa_ukf* h, cudaStream_t st, int auto_reset) {
+// SSA_ROLLOUT_OBS_F32: the step's observations as floats (round to nearest), two per thread
+__global__ void __launch_bounds__(256) k_obs_to_f32(const double2* __restrict__ obs, float2* __restrict__ out, const long n2) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n2) {
+    const double2 v = obs[i];
+    out[i] = make_float2(__double2float_rn(v.x), __double2float_rn(v.y));
+  }
+}
+
+static int rollout_chain(ssa_ukf* h, cudaStream_t st, int auto_reset, int obs_f32) {
   RolloutParams rp;
   rollout_params(h, &rp, 1);
   const long N = h->cfg.n_objects;
@@ -2528,6 +2543,18 @@ static int rollout_chain(ssa_ukf* h, cudaStream_t st, int auto_reset) {
     rc = rollout_refresh(h, st, 1);
     if (rc) return rc;
   }
+  if (obs_f32) {
+    const long n2 = 6 * N;  // 12 N doubles, two at a time (the block is cudaMalloc-aligned)
+    k_obs_to_f32<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>((const double2*)h->ro.dout, (float2*)h->ro.dobs32, n2);
+    h->launches++;
+  }
+  return SSA_OK;
+}
+
+int ssa_ukf_rollout_obs_f32(ssa_ukf* h, float** host, float** device) {
+  if (!h || !h->ro.init) return SSA_EINVAL;
+  if (host) *host = h->ro.hobs32;
+  if (device) *device = h->ro.dobs32;
   return SSA_OK;
 }
 
@@ -2536,7 +2563,9 @@ int ssa_ukf_rollout_step(ssa_ukf* h, int auto_reset, void* stream) {
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const size_t E = h->cfg.n_envs;
-  const int a = (auto_reset & 1) ? 1 : 0;
+  const bool obs_f32 = (auto_reset & SSA_ROLLOUT_OBS_F32) != 0;
+  const int ar = (auto_reset & 1) ? 1 : 0;
+  const int a = ar + (obs_f32 ? 2 : 0);
   const bool device_io = (auto_reset & SSA_ROLLOUT_DEVICE_IO) != 0;
   if (!device_io) CK(cudaMemcpyAsync(h->ro.act_in, h->ro.hin, sizeof(int32_t) * E, cudaMemcpyHostToDevice, st));
   const char* gv = getenv("SSA_UKF_GRAPH");
@@ -2546,7 +2575,7 @@ int ssa_ukf_rollout_step(ssa_ukf* h, int auto_reset, void* stream) {
       CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
       const long l0 = h->launches;
       CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      const int rc = rollout_chain(h, cs, a);
+      const int rc = rollout_chain(h, cs, ar, obs_f32);
       cudaGraph_t g = nullptr;
       const cudaError_t ce = cudaStreamEndCapture(cs, &g);
       h->ro.gkernels[a] = (int)(h->launches - l0);
@@ -2561,10 +2590,18 @@ int ssa_ukf_rollout_step(ssa_ukf* h, int auto_reset, void* stream) {
     CK(cudaGraphLaunch(h->ro.gexec[a], st));
     h->launches += h->ro.gkernels[a];
   } else {
-    const int rc = rollout_chain(h, st, a);
+    const int rc = rollout_chain(h, st, ar, obs_f32);
     if (rc) return rc;
   }
-  if (!device_io) CK(cudaMemcpyAsync(h->ro.hout, h->ro.dout, h->ro.out_bytes, cudaMemcpyDeviceToHost, st));
+  if (!device_io) {
+    if (obs_f32) {  // float observations + the reward / greedy / done tail of the double block
+      const size_t N = h->cfg.n_objects;
+      CK(cudaMemcpyAsync(h->ro.hobs32, h->ro.dobs32, sizeof(float) * 12 * N, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(h->ro.hout + 12 * N, h->ro.dout + 12 * N, h->ro.out_bytes - sizeof(double) * 12 * N, cudaMemcpyDeviceToHost, st));
+    } else {
+      CK(cudaMemcpyAsync(h->ro.hout, h->ro.dout, h->ro.out_bytes, cudaMemcpyDeviceToHost, st));
+    }
+  }
   return SSA_OK;
 }
 

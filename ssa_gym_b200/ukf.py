@@ -264,13 +264,18 @@ class BatchedUKF:
                            "reward": view(ptrs[2], ctypes.c_double, (E,)),
                            "greedy": view(ptrs[3], ctypes.c_int32, (E, _lib.N_TASKERS)),
                            "done": view(ptrs[4], ctypes.c_uint8, (E,))}
+        h32, d32 = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(self.lib.ssa_ukf_rollout_obs_f32(self.h, ctypes.byref(h32), ctypes.byref(d32)), "ssa_ukf_rollout_obs_f32")
+        self.rollout_io["obs_f32"] = view(h32, ctypes.c_float, (N, 12))  # filled by rollout_step(obs_f32=True)
+        self.rollout_obs_f32_device = d32.value
         return self.rollout_io
 
     def rollout_reset(self, stream=None):
         _lib.check(self.lib.ssa_ukf_rollout_reset(self.h, stream), "ssa_ukf_rollout_reset")
 
-    def rollout_step(self, auto_reset=True, stream=None, device_io=False):
-        mode = (1 if auto_reset else 0) | (_lib.ROLLOUT_DEVICE_IO if device_io else 0)
+    def rollout_step(self, auto_reset=True, stream=None, device_io=False, obs_f32=False):
+        """obs_f32: the observations leave the device as float32 (rollout_io['obs_f32']; the float64 block is not copied)."""
+        mode = (1 if auto_reset else 0) | (_lib.ROLLOUT_DEVICE_IO if device_io else 0) | (_lib.ROLLOUT_OBS_F32 if obs_f32 else 0)
         _lib.check(self.lib.ssa_ukf_rollout_step(self.h, mode, stream), "ssa_ukf_rollout_step")
 
     @property

@@ -39,6 +39,14 @@ class VecSSATaskerEnv:
         self.reward_type = config['reward_type']
         self.obs_type = config['obs_type']
         self.obs_returned = config.get('obs_returned', 'flatten')
+        # 'float32' (device mode, state-vector layouts): the observations cross PCIe as floats — half the bytes of the
+        # step's only large copy — rounded on the device exactly like numpy's astype(float32) of the float64 rows
+        self.obs_dtype = np.dtype(config.get('obs_dtype', 'float64'))
+        if self.obs_dtype == np.float32:
+            if rng != 'device' or self.obs_returned == 'aer':
+                raise ValueError("obs_dtype='float32' needs rng='device' and a state-vector layout (obs_returned != 'aer')")
+        elif self.obs_dtype != np.float64:
+            raise ValueError("obs_dtype must be 'float64' or 'float32'")
         self.update_interval = config['update_interval']
         self.auto_reset = auto_reset
         if config.get('orbits') is not None:
@@ -68,7 +76,7 @@ class VecSSATaskerEnv:
         # SS2:164-177: 'flatten' [m*12] (x and diag P per RSO), 'aer' [m*4] (az, el, range of the filter mean and trace P),
         # anything else the 2-d [m, 12] array
         oshape = {'flatten': (self.m * 12,), 'aer': (self.m * 4,)}.get(self.obs_returned, (self.m, 12))
-        self.observation_space = spaces.Box(low=np.full(oshape, -np.inf), high=np.full(oshape, np.inf), dtype=np.float64)
+        self.observation_space = spaces.Box(low=np.full(oshape, -np.inf), high=np.full(oshape, np.inf), dtype=self.obs_dtype.type)
         self._device = device
         self.np_randoms = [None] * self.E
         self.i = np.zeros(self.E, dtype=np.int32)
@@ -149,7 +157,7 @@ class VecSSATaskerEnv:
             self.ukf.rollout_reset()
             self.ukf.sync()
             self.i[:] = 0
-            return self._format_obs(self._io["obs"].reshape(self.E, self.m * 12))
+            return self._format_obs(self._io["obs"].reshape(self.E, self.m * 12).astype(self.obs_dtype, copy=False))
         for e in range(self.E):
             self._draw(e)
         self.ukf.reset(self.x_true0.reshape(self.N, 6), self.x_filter0.reshape(self.N, 6), self.P_0)
@@ -232,7 +240,8 @@ class VecSSATaskerEnv:
         is a VIEW of the handle's pinned output block: it is overwritten by the next step."""
         io = self._io
         io["actions"][:] = actions
-        self.ukf.rollout_step(self.auto_reset)
+        f32 = self.obs_dtype == np.float32
+        self.ukf.rollout_step(self.auto_reset, obs_f32=f32)
         self.ukf.sync()
         dones = io["done"].astype(bool)
         rewards = io["reward"].copy()
@@ -240,7 +249,7 @@ class VecSSATaskerEnv:
         if self.auto_reset:
             self.i[dones] = 0
             self.episodes[dones] += 1
-        self.obs = self._format_obs(io["obs"].reshape(self.E, self.m * 12))
+        self.obs = self._format_obs(io["obs_f32" if f32 else "obs"].reshape(self.E, self.m * 12))
         return self.obs, self._format_reward(rewards), dones, self._infos  # E empty dicts, allocated once (4096 dict constructions cost 100 us)
 
     # -- device-resident consumer (a policy on the same GPU): no host copies, nothing synchronises -------------------

@@ -186,3 +186,35 @@ def test_device_resident_step_equals_host_io_step():
         n_done += int(done.sum())
     assert n_done > E
     a_env.close(); b_env.close()
+
+
+@pytest.mark.parametrize("layout", ["flatten", "2d"])
+def test_float32_observations_are_the_rounded_float64_ones(layout):
+    """obs_dtype='float32' (SSA_ROLLOUT_OBS_F32): the step's observations leave the device as floats — the float64 rows
+    rounded to nearest, bit for bit numpy's astype(float32) — and reward / done / greedy are untouched, over auto-resets."""
+    E = 48
+    cfg = dict(ssa_gym_b200.env_config, steps=10, obs_returned=layout)
+    cfg["trans_matrix"] = gcrs2irts_matrix_approx(time_table(cfg["t_0"], cfg["time_step"], cfg["steps"]))
+    seeds = list(range(300, 300 + E))
+    a_env = VecSSATaskerEnv(cfg, E, seeds=seeds, rng="device")
+    b_env = VecSSATaskerEnv(dict(cfg, obs_dtype="float32"), E, seeds=seeds, rng="device")
+    assert b_env.observation_space.dtype == np.float32 and a_env.observation_space.dtype == np.float64
+    o64, o32 = a_env.vector_reset(), b_env.vector_reset()
+    assert o32.dtype == np.float32 and np.array_equal(o32, o64.astype(np.float32))
+    rng = np.random.RandomState(5)
+    n_done = 0
+    for t in range(25):
+        act = rng.randint(0, cfg["rso_count"], size=E).astype(np.int32)
+        o64, r64, d64, _ = a_env.vector_step(act)
+        o32, r32, d32, _ = b_env.vector_step(act)
+        assert o32.dtype == np.float32 and o32.shape == o64.shape
+        assert np.array_equal(o32.view(np.uint32), o64.astype(np.float32).view(np.uint32))
+        assert H.bits_equal(r32, r64) and np.array_equal(d32, d64)
+        assert np.array_equal(a_env._io["greedy"], b_env._io["greedy"])
+        n_done += int(d64.sum())
+    assert n_done > E
+    a_env.close(); b_env.close()
+    with pytest.raises(ValueError):
+        VecSSATaskerEnv(dict(cfg, obs_dtype="float32", obs_returned="aer"), 4, rng="device")
+    with pytest.raises(ValueError):
+        VecSSATaskerEnv(dict(cfg, obs_dtype="float32"), 4, rng="host")
