@@ -270,6 +270,7 @@ struct UpdateTile {
   double xn[6][T];
   uint64_t bar;
   int st[T], code[T], vis[T], ok[T], nan[T];
+  int want[T];  // the object takes the update this step: every object (SSA_STEP_UPDATE_ALL) or the tasked one of its environment (_ACT)
   int live0[T], live[T], exc[T], texc[T], pnan[T], res[T], bad[T];  // predict phases of the fused kernel k_step_tile
 };
 
@@ -325,7 +326,7 @@ __device__ __forceinline__ void tile_update_body(const KParams& p, UpdateTile<T>
     const int k = tid % 14;
     const long loc = loc0 + o;
     const bool is_truth = (k == 13);
-    const bool live = !(sm.st[o] & SSA_ST_FAILED) && !sm.code[o];
+    const bool live = !(sm.st[o] & SSA_ST_FAILED) && !sm.code[o] && sm.want[o];
     if (loc < p.Nc && (is_truth || live)) {
       const long obj = p.obj0 + loc;
       double s[6], z[3], uvw[3];
@@ -363,7 +364,7 @@ __device__ __forceinline__ void tile_update_body(const KParams& p, UpdateTile<T>
   __syncthreads();
 
   // the object of this thread's algebra column takes the update: wanted, not failed, factor available, visible
-  const bool upd_a = valid_a && !(sm.st[o_a] & SSA_ST_FAILED) && !sm.code[o_a] && sm.vis[o_a];
+  const bool upd_a = valid_a && !(sm.st[o_a] & SSA_ST_FAILED) && !sm.code[o_a] && sm.vis[o_a] && sm.want[o_a];
   // ---- mean_z: Cartesian (uvw) mean of the angular measurements, or the plain mean (xyz) ----
   if (r_a < 3) {
     if (upd_a) {
@@ -374,7 +375,7 @@ __device__ __forceinline__ void tile_update_body(const KParams& p, UpdateTile<T>
       sm.zm[r_a][o_a] = acc;
     }
   } else if (r_a == 3) {
-    if (valid_a && !(sm.st[o_a] & SSA_ST_FAILED) && p.z_true) {
+    if (valid_a && !(sm.st[o_a] & SSA_ST_FAILED) && sm.want[o_a] && p.z_true) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) p.z_true[obj_a * 3 + a] = sm.zt[a][o_a];  // SS2:298
     }
@@ -491,7 +492,7 @@ __device__ __forceinline__ void tile_update_body(const KParams& p, UpdateTile<T>
   // ---- P -= K (S K^T) and the new mean go back to HBM and into the tile (the epilogue reads them): thread (element,
   //      object), elements 0..20 of P then 21..26 = the mean.  A failure of this update (or of the stand-alone
   //      factorisation before it) stores the sentinels instead, SS2:369-382 ----
-  const bool alive_a = valid_a && !(sm.st[o_a] & SSA_ST_FAILED);
+  const bool alive_a = valid_a && !(sm.st[o_a] & SSA_ST_FAILED) && sm.want[o_a];  // (objects that do not take the update only get the epilogue)
   const int fail_a = !alive_a ? 0
                               : (sm.code[o_a] ? sm.code[o_a]
                                               : (sm.vis[o_a] ? (!sm.ok[o_a] ? (SSA_ST_LINALG | SSA_ST_IN_UPDATE)
@@ -598,8 +599,13 @@ __global__ void __launch_bounds__(NT, SSA_LB_UTILE) k_update_tile(const KParams 
   int st_r = SSA_ST_FAILED, code_r = 0;  // threads 3 T .. 4 T - 1 keep the words of object tid - 3 T
   if (tid >= 3 * T && tid < 4 * T) {
     const int o = tid - 3 * T;
-    if (loc0 + o < p.Nc) { st_r = p.status[p.obj0 + loc0 + o]; code_r = p.code[p.obj0 + loc0 + o]; }
-    sm.st[o] = st_r; sm.code[o] = code_r; sm.ok[o] = 1; sm.nan[o] = 0; sm.vis[o] = 0;
+    int want = 0;
+    if (loc0 + o < p.Nc) {
+      const long obj = p.obj0 + loc0 + o;
+      st_r = p.status[obj]; code_r = p.code[obj];
+      want = (p.flags & SSA_STEP_UPDATE_ALL) ? 1 : (((p.flags & SSA_STEP_UPDATE_ACT) && p.actions[obj / p.m] == (int)(obj % p.m)) ? 1 : 0);
+    }
+    sm.st[o] = st_r; sm.code[o] = code_r; sm.ok[o] = 1; sm.nan[o] = 0; sm.vis[o] = 0; sm.want[o] = want;
     if (REFACTOR) {
       sm.res[o] = (!(st_r & SSA_ST_FAILED) && (code_r == 0 || code_r == SSA_ST_NAN)) ? CHOL_PENDING : 0;
       sm.bad[o] = 0;
@@ -746,7 +752,7 @@ __global__ void __launch_bounds__(NT, 4) k_step_tile(const KParams p, const __gr
     int st = SSA_ST_FAILED;
     if (loc0 + o < p.Nc) st = p.status[p.obj0 + loc0 + o];
     const int alive = (loc0 + o < p.Nc) && !(st & SSA_ST_FAILED);
-    sm.st[o] = st; sm.code[o] = 0; sm.ok[o] = 1; sm.nan[o] = 0; sm.vis[o] = 0;
+    sm.st[o] = st; sm.code[o] = 0; sm.ok[o] = 1; sm.nan[o] = 0; sm.vis[o] = 0; sm.want[o] = 1;
     sm.live0[o] = alive; sm.live[o] = 0; sm.exc[o] = 0; sm.texc[o] = 0; sm.pnan[o] = 0; sm.bad[o] = 0;
     sm.res[o] = alive ? CHOL_PENDING : 0;
   }

@@ -1644,6 +1644,7 @@ struct ssa_ukf {
   int use_tile;   // tile kernels (default); SSA_UKF_KERNEL=split selects the five-kernel split pipeline
   int use_team;   // SSA_UKF_KERNEL=team selects the fused 16-lane team kernel instead of the split pipeline
   int use_fused;  // one launch per full catalog step (k_step_tile) instead of the four tile kernels
+  int legacy_act; // SSA_UKF_ACT=split: the RL-mode update of the tasked objects runs as k_hx + k_update instead of k_update_tile
   int fold_factor;  // tile2: the two factorisations inside the tile kernels instead of k_factor / k_refactor
   int sm_count;
   // double-buffered host pipeline (ssa_ukf_step_host)
@@ -1809,6 +1810,7 @@ int ssa_ukf_create(const ssa_ukf_cfg* cfg, int device, ssa_ukf** out) {
     h->use_team = (kv && strcmp(kv, "team") == 0) ? 1 : 0;
     h->use_tile = (kv && strcmp(kv, "split") == 0) ? 0 : 1;
     h->use_fused = (kv && strcmp(kv, "fused") == 0) ? 1 : 0;
+    { const char* av = getenv("SSA_UKF_ACT"); h->legacy_act = (av && strcmp(av, "split") == 0) ? 1 : 0; }
     h->fold_factor = (kv && strcmp(kv, "tile2") == 0) ? 1 : 0;
     h->sm_count = 148;
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
@@ -2119,7 +2121,9 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
     // SSA_UKF_KERNEL=tile2: the factorisations ride inside the tile kernels (two launches per catalog step, the factor
     // never in HBM) instead of running as k_factor / k_refactor (default: four launches, measured faster — DESIGN.md)
     const bool fold = tile && h->fold_factor && predict;
-    const bool tile_upd = tile && (flags & SSA_STEP_UPDATE_ALL);
+    // (RL mode: the same kernel, only the tasked object of an environment takes the update — the others get the truth
+    // measurement and the epilogue; the refresh after an auto-reset, gated per environment, keeps the split kernels)
+    const bool tile_upd = tile && ((flags & SSA_STEP_UPDATE_ALL) || ((flags & SSA_STEP_UPDATE_ACT) && !p.env_gate && !h->legacy_act));
     if ((predict || update) && !fold) { launch_chain(pdl, k_factor, gobj2, kObjThreads, 0, st, p); h->launches++; }
     if (evc) CK(cudaEventRecord(evc[1], st));
     if (predict || truth) {

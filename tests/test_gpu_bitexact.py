@@ -161,6 +161,43 @@ def test_rl_mode_actions_bitexact(kernel):
     ukf.close()
 
 
+@pytest.mark.parametrize("act", ["tile", "split"])
+@pytest.mark.parametrize("chunk", [None, "1000"])
+def test_rl_mode_tile_update_equals_split_update(act, chunk, monkeypatch):
+    """RL mode runs the update of the tasked objects through k_update_tile (the other objects of a tile only get the truth
+    measurement and the epilogue); SSA_UKF_ACT=split keeps k_hx + k_update.  Both equal the twin in every output, including
+    the `updated` flags, environments that task nothing (action -1) and environment-straddling chunks."""
+    if act == "split":
+        monkeypatch.setenv("SSA_UKF_ACT", "split")
+    if chunk:
+        monkeypatch.setenv("SSA_UKF_CHUNK", chunk)
+    E, m, steps = 517, 7, 4
+    N = E * m
+    cat, x, P0, zn = H.c2_inputs(N, steps)
+    rng = np.random.RandomState(6)
+    actions = rng.randint(-1, m, size=(steps, E)).astype(np.int32)
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ACT | F.STEP_EPILOGUE | F.STEP_RECORD
+    cfg = H.make_cfg(N, E=E, m=m, obs_limit_deg=10.0)
+    st = H.HostState(cat, x, P0)
+    for s in range(steps):
+        H.cpu_step("twin", cfg, st, H.CEL2TER06AXY, flags, actions=actions[s], z_noise=zn[s])
+    ukf = _gpu_run(dict(obs_limit_deg=10.0), cat, x, P0, zn, [flags] * steps, actions=actions, E=E, m=m)
+    _compare_all(ukf, st, check_update_outputs=False)
+    upd = st.updated.astype(bool)
+    assert np.array_equal(ukf.download(F.F_UPDATED).astype(bool), upd) and 0 < upd.sum() < E
+    assert H.bits_equal(ukf.download(F.F_Y)[upd], st.y[upd]) and H.bits_equal(ukf.download(F.F_S)[upd], st.S[upd])
+    assert H.bits_equal(ukf.download(F.F_Z_TRUE)[upd], st.z_true[upd])
+    ukf.close()
+    # stand-alone update of the tasked objects (no predict in the step): factor, then update
+    st2 = H.HostState(cat, x, P0)
+    f2 = F.STEP_UPDATE_ACT | F.STEP_EPILOGUE | F.STEP_RECORD
+    H.cpu_step("twin", cfg, st2, H.CEL2TER06AXY, f2, actions=actions[0], z_noise=zn[0])
+    ukf = _gpu_run(dict(obs_limit_deg=10.0), cat, x, P0, zn, [f2], actions=actions[:1], E=E, m=m)
+    _compare_all(ukf, st2, check_update_outputs=False)
+    assert np.array_equal(ukf.download(F.F_UPDATED).astype(bool), st2.updated.astype(bool))
+    ukf.close()
+
+
 @pytest.mark.parametrize("obs_type,resample", [("xyz", True), ("aer", False), ("xyz", False)])
 def test_variants_bitexact(obs_type, resample, kernel):
     N, steps = 2048, 3
