@@ -836,7 +836,7 @@ def run_catalog(a, rank, local_rank, world):
         # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel at this shard size
         traffic = traffic_step = hw = None
         try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r03_ncu_kernels.json")))
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r04_ncu_kernels.json")))
             ent = cap.get(str(n_obj))
             if ent and tile and not team:
                 traffic = ent["k_predict_tile"]["dram_bytes_per_launch"]
@@ -852,7 +852,7 @@ def run_catalog(a, rank, local_rank, world):
                           "whole_step": {"flop_per_object": sf / n_obj, "achieved": sf / (kern_ms * 1e-3) / 1e12,
                                          "frac": sf / (kern_ms * 1e-3) / 1e12 / peak_tf},
                           "what": "sm__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on of the committed ncu capture "
-                                  "(profiles/r03_ncu_kernels.json): flops the threads actually executed, divisions / square roots / "
+                                  "(profiles/r04_ncu_kernels.json): flops the threads actually executed, divisions / square roots / "
                                   "transcendentals expanded into their FMA sequences; the FP64 pipe is busier than this fraction "
                                   "because DADD / DMUL / DSETP occupy it like an FMA"}
         except Exception:
@@ -885,7 +885,7 @@ def run_catalog(a, rank, local_rank, world):
                                  "39 kflop and 920 B per object over the mean step; frac_as_implemented prices the streamlined arithmetic "
                                  "actually executed (20.6 kflop per object); peak = DFMA microbenchmark measured live in this run "
                                  "(ssa_ukf_fp64_peak; FP64 is not in MEASURED_PEAKS.json); traffic = DRAM bytes of the kernel / of the "
-                                 "step's kernels from the committed ncu capture (profiles/r03_ncu_kernels.json) when one exists for this shard size"},
+                                 "step's kernels from the committed ncu capture (profiles/r04_ncu_kernels.json) when one exists for this shard size"},
             "e2e": {"value": e2e_val, "unit": "object-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "gpu_launches": int(e2e_launches), "bytes_are": "per rank",
                     "api": "BatchedUKF.step_pinned (ssa_ukf_step_pinned): pinned host input block, 1 H2D + 1 graph launch per step"
