@@ -857,6 +857,23 @@ def run_catalog(a, rank, local_rank, world):
                                   "because DADD / DMUL / DSETP occupy it like an FMA"}
         except Exception:
             pass
+        # SURVEY 8(d)'s counts are estimates; the measured ones (tools/opcount.py: the reference's literal sequence run through
+        # an operation-counting build of the oracle, priced with the same convention) are reported beside the fractions they give
+        ref_counted = None
+        try:
+            oc = json.load(open(os.path.join(ROOT, "profiles", "opcount_reference_sequence.json")))
+            fu = oc["unit (truth + predict + update + epilogue)"]["flop_survey_convention"]
+            fp = oc["truth + predict"]["flop_survey_convention"]
+            ref_counted = {"flop_per_object": fu, "flop_per_object_predict_and_truth": fp,
+                           "flop_per_propagation": oc["fx (one propagation, dt = 20 s)"]["flop_survey_convention"],
+                           "flop_per_object_every_operation_1": oc["unit (truth + predict + update + epilogue)"]["flop_every_op_1"],
+                           "whole_step_frac": fu * n_obj / (kern_ms * 1e-3) / 1e12 / peak_tf,
+                           "what": "operation count of the reference's literal sequence, MEASURED (profiles/opcount_reference_sequence.json) "
+                                   "instead of SURVEY 8(d)'s estimate of 39 kflop / 27.5 kflop / 1.85 kflop, same pricing convention; the "
+                                   "fraction it gives exceeds the executed-arithmetic fractions (hw_counted, frac_as_implemented) because "
+                                   "the implementation does not execute most of the reference's divisions and transcendentals"}
+        except Exception:
+            pass
         step_tf = FLOP_PER_UNIT_REF * n_obj / (kern_ms * 1e-3) / 1e12
         step_gb = BYTES_PER_UNIT_REF * n_obj / (kern_ms * 1e-3) / 1e9
         line = {
@@ -870,6 +887,7 @@ def run_catalog(a, rank, local_rank, world):
                          "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / float(np.sum(kms)),
                          "frac_as_implemented": dom_flop_impl / (dom_ms * 1e-3) / 1e12 / peak_tf,
                          "hw_counted": hw,
+                         "reference_sequence_measured": ref_counted,
                          "step_kernels_ms": ({"k_factor": float(kms[0]), "k_predict_tile": float(kms[1]), "k_refactor": float(kms[2]),
                                               "k_update_tile": float(kms[4])} if tile and not team else
                                              {"factor": float(kms[0]), "fx": float(kms[1]), "ut": float(kms[2]), "hx": float(kms[3]),

@@ -1,0 +1,46 @@
+"""CPU: the operation-counting build of the oracle (oracle/opcount.cpp, tools/opcount.py) is the same arithmetic as
+liboracle.so and its counts are the ones committed in profiles/opcount_reference_sequence.json (the measured replacement
+of SURVEY 8(d)'s estimated flop counts that bench.py reports as roofline.reference_sequence_measured)."""
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+import helpers as H
+from ssa_gym_b200 import _lib as F
+
+sys.path.insert(0, os.path.join(H.ROOT, "tools"))
+
+
+def test_counting_build_equals_oracle_and_committed_counts():
+    import opcount
+    L = opcount.build()
+    n = 600
+    cat, x, P0, zn = H.c2_inputs(n, 2)
+    cfg = H.make_cfg(n)
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE
+    sts = []
+    for lib in (L, H.oracle()):
+        st = H.HostState(cat, x, P0)
+        if lib is L:
+            L.opcount_reset()
+        for s in range(2):
+            lib.oracle_step(ctypes.byref(cfg), H.p(np.ascontiguousarray(H.CEL2TER06AXY)), ctypes.c_int(flags), H.p(st.x_true), H.p(st.x),
+                            H.p(st.P), H.p(st.status), H.p(st.infl), None, H.p(np.ascontiguousarray(zn[s])), H.p(st.obs), H.p(st.dpos),
+                            H.p(st.dvel), H.p(st.spos), H.p(st.svel), H.p(st.trace), H.p(st.z_true), H.p(st.y), H.p(st.S),
+                            H.p(st.sigmas_h), H.p(st.visible), H.p(st.updated))
+        sts.append(st)
+    a, b = sts
+    assert H.bits_equal(a.x, b.x) and H.bits_equal(a.P, b.P) and H.bits_equal(a.obs, b.obs) and H.bits_equal(a.x_true, b.x_true)
+    buf = (ctypes.c_uint64 * L.opcount_slots())()
+    L.opcount_get(buf)
+    per = dict(zip(opcount.SLOTS, [v / (2 * n) for v in buf]))
+    flop = sum(per[k] * opcount.WEIGHT[k] for k in per)
+    ref = json.load(open(os.path.join(H.ROOT, "profiles", "opcount_reference_sequence.json")))
+    committed = ref["unit (truth + predict + update + epilogue)"]["flop_survey_convention"]
+    assert abs(flop - committed) < 0.03 * committed, (flop, committed)   # (Newton trip counts vary a little with the sample)
+    assert 35e3 < committed < 50e3
+    # the structural counts do not depend on the sample: 14 propagations -> 14 acos (rv2coe), 13 + 1 + 1 asin (hx + uvw2aer)
+    assert abs(per["acos"] - 14.0) < 1e-9 and abs(per["asin"] - 15.0) < 1e-9
