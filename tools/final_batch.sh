@@ -1,8 +1,8 @@
 #!/bin/bash
 # The measurement batch whose outputs are committed under profiles/ (one B200): smoke, the GPU test suite, ncu --set full of
 # the four step kernels at three catalog sizes, the default bench line, the reference arm and the two launch lists.
-#   gpurun --timeout 2400 -- 'bash tools/final_batch.sh r03'
-tag=${1:-r03}
+#   gpurun --timeout 2400 -- 'bash tools/final_batch.sh r04'
+tag=${1:-r04}
 out=gpurun_out
 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; tail -1 $out/${tag}_smoke.log
 python -m pytest tests -m gpu -x -q > $out/${tag}_gputests.log 2>&1; tail -2 $out/${tag}_gputests.log
