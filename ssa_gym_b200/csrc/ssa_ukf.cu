@@ -706,6 +706,24 @@ __device__ __forceinline__ long upd_object(const KParams& p, long lidx) {
 #ifndef SSA_HX_INLINE
 #define SSA_HX_INLINE true
 #endif
+// measurement of the TRUE state of object idx (scratch column loc): visibility (SS2:418-425), z_true into the scratch row ZT
+__device__ __forceinline__ void hx_truth(const KParams& p, const long idx, const long loc, const bool store_zt) {
+  double xt[3], zt[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) xt[i] = p.xt[i * p.ld + idx];
+  ssa_obs ob = p.ob;
+  if (p.Menv) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ob.M[i] = env_M(p, idx / p.m)[i];
+  }
+  ssa_hx_aer_t<SSA_HX_INLINE>(xt, &ob, zt);
+  if (store_zt) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p.ZT[a * p.lds + loc] = zt[a];
+  }
+  p.visible[idx] = (uint8_t)(zt[1] >= p.obs_limit);
+}
+
 __global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx(const KParams p) {
   pdl_prologue();
   const long lidx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -716,19 +734,7 @@ __global__ void __launch_bounds__(kFxThreads, SSA_LB_HX * 128 / kFxThreads) k_hx
     if (lidx >= p.Nc) return;
     const long idx = p.obj0 + lidx;
     if (p.env_gate && !p.env_gate[idx / p.m]) return;
-    const long loc = lidx;
-    double xt[3], zt[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) xt[i] = p.xt[i * ld + idx];
-    ssa_obs ob = p.ob;
-    if (p.Menv) {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) ob.M[i] = env_M(p, idx / p.m)[i];
-    }
-    ssa_hx_aer_t<SSA_HX_INLINE>(xt, &ob, zt);
-#pragma unroll
-    for (int a = 0; a < 3; ++a) p.ZT[a * lds + loc] = zt[a];
-    p.visible[idx] = (uint8_t)(zt[1] >= p.obs_limit);
+    hx_truth(p, idx, lidx, true);
     return;
   }
   const long obj = upd_object(p, lidx);
@@ -1058,11 +1064,19 @@ __global__ void __launch_bounds__(128) ssa_det_kernel(const double* __restrict__
 // shared memory and no barrier — with one CTA per 10-object environment 118 of 128 threads only took part in the
 // shuffles (measured at E = 4096: 30 us per launch, two launches per episodic step).
 template <bool WARP>
+__device__ __forceinline__ void env_reduce_body(const EnvParams& p, const int e);
+template <bool WARP>
 __global__ void __launch_bounds__(128, 6) ssa_env_reduce_kernel(const EnvParams p) {
   const int e = WARP ? (int)(blockIdx.x * 4 + (threadIdx.x >> 5)) : (int)blockIdx.x;
   if (WARP && e >= p.E) return;
   // the refresh after an auto-reset concerns the re-drawn environments only: the others keep this step's results
   if (p.greedy_only && p.reset_mask && !p.reset_mask[e]) return;
+  env_reduce_body<WARP>(p, e);
+}
+// WARP: the calling warp reduces environment e (its results go through slot threadIdx.x >> 5 of the shared scratch);
+// else the whole CTA does.
+template <bool WARP>
+__device__ __forceinline__ void env_reduce_body(const EnvParams& p, const int e) {
   const int j0 = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x, jstep = WARP ? 32 : (int)blockDim.x;
   const long base = (long)e * p.m;
   ArgMax a_trace{0.0, -1}, a_vtrace{0.0, -1}, a_vdpos{0.0, -1}, a_vdvel{0.0, -1}, a_spos{0.0, -1}, a_dpos{0.0, -1};
@@ -1196,9 +1210,13 @@ __global__ void __launch_bounds__(128) k_env_begin(const RolloutParams p) {
 }
 
 // (re)draw the environments whose done flag is set (all of them when p.done is null): SS2:193-221
+__device__ __forceinline__ void env_reset_body(const RolloutParams& p, const int e);
 __global__ void __launch_bounds__(128) k_env_reset(const RolloutParams p) {
   const int e = blockIdx.x;
   if (p.done && !p.done[e]) return;
+  env_reset_body(p, e);
+}
+__device__ __forceinline__ void env_reset_body(const RolloutParams& p, const int e) {
   const uint32_t k0 = p.key[2 * e], k1 = p.key[2 * e + 1], ep = p.episode[e];
   for (int j = threadIdx.x; j < p.m; j += blockDim.x) {
     const long obj = (long)e * p.m + j;
@@ -2039,7 +2057,7 @@ struct StepOverride {  // episodic mode: redirect the step's inputs / outputs
 static int cat_stats_launch(ssa_ukf* h, const double* dpos, const double* trace, long index_offset, cudaStream_t st, double* out);
 
 static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cudaEvent_t* ev, int hostbuf = -1,
-                     const StepOverride* ov = nullptr, KParams* p_out = nullptr) {
+                     const StepOverride* ov = nullptr, KParams* p_out = nullptr, bool params_only = false) {
   if (!h) return SSA_EINVAL;
   if ((flags & (SSA_STEP_UPDATE_ALL | SSA_STEP_UPDATE_ACT | SSA_STEP_EPILOGUE)) && !M && !(flags & SSA_STEP_M_PER_ENV) &&
       hostbuf < 0 && !ov) {
@@ -2087,6 +2105,7 @@ static int step_impl(ssa_ukf* h, const double M[9], int flags, void* stream, cud
   memcpy(p.ob.obs_itrs, c.obs_itrs, sizeof(p.ob.obs_itrs));
   memcpy(p.ob.T, c.T, sizeof(p.ob.T));
   if (p_out) *p_out = p;  // single-chunk launches all use these parameters (obj0 = 0, Nc = N)
+  if (params_only) return SSA_OK;
   if (ev) CK(cudaEventRecord(ev[0], st));
   if (h->use_team) {
     const unsigned grid = (unsigned)((c.n_objects + kTeamsPerCta - 1) / kTeamsPerCta);
@@ -2520,6 +2539,31 @@ int ssa_ukf_rollout_reset(ssa_ukf* h, void* stream) {
 }
 
 // the kernels of one episodic step (captured into a graph by ssa_ukf_rollout_step)
+// What follows the reward / done reduction of an episodic step with auto-reset, in ONE launch: every finished environment
+// is re-drawn (k_env_reset), the visibility, observations and errors of its fresh objects are evaluated (the truth slice of
+// k_hx, the epilogue of k_update), the determinants of its fresh covariances stored (ssa_det_kernel) and its greedy actions
+// re-evaluated (ssa_env_reduce_kernel) — one CTA per environment, the same device functions in the same order, so every
+// value equals the five-launch chain's; the CTA of an environment that is still running exits at once.  With episodes of
+// 480 steps the five launches found nothing to do in 479 steps of 480 and still cost ~20 us of a 130 us step.
+__global__ void __launch_bounds__(128) k_env_refresh(const RolloutParams rp, const KParams p, const EnvParams ep) {
+  const int e = blockIdx.x;
+  if (!rp.done[e]) return;
+  env_reset_body(rp, e);  // (ends with thread 0 advancing the episode counter and zeroing the step index)
+  __syncthreads();
+  for (int j = threadIdx.x; j < rp.m; j += blockDim.x) {
+    const long obj = (long)e * rp.m + j;
+    hx_truth(p, obj, obj, false);
+    update_body<false>(p, obj, obj, nullptr, 0);  // p.flags = SSA_STEP_EPILOGUE: obs row, errors, trace
+    const_cast<double*>(ep.det_cur)[obj] = ssa_det6_sym(ep.P + obj, ep.ld);  // (h->det_cur: ssa_det_kernel's output)
+  }
+  __syncthreads();
+  if (ep.m <= 64) {
+    if (threadIdx.x < 32) env_reduce_body<true>(ep, e);
+  } else {
+    env_reduce_body<false>(ep, e);
+  }
+}
+
 // SSA_ROLLOUT_OBS_F32: the step's observations as floats (round to nearest), two per thread
 __global__ void __launch_bounds__(256) k_obs_to_f32(const double2* __restrict__ obs, float2* __restrict__ out, const long n2) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2541,7 +2585,17 @@ static int rollout_chain(ssa_ukf* h, cudaStream_t st, int auto_reset, int obs_f3
   EnvParams ep;
   rollout_env_params(h, &ep, 1, 0);
   launch_env_reduce(h, ep, st);
-  if (auto_reset) {
+  if (auto_reset && !h->use_team && !getenv("SSA_UKF_REFRESH_CHAIN")) {  // one launch (k_env_refresh)
+    EnvParams rep;
+    rollout_env_params(h, &rep, 0, 1);
+    rep.reset_mask = rep.done;
+    StepOverride rov{h->ro.dout, h->ro.act_eff, h->ro.table, h->step_idx, 0, h->ro.n_table, rep.done};
+    KParams kp;
+    rc = step_impl(h, nullptr, SSA_STEP_EPILOGUE, st, nullptr, -1, &rov, &kp, true);
+    if (rc) return rc;
+    k_env_refresh<<<(unsigned)rp.E, 128, 0, st>>>(rp, kp, rep);
+    h->launches++;
+  } else if (auto_reset) {  // SSA_UKF_REFRESH_CHAIN=1 / team kernel: k_env_reset, then the gated refresh chain
     k_env_reset<<<(unsigned)rp.E, 128, 0, st>>>(rp);
     h->launches++;
     rc = rollout_refresh(h, st, 1);
