@@ -874,6 +874,19 @@ def run_catalog(a, rank, local_rank, world):
                                    "the implementation does not execute most of the reference's divisions and transcendentals"}
         except Exception:
             pass
+        impl_counted = None
+        try:
+            oi = json.load(open(os.path.join(ROOT, "profiles", "opcount_implemented.json")))
+            fi = oi["unit (truth + predict + update + epilogue)"]["flop_survey_convention"]
+            impl_counted = {"flop_per_object": fi, "flop_per_object_add_mul_2fma": oi["unit (truth + predict + update + epilogue)"]["flop_add_mul_2fma_only"],
+                            "flop_per_propagation": oi["fx (one propagation, dt = 20 s)"]["flop_survey_convention"],
+                            "whole_step_frac": fi * n_obj / (kern_ms * 1e-3) / 1e12 / peak_tf,
+                            "what": "primitive operations the IMPLEMENTED algorithm executes per object, MEASURED with an operation-counting "
+                                    "build of the host twin (profiles/opcount_implemented.json; add = mul = compare = 1, fma = 2, div = sqrt = "
+                                    "10; the elementary functions are FMA polynomials and are counted through their primitives) - agrees with "
+                                    "the hardware count hw_counted.whole_step.flop_per_object"}
+        except Exception:
+            pass
         step_tf = FLOP_PER_UNIT_REF * n_obj / (kern_ms * 1e-3) / 1e12
         step_gb = BYTES_PER_UNIT_REF * n_obj / (kern_ms * 1e-3) / 1e9
         line = {
@@ -888,6 +901,7 @@ def run_catalog(a, rank, local_rank, world):
                          "frac_as_implemented": dom_flop_impl / (dom_ms * 1e-3) / 1e12 / peak_tf,
                          "hw_counted": hw,
                          "reference_sequence_measured": ref_counted,
+                         "implemented_measured": impl_counted,
                          "step_kernels_ms": ({"k_factor": float(kms[0]), "k_predict_tile": float(kms[1]), "k_refactor": float(kms[2]),
                                               "k_update_tile": float(kms[4])} if tile and not team else
                                              {"factor": float(kms[0]), "fx": float(kms[1]), "ut": float(kms[2]), "hx": float(kms[3]),

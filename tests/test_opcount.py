@@ -44,3 +44,35 @@ def test_counting_build_equals_oracle_and_committed_counts():
     assert 35e3 < committed < 50e3
     # the structural counts do not depend on the sample: 14 propagations -> 14 acos (rv2coe), 13 + 1 + 1 asin (hx + uvw2aer)
     assert abs(per["acos"] - 14.0) < 1e-9 and abs(per["asin"] - 15.0) < 1e-9
+
+
+def test_counting_twin_equals_twin_and_committed_counts():
+    import opcount
+    L = opcount.build_twin()
+    n = 600
+    cat, x, P0, zn = H.c2_inputs(n, 2)
+    cfg = H.make_cfg(n)
+    flags = F.STEP_TRUTH | F.STEP_PREDICT | F.STEP_UPDATE_ALL | F.STEP_EPILOGUE
+    sts = []
+    L.opcount_reset()
+    for lib in (L, H.twin()):
+        st = H.HostState(cat, x, P0)
+        for s in range(2):
+            P = H.pack_P(st.P)
+            lib.twin_step(ctypes.byref(cfg), H.p(np.ascontiguousarray(H.CEL2TER06AXY)), ctypes.c_int(flags), H.p(st.x_true), H.p(st.x),
+                          H.p(P), H.p(st.status), H.p(st.infl), None, H.p(np.ascontiguousarray(zn[s])), H.p(st.obs), H.p(st.dpos),
+                          H.p(st.dvel), H.p(st.spos), H.p(st.svel), H.p(st.trace), H.p(st.z_true), H.p(st.y), H.p(st.S),
+                          H.p(st.sigmas_h), H.p(st.visible), H.p(st.updated))
+            st.P = H.unpack_P(P)
+        sts.append(st)
+    a, b = sts
+    assert H.bits_equal(a.x, b.x) and H.bits_equal(a.P, b.P) and H.bits_equal(a.obs, b.obs) and H.bits_equal(a.x_true, b.x_true)
+    buf = (ctypes.c_uint64 * L.opcount_slots())()
+    L.opcount_get(buf)
+    per = dict(zip(opcount.TSLOTS, [v / (2 * n) for v in buf]))
+    flop = sum(per[k] * opcount.TWEIGHT[k] for k in per)
+    committed = json.load(open(os.path.join(H.ROOT, "profiles", "opcount_implemented.json")))
+    c = committed["unit (truth + predict + update + epilogue)"]["flop_survey_convention"]
+    assert abs(flop - c) < 0.03 * c, (flop, c)
+    ref = json.load(open(os.path.join(H.ROOT, "profiles", "opcount_reference_sequence.json")))
+    assert c < 0.5 * ref["unit (truth + predict + update + epilogue)"]["flop_survey_convention"]  # the implementation executes a third of it
