@@ -86,7 +86,9 @@ def _emu_env_reduce(st, E, m, step_idx, reward_type, n_steps):
 
 
 @pytest.mark.parametrize("over", [{"steps": 14, "reward_type": "jones", "update_interval": 1},
-                                  {"steps": 9, "reward_type": "trinary", "update_interval": 2, "obs_limit": 10}])
+                                  {"steps": 9, "reward_type": "trinary", "update_interval": 2, "obs_limit": 10},
+                                  # m > 64: the per-environment reductions (step and refresh) run CTA-wide instead of per warp
+                                  {"steps": 7, "reward_type": "trinary", "update_interval": 1, "rso_count": 70}])
 def test_device_episodic_mode_equals_twin_emulation(over):
     """ssa_ukf_rollout_reset / ssa_ukf_rollout_step (one graph launch per step: noise, UKF kernels, reward / done,
     auto-reset, fresh obs, greedy taskers) against a step-by-step emulation built from the host twin: the same
