@@ -1066,7 +1066,7 @@ __global__ void __launch_bounds__(128) ssa_det_kernel(const double* __restrict__
 template <bool WARP>
 __device__ __forceinline__ void env_reduce_body(const EnvParams& p, const int e);
 template <bool WARP>
-__global__ void __launch_bounds__(128, 6) ssa_env_reduce_kernel(const EnvParams p) {
+__global__ void __launch_bounds__(128, 5) ssa_env_reduce_kernel(const EnvParams p) {
   const int e = WARP ? (int)(blockIdx.x * 4 + (threadIdx.x >> 5)) : (int)blockIdx.x;
   if (WARP && e >= p.E) return;
   // the refresh after an auto-reset concerns the re-drawn environments only: the others keep this step's results
@@ -1090,7 +1090,9 @@ __device__ __forceinline__ void env_reduce_body(const EnvParams& p, const int e)
     // reference reads row -1 of its history array there): the ratio is taken as 1
     double shan = 0.0;
     if (p.det_prev && !(p.greedy_only && !restart)) {
-      const double det = p.det_cur[base + j];
+      // (det_cur null: the determinant is evaluated here — the RL-sized environments, one lane per object — instead of
+      // by ssa_det_kernel: one launch fewer per episodic step)
+      const double det = p.det_cur ? p.det_cur[base + j] : ssa_det6_sym(p.P + base + j, p.ld);
       double prev = p.det_prev[base + j];
       if (restart || prev != prev) prev = det;  // (NaN = never set: ssa_ukf_reset)
       shan = ssa_log(ssa_div(det, prev));
@@ -2444,6 +2446,13 @@ static void rollout_env_params(ssa_ukf* h, EnvParams* p, int increment, int gree
 
 static void launch_env_reduce(ssa_ukf* h, const EnvParams& ep, cudaStream_t st) {
   const int N = h->cfg.n_objects;
+  if (ep.m <= 64 && !getenv("SSA_UKF_DET_KERNEL")) {  // determinants inside the reduction
+    EnvParams e2 = ep;
+    e2.det_cur = nullptr;
+    ssa_env_reduce_kernel<true><<<(unsigned)((ep.E + 3) / 4), 128, 0, st>>>(e2);
+    h->launches += 1;
+    return;
+  }
   ssa_det_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(h->P, h->ld, N, h->det_cur, ep.greedy_only ? ep.reset_mask : nullptr, ep.m);
   if (ep.m <= 64) ssa_env_reduce_kernel<true><<<(unsigned)((ep.E + 3) / 4), 128, 0, st>>>(ep);
   else ssa_env_reduce_kernel<false><<<(unsigned)ep.E, 128, 0, st>>>(ep);
@@ -2554,7 +2563,7 @@ __global__ void __launch_bounds__(128) k_env_refresh(const RolloutParams rp, con
     const long obj = (long)e * rp.m + j;
     hx_truth(p, obj, obj, false);
     update_body<false>(p, obj, obj, nullptr, 0);  // p.flags = SSA_STEP_EPILOGUE: obs row, errors, trace
-    const_cast<double*>(ep.det_cur)[obj] = ssa_det6_sym(ep.P + obj, ep.ld);  // (h->det_cur: ssa_det_kernel's output)
+    if (ep.det_cur) const_cast<double*>(ep.det_cur)[obj] = ssa_det6_sym(ep.P + obj, ep.ld);  // (h->det_cur: ssa_det_kernel's output)
   }
   __syncthreads();
   if (ep.m <= 64) {
@@ -2589,6 +2598,7 @@ static int rollout_chain(ssa_ukf* h, cudaStream_t st, int auto_reset, int obs_f3
     EnvParams rep;
     rollout_env_params(h, &rep, 0, 1);
     rep.reset_mask = rep.done;
+    if (rep.m <= 64 && !getenv("SSA_UKF_DET_KERNEL")) rep.det_cur = nullptr;  // determinants inside the reduction
     StepOverride rov{h->ro.dout, h->ro.act_eff, h->ro.table, h->step_idx, 0, h->ro.n_table, rep.done};
     KParams kp;
     rc = step_impl(h, nullptr, SSA_STEP_EPILOGUE, st, nullptr, -1, &rov, &kp, true);
