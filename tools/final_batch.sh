@@ -19,4 +19,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 3 --warmup 3 --no-extra --no-cpu-baseline > $out/${tag}_ncu_bench.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $out/${tag}_launches_c3.csv \
     python bench.py --workload c3 --steps 3 --warmup 3 --no-extra --no-cpu-baseline > $out/${tag}_ncu_c3.log 2>&1
+# the episodic (C3) step's kernels
+ncu --set full --clock-control none --import-source on -k regex:"k_env_begin|k_factor|k_predict_tile|k_refactor|k_update_tile|ssa_det_kernel|ssa_env_reduce_kernel|k_env_refresh|k_obs_to_f32" \
+    -s 54 -c 18 -o $out/${tag}_c3 -f python bench.py --workload c3 --steps 4 --warmup 3 --no-extra --no-cpu-baseline --obs-dtype float32 > $out/${tag}_ncu_c3full.log 2>&1
+ncu -i $out/${tag}_c3.ncu-rep --page raw --csv > $out/${tag}_raw_c3.csv 2>/dev/null
+python tools/ncu_summary.py 40960 $out/${tag}_raw_c3.csv > $out/${tag}_ncu_c3_kernels.json
 echo batch done
