@@ -252,6 +252,15 @@ int ssa_ukf_scores(ssa_ukf* h, void* stream);
 int ssa_orbit_gen_eval(const double* cand, int K, const double* trans_table, int n, double step_s, const double obs_itrs[3],
                        const double T[9], double obs_limit, double min_alt, int first_window, int max_gap, uint8_t* accept,
                        double* elev, double* alt, int device);
+/* HOST (no device): the GCRS -> ITRS rotation table the path takes as its per-step input — trans_matrix[i] of
+ * ssa_tasker_simple_2.py:136-137, which the reference builds through ERFA (envs/transformations.py:143-214) — for the n
+ * UTC instants (year-month-day, seconds_of_day) + i * dt (whole seconds are used, like the reference's datetime fields).
+ * ERFA-free restatement (csrc/ssa_frames.h): exact calendar, leap seconds, Earth rotation angle, TIO locator and polar
+ * motion; CIP X, Y from the IAU 2006/2000A series truncated at 12 mas (5e-8 rad against the SOFA matrix of the
+ * reference's tests.py:107-109).  eop: daily IERS rows [mjd, x", y", UT1-UTC s, dX", dY"] (n_eop of them) or NULL.
+ * out: [n][9] row-major matrices.                                                                                     */
+int ssa_trans_matrix_table(int year, int month, int day, double seconds_of_day, double dt, int n, const double* eop, int n_eop,
+                           double* out);
 /* Catalog mode (C4: one shard of a large catalog per GPU): the shard's reward terms over ALL its objects, left in
  * device memory (SSA_F_CATALOG_STATS, 5 doubles) so that the shards can be combined with one small all_gather:
  * max delta_pos (SS2:329-331), sum of the trinary counts (results.py:431-433) and the object count, the largest

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libssa_ukf.so")
 SOURCES = ["ssa_ukf.cu"]
-HEADERS = ["ssa_math.h", "ssa_orbit.h", "ssa_meas.h", "ssa_ukf_core.h", os.path.join("..", "..", "include", "ssa_ukf.h")]
+HEADERS = ["ssa_math.h", "ssa_orbit.h", "ssa_meas.h", "ssa_ukf_core.h", "ssa_tile.cuh", "ssa_frames.h", "ssa_rng.h", os.path.join("..", "..", "include", "ssa_ukf.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

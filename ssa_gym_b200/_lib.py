@@ -71,6 +71,7 @@ PROTOTYPES = {
     "ssa_ukf_rollout_reset": (_I, [c_void_p, c_void_p]),
     "ssa_ukf_rollout_step": (_I, [c_void_p, _I, c_void_p]),
     "ssa_ukf_rollout_obs_f32": (_I, [c_void_p, c_void_p, c_void_p]),
+    "ssa_trans_matrix_table": (_I, [_I, _I, _I, _D, _D, _I, c_void_p, _I, c_void_p]),
     "ssa_ukf_predict": (_I, [c_void_p, c_void_p]),
     "ssa_ukf_update": (_I, [c_void_p, c_void_p, _I, c_void_p]),
     "ssa_ukf_env_reduce": (_I, [c_void_p, c_void_p, _I, c_void_p]),

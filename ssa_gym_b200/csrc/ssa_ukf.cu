@@ -45,6 +45,7 @@
 
 #include "../../include/ssa_ukf.h"
 #include "ssa_math.h"
+#include "ssa_frames.h"
 #include "ssa_meas.h"
 #include "ssa_orbit.h"
 #include "ssa_rng.h"
@@ -2781,6 +2782,22 @@ int ssa_ukf_diagnostics(ssa_ukf* h, void* stream) {
                                                              h->ld, N);
   h->launches++;
   CK(cudaGetLastError());
+  return SSA_OK;
+}
+
+// HOST: the trans_matrix table of an episode (csrc/ssa_frames.h); no device needed
+int ssa_trans_matrix_table(int year, int month, int day, double seconds_of_day, double dt, int n, const double* eop, int n_eop,
+                           double* out) {
+  if (n < 1 || !out || month < 1 || month > 12 || day < 1 || day > 31 || !(dt == dt) || (eop && n_eop < 2)) return SSA_EINVAL;
+  const long mjd0 = (long)ssa_frames::cal2mjd(year, month, day);
+  for (int i = 0; i < n; ++i) {
+    const double total = seconds_of_day + dt * (double)i;
+    const double days = floor(total / 86400.0);
+    const double sec = floor(total - days * 86400.0);  // whole seconds, like the reference's datetime.hour / minute / second
+    const ssa_frames::M3 m = ssa_frames::gcrs2itrs(mjd0 + (long)days, sec, eop, n_eop);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) out[9 * (size_t)i + 3 * r + c] = m.a[r][c];
+  }
   return SSA_OK;
 }
 

@@ -197,6 +197,24 @@ def gcrs2irts_matrix_approx(t, eop=None):
     return out[0] if single else np.array(out)
 
 
+def gcrs2irts_matrix_native(t_0, dt, n, eop=None):
+    """The table of `gcrs2irts_matrix_approx(time_table(t_0, dt, n), eop)` computed by the library's host-side C++
+    restatement of the same chain (`ssa_trans_matrix_table`, csrc/ssa_frames.h) — what a C / C++ caller of libssa_ukf.so
+    uses; needs no GPU.  `eop`: table from load_eop_c04 / default_eops or None."""
+    import ctypes
+    from . import _lib
+    rows = None
+    if eop:
+        rows = np.ascontiguousarray([[k, *eop[k]] for k in sorted(eop)], dtype=np.float64)
+    out = np.empty((int(n), 3, 3))
+    sec = 3600.0 * t_0.hour + 60.0 * t_0.minute + t_0.second
+    rc = _lib.load().ssa_trans_matrix_table(t_0.year, t_0.month, t_0.day, sec, float(dt), int(n),
+                                            None if rows is None else rows.ctypes.data_as(ctypes.c_void_p),
+                                            0 if rows is None else len(rows), out.ctypes.data_as(ctypes.c_void_p))
+    _lib.check(rc, "ssa_trans_matrix_table")
+    return out
+
+
 def _find_erfa():
     try:
         import erfa  # pyerfa

@@ -77,6 +77,26 @@ def test_trans_matrix_generator_against_sofa_golden():
     assert abs(ang - 7.292115e-5 * 20.0) < 1e-9
 
 
+def test_native_trans_matrix_table_equals_the_python_generator():
+    """ssa_trans_matrix_table (csrc/ssa_frames.h, host C++ inside libssa_ukf.so, no device needed) is the same chain as
+    transformations.gcrs2irts_matrix_approx: equal to rounding (libm vs numpy sin / cos) over episodes that cross
+    midnight, a month boundary and a leap-second date, with and without the EOP table, and within the documented bound
+    of the SOFA cookbook matrix."""
+    eop = T.default_eops()
+    for t0, dt, n, use_eop in ((datetime(2020, 5, 4, 0, 0, 0), 20.0, 480, True), (datetime(2020, 5, 31, 23, 50, 0), 30.0, 100, True),
+                               (datetime(2016, 12, 31, 23, 0, 0), 300.0, 40, False), (datetime(2020, 4, 30, 12, 0, 7), 3600.0, 60, True),
+                               (datetime(2007, 4, 5, 12, 0, 0), 20.0, 3, True)):
+        e = eop if use_eop else None
+        ref = T.gcrs2irts_matrix_approx(T.time_table(t0, dt, n), e)
+        nat = T.gcrs2irts_matrix_native(t0, dt, n, e)
+        assert nat.shape == ref.shape == (n, 3, 3)
+        assert np.max(np.abs(nat - ref)) < 5e-13, (t0, np.max(np.abs(nat - ref)))
+        assert np.allclose(nat @ np.transpose(nat, (0, 2, 1)), np.eye(3), atol=1e-14)
+    mjd = int(T.cal2jd(2007, 4, 5)[1])
+    sofa = {mjd: (0.0349282, 0.4833163, -0.072073685, 0.1750e-3, -0.2259e-3), mjd + 1: (0.0349282, 0.4833163, -0.072073685, 0.1750e-3, -0.2259e-3)}
+    assert np.max(np.abs(T.gcrs2irts_matrix_native(datetime(2007, 4, 5, 12, 0, 0), 20.0, 1, sofa)[0] - H.CEL2TER06AXY)) < 1e-7
+
+
 def test_eop_table_parsing_interpolation_and_default():
     """The IERS EOP 14 C04 rows the reference reads (transformations.py:19-31; SURVEY 8c quotes MJD 58973): parsed from the
     shipped excerpt in the original file format, interpolated linearly between the daily rows like the reference
