@@ -256,7 +256,7 @@ int ssa_orbit_gen_eval(const double* cand, int K, const double* trans_table, int
  * ssa_tasker_simple_2.py:136-137, which the reference builds through ERFA (envs/transformations.py:143-214) — for the n
  * UTC instants (year-month-day, seconds_of_day) + i * dt (whole seconds are used, like the reference's datetime fields).
  * ERFA-free restatement (csrc/ssa_frames.h): exact calendar, leap seconds, Earth rotation angle, TIO locator and polar
- * motion; CIP X, Y from the IAU 2006/2000A series truncated at 12 mas (5e-8 rad against the SOFA matrix of the
+ * motion; CIP X, Y from the IAU 2006/2000A series truncated at 1 mas (7.5e-9 rad against the SOFA matrix of the
  * reference's tests.py:107-109).  eop: daily IERS rows [mjd, x", y", UT1-UTC s, dX", dY"] (n_eop of them) or NULL.
  * out: [n][9] row-major matrices.                                                                                     */
 int ssa_trans_matrix_table(int year, int month, int day, double seconds_of_day, double dt, int n, const double* eop, int n_eop,

@@ -5,8 +5,9 @@
 // part of this image; this is the same chain restated in C++ so that a C / C++ caller of libssa_ukf.so can produce the
 // per-step input of the measurement model itself: exact calendar / leap-second / Earth-rotation-angle / TIO-locator /
 // polar-motion arithmetic, CIP X, Y from the truncated IAU 2006/2000A series (IERS Conventions 2010, eq. 5.16 and the
-// leading rows of Tables 5.2a / 5.2b: polynomial part + every periodic term above 12 mas).  Accuracy: 5e-8 rad against the
-// SOFA matrix quoted in the reference's tests.py:107-109 (2 m at GEO) — an INPUT generator, flagged approximate; parity of
+// leading rows of Tables 5.2a / 5.2b: polynomial part + every periodic term above 12 mas; the lunisolar terms between 1 and
+// 9 mas from their nutation amplitudes).  Accuracy: 7.5e-9 rad against the SOFA matrix quoted in the reference's
+// tests.py:107-109 (0.3 m at GEO) — an INPUT generator, flagged approximate; parity of
 // the path is defined for identical matrices.  ssa_gym_b200/transformations.py holds the same arithmetic in Python
 // (tests/test_host_logic.py compares the two).
 #pragma once
@@ -81,6 +82,19 @@ inline void xys(double t, double* X, double* Y, double* s) {
   double y = -0.006951 - 0.025896 * t - 22.4072747 * t * t + 0.00190059 * t * t * t + 9.205236 * cos(om) + 0.573033 * cos(a2) +
              0.097847 * cos(a3) - 0.089618 * cos(2 * om) + 0.022438 * cos(lp + a2) + 0.020070 * cos(2 * F + om) +
              0.012902 * cos(l + a3) + 0.153042 * t * sin(om);
+  // the next lunisolar terms, 1 - 9 mas: X_i = sin(eps0) dpsi_i sin(arg_i), Y_i = deps_i cos(arg_i) from the nutation
+  // amplitudes of the classical series [0.1 mas] (within 1 % of the IAU 2000A X,Y coefficients at this level)
+  static const double minor[14][7] = {{0, -1, 2, -2, 2, 217.0, -95.0}, {0, 0, 2, -2, 1, 129.0, -70.0}, {1, 0, 0, -2, 0, -158.0, -1.0},
+                                      {-1, 0, 2, 0, 2, 123.0, -53.0}, {0, 0, 0, 2, 0, 63.0, -2.0},     {1, 0, 0, 0, 1, 63.0, -33.0},
+                                      {-1, 0, 0, 0, 1, -58.0, 32.0},  {-1, 0, 2, 2, 2, -59.0, 26.0},   {1, 0, 2, 0, 1, -51.0, 27.0},
+                                      {0, 0, 2, 2, 2, -38.0, 16.0},   {2, 0, 0, 0, 0, 29.0, -1.0},     {1, 0, 2, -2, 2, 29.0, -12.0},
+                                      {2, 0, 2, 0, 2, -31.0, 13.0},   {0, 0, 2, 0, 0, 26.0, -1.0}};
+  const double sin_eps0 = 0.397777156;  // sin of the J2000 obliquity
+  for (const auto& m : minor) {
+    const double arg = m[0] * l + m[1] * lp + m[2] * F + m[3] * D + m[4] * om;
+    x = x + (1e-4 * sin_eps0 * m[5]) * sin(arg);
+    y = y + (1e-4 * m[6]) * cos(arg);
+  }
   x *= kDAS2R;
   y *= kDAS2R;
   *X = x;

@@ -10,8 +10,8 @@ reference computes the table once in __init__: ssa_tasker_simple_2.py:136-137 ->
     reference's call sequence exactly (same ERFA routines, same EOP interpolation);
   * otherwise `gcrs2irts_matrix_approx` builds the matrix from the exact Earth-rotation angle (ERA00),
     TIO locator and polar motion, and a truncated series for the CIP X,Y (polynomial part plus every
-    periodic term above 12 mas).  It is accurate to ~0.01 arcsec (5e-8 rad against the SOFA cookbook matrix
-    quoted in the reference's tests.py:107-109; 2 m at GEO) and is flagged "approximate": the measurement model's
+    periodic term above 1 mas).  It is accurate to ~2 mas (7.5e-9 rad against the SOFA cookbook matrix
+    quoted in the reference's tests.py:107-109; 0.3 m at GEO) and is flagged "approximate": the measurement model's
     parity is defined for identical matrices, the matrix generator is an input, not graded arithmetic.
 
 Geometry (`lla2ecef`, `trans_uvw_ecef`) follows transformations.py:216-235 and :341-343 with the same
@@ -143,10 +143,20 @@ def _rz(a):
     return np.array([[c, s, 0], [-s, c, 0], [0, 0, 1]])
 
 
+_SIN_EPS0 = 0.397777156  # sin of the J2000 obliquity 84381.406"
+# multipliers of (l, l', F, D, Omega), nutation in longitude and in obliquity [0.1 mas]
+_XY_MINOR = (((0, -1, 2, -2, 2), 217.0, -95.0), ((0, 0, 2, -2, 1), 129.0, -70.0), ((1, 0, 0, -2, 0), -158.0, -1.0),
+             ((-1, 0, 2, 0, 2), 123.0, -53.0), ((0, 0, 0, 2, 0), 63.0, -2.0), ((1, 0, 0, 0, 1), 63.0, -33.0),
+             ((-1, 0, 0, 0, 1), -58.0, 32.0), ((-1, 0, 2, 2, 2), -59.0, 26.0), ((1, 0, 2, 0, 1), -51.0, 27.0),
+             ((0, 0, 2, 2, 2), -38.0, 16.0), ((2, 0, 0, 0, 0), 29.0, -1.0), ((1, 0, 2, -2, 2), 29.0, -12.0),
+             ((2, 0, 2, 0, 2), -31.0, 13.0), ((0, 0, 2, 0, 0), 26.0, -1.0))
+
+
 def xys_approx(t):
     """CIP X, Y and CIO locator s [rad]; t = TT Julian centuries since J2000.  Truncated IAU 2006/2000A series (IERS
     Conventions 2010, eq. 5.16 and the leading rows of Tables 5.2a/5.2b): polynomial part, the nine largest periodic
-    terms of X and seven of Y (every term above 12 mas) and the leading t-proportional term of each."""
+    terms of X and seven of Y (every term above 12 mas), the leading t-proportional term of each, and the fourteen
+    lunisolar terms between 1 and 9 mas formed from their nutation amplitudes (_XY_MINOR)."""
     om = (450160.398036 - 6962890.5431 * t) * DAS2R              # mean longitude of the Moon's node
     F = (335779.526232 + 1739527262.8478 * t) * DAS2R            # L - Omega
     D = (1072260.70369 + 1602961601.2090 * t) * DAS2R            # mean elongation of the Moon
@@ -161,6 +171,13 @@ def xys_approx(t):
     Y = (-0.006951 - 0.025896 * t - 22.4072747 * t ** 2 + 0.00190059 * t ** 3
          + 9.205236 * cos(om) + 0.573033 * cos(a2) + 0.097847 * cos(a3) - 0.089618 * cos(2 * om)
          + 0.022438 * cos(lp + a2) + 0.020070 * cos(2 * F + om) + 0.012902 * cos(l + a3) + 0.153042 * t * sin(om))
+    # the next lunisolar terms, 1 - 9 mas: X_i = sin(eps0) dpsi_i sin(arg_i), Y_i = deps_i cos(arg_i) with the nutation
+    # amplitudes of the classical series (units 0.1 mas; at this level they agree with the IAU 2000A X,Y coefficients to 1 %,
+    # as the twelve tabulated terms above do: e.g. 0.39778 x -1.3187" = -0.52455" for -0.523908")
+    for (kl, klp, kF, kD, kom), dpsi, deps in _XY_MINOR:
+        arg = kl * l + klp * lp + kF * F + kD * D + kom * om
+        X = X + (1e-4 * _SIN_EPS0 * dpsi) * sin(arg)
+        Y = Y + (1e-4 * deps) * cos(arg)
     X, Y = X * DAS2R, Y * DAS2R
     s = -X * Y / 2 + (94e-6 + 3808.65e-6 * t - 2640.73e-6 * sin(om)) * DAS2R
     return X, Y, s
