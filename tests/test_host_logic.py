@@ -97,6 +97,21 @@ def test_native_trans_matrix_table_equals_the_python_generator():
     assert np.max(np.abs(T.gcrs2irts_matrix_native(datetime(2007, 4, 5, 12, 0, 0), 20.0, 1, sofa)[0] - H.CEL2TER06AXY)) < 1.5e-8
 
 
+def test_native_trans_matrix_table_rejects_bad_arguments():
+    import ctypes
+    from ssa_gym_b200 import _lib
+    L = _lib.load()
+    out = np.zeros(9)
+    po = out.ctypes.data_as(ctypes.c_void_p)
+    assert L.ssa_trans_matrix_table(2020, 5, 4, 0.0, 20.0, 1, None, 0, po) == 0
+    assert L.ssa_trans_matrix_table(2020, 13, 4, 0.0, 20.0, 1, None, 0, po) == _lib.SSA_EINVAL
+    assert L.ssa_trans_matrix_table(2020, 5, 4, 0.0, 20.0, 0, None, 0, po) == _lib.SSA_EINVAL
+    assert L.ssa_trans_matrix_table(2020, 5, 4, 0.0, 20.0, 1, None, 0, None) == _lib.SSA_EINVAL
+    assert L.ssa_trans_matrix_table(2020, 5, 4, 0.0, float("nan"), 1, None, 0, po) == _lib.SSA_EINVAL
+    one_row = np.array([[58973.0, 0.08, 0.44, -0.24, 0.0, 0.0]])
+    assert L.ssa_trans_matrix_table(2020, 5, 4, 0.0, 20.0, 1, one_row.ctypes.data_as(ctypes.c_void_p), 1, po) == _lib.SSA_EINVAL
+
+
 def test_eop_table_parsing_interpolation_and_default():
     """The IERS EOP 14 C04 rows the reference reads (transformations.py:19-31; SURVEY 8c quotes MJD 58973): parsed from the
     shipped excerpt in the original file format, interpolated linearly between the daily rows like the reference
