@@ -67,3 +67,29 @@ def test_unknown_operator_is_rejected():
     with pytest.raises(NotImplementedError):
         dynamics.resolve_operator("fx", lambda x, dt: x)
     assert dynamics.resolve_operator("hx", dynamics.hx_aer_erfa) == "hx_aer_erfa"
+
+
+def test_plain_c_program_links_against_the_header_and_library(tmp_path):
+    """The boundary is a C ABI: include/ssa_ukf.h is valid C99 and a plain-C caller links against libssa_ukf.so, reads the
+    ABI version, asks for the device count and produces the path's per-step host input (the trans_matrix table)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "caller.c"
+    src.write_text('#include <stdio.h>\n#include "ssa_ukf.h"\n'
+                   'int main(void) {\n  double out[18];\n'
+                   '  int rc = ssa_trans_matrix_table(2020, 5, 4, 0.0, 20.0, 2, NULL, 0, out);\n'
+                   '  printf("%d %d %.17g %.17g\\n", rc, ssa_ukf_abi_version(), out[0], out[9]);\n'
+                   '  return ssa_ukf_device_count() < 0;\n}\n')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_build.LIB)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(H.ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-lssa_ukf", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == "0" and out[1] == "1"
+    from datetime import datetime
+    from ssa_gym_b200 import transformations as T
+    ref = T.gcrs2irts_matrix_native(datetime(2020, 5, 4), 20.0, 2)
+    assert float(out[2]) == ref[0, 0, 0] and float(out[3]) == ref[1, 0, 0]
